@@ -1,0 +1,194 @@
+/*
+ * ou_b200.h -- C ABI of libou_b200.so: hand-written sm_100a kernels for the enhance() hot path
+ * of line/open-universe (UNIVERSE / UNIVERSE++ diffusion speech enhancement).
+ *
+ * The reference has NO native / FFI layer: its device work is eager ATen
+ * and cuDNN calls made from Python.  This header is therefore the boundary a maintainer would
+ * bind (ctypes stub in INTEGRATION.md); every entry point names the reference code it replaces
+ * (paths relative to /root/reference/open_universe/).
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative OU_ERR_* code otherwise; it never throws,
+ *     never synchronises the device and never allocates: the caller owns all buffers and passes
+ *     the CUDA stream (a cudaStream_t cast to void*; NULL = legacy default stream);
+ *   - all pointers are DEVICE pointers unless stated otherwise;
+ *   - ou_last_error() returns a thread-local human-readable message for the last failure.
+ *
+ * Activation layout ("blocked"): bf16 [B][C/8][T][8] -- channel c of time step t of clip b lives at
+ *   ((b * (C/8) + c/8) * T + t) * 8 + c%8.   C must be a multiple of 8.
+ * Signals are fp32 [B][T]; GRU pre-activations fp32 time-major [B][T][N].
+ */
+#ifndef OU_B200_H
+#define OU_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OU_ABI_VERSION 1
+
+enum {
+  OU_OK = 0,
+  OU_ERR_INVALID = -1,   /* bad argument (shape / alignment / null pointer)          */
+  OU_ERR_CUDA = -2,      /* a CUDA runtime call failed (launch, attribute, ...)      */
+  OU_ERR_UNSUPPORTED = -3 /* valid request this build has no kernel for              */
+};
+
+int ou_abi_version(void);
+/* Copies the last error message of the calling thread into buf (NUL-terminated). */
+int ou_last_error(char* buf, size_t n);
+/* Number of kernels launched by this library in the calling process since load (bench.py's
+ * gpu_launches claim). */
+int64_t ou_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused implicit-GEMM Conv1d.   Replaces, in ONE launch:
+ *   PReLU_Conv.forward                 networks/universe/blocks.py:205-227
+ *     (right-pad, PReLU, binomial low-pass :119-130 folded into the weights, Conv1d /
+ *      ConvTranspose1d, separate bias)
+ *   the element-wise glue of ConvBlock.forward   blocks.py:355-412
+ *     (residual / conditioning adds with 1/sqrt2, FiLM :53-59, the next layer's PReLU)
+ *   LinearProj / signal_cond_proj 1x1 convs       score.py:165-170,189-194
+ *   the GRU input projection x @ W_ih^T + b_ih    score.py:83-89 (torch.nn.GRU)
+ *   the conditioner's st_convs                    condition.py:33-65
+ *
+ *   acc[j][n] = sum_{q<taps} sum_{c'<s*cin} W[n][q][c'] * PReLU_in(X)[ci][(j+tap_off+q)*s + r],
+ *               c' = r*cin + ci, X zero outside [0, t_in)
+ *   co = n % cout, p = n / cout, t = j*up + p   (t < t_out, j < rows)
+ *   y = ((acc + bias[n] + add1[co][t]) * scale1 + add2[co][t]) * scale2
+ *   y = gamma[b][co] * y + beta[b][co]                    (if gamma != NULL)
+ *   y = PReLU(PReLU(y, prelu_out), prelu_out2)            (each if enabled)
+ *   out (blocked bf16 [B][cout/8][t_out][8])  or  out_f32_tm (fp32 [B][rows][n], no add/film/prelu)
+ * ------------------------------------------------------------------------------------------ */
+typedef struct ou_conv_params {
+  const void* x;          /* blocked bf16 [B][cin/8][t_in][8]                                  */
+  const void* w;          /* packed bf16 [taps][kpad/8][npad][8]; element (q, c', n_) = W[n_][q][c'],
+                             zero padded; kpad % 32 == 0, npad % 32 == 0                        */
+  const float* bias;      /* fp32 [n] or NULL                                                   */
+  const void* add1;       /* blocked bf16 [B][cout/8][t_out][8] or NULL                         */
+  const void* add2;       /* blocked bf16 [B][cout/8][t_out][8] or NULL                         */
+  const float* gamma;     /* fp32, element (b, co) at gamma[b*film_bstride + co], or NULL       */
+  const float* beta;      /* fp32, same indexing                                                */
+  void* out;              /* blocked bf16 [B][cout/8][t_out][8] or NULL                         */
+  float* out_f32_tm;      /* fp32 [B][rows][n] or NULL (exactly one of out / out_f32_tm)        */
+  int32_t batch, cin, t_in;
+  int32_t s, taps, tap_off;
+  int32_t n, cout, up;
+  int32_t kpad, npad;     /* padded K (= s*cin rounded up to 32) and N of the packed weights    */
+  int32_t rows, t_out;
+  int32_t film_bstride;
+  int32_t has_prelu_in, has_prelu_out, has_prelu_out2;
+  float prelu_in, prelu_out, prelu_out2;
+  float scale1, scale2;
+} ou_conv_params;
+
+int ou_conv1d(const ou_conv_params* p, void* stream);
+
+/* Reference-quality fp32 CUDA-core version of the same contract (one thread per output): used by
+ * the GPU tests to cross-check the tensor-core kernel on device.  Same arguments. */
+int ou_conv1d_naive(const ou_conv_params* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * First layer: k-tap 'same' Conv1d of the 1-channel signal, with the EDM input scale folded in.
+ * Replaces ScoreNetwork.input_conv (score.py:239-241,285) + `w_in * x` of _edm_score_wrapper
+ * (universe.py:197-203), and ConditionerNetwork.input_conv (condition.py:290-295,361).
+ *   out[co][t] = bias[co] + sum_k w[co][k] * in_scale[b] * x[b][t + k - k/2]
+ * x fp32 [B][t]; w fp32 [cout][k]; in_scale fp32 [B] or NULL; out blocked bf16 [B][cout/8][t][8].
+ * ------------------------------------------------------------------------------------------ */
+int ou_input_conv(const float* x, const float* w, const float* bias, const float* in_scale,
+                  void* out, int batch, int t, int cout, int k, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Last layer fused with the sampler update.  Replaces ScoreNetwork.output_conv + final pad
+ * (score.py:288,294), the EDM mix `w_skip*x + w_out*net`, `score = (est-x)/sigma^2`
+ * (universe.py:204-206) and the reverse-SDE update (universe.py:337-339, 342-343):
+ *   net[b][t]  = bias + sum_{ci,k} w[ci][k] * src[ci][t + k - k/2]      (t < t_src, else 0)
+ *   xout[b][t] = ca[b]*x[b][t] + cb[b]*net[b][t] + cc[b]*noise[b][t]    (t < t_sig)
+ * src blocked bf16 [B][cin/8][t_src][8] (already activated by the producer); w fp32 [cin][k];
+ * coef fp32 [B][3] = (ca, cb, cc) or NULL; noise fp32 [B][t_sig] or NULL; net_out fp32 [B][t_sig]
+ * or NULL; x / xout fp32 [B][t_sig] (may alias) or NULL when coef is NULL.
+ * ------------------------------------------------------------------------------------------ */
+int ou_output_sde(const void* src, const float* w, float bias, const float* coef, const float* x,
+                  const float* noise, float* xout, float* net_out, int batch, int cin, int k,
+                  int t_src, int t_sig, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Bidirectional GRU recurrence (one layer).  Replaces torch.nn.GRU at the score bottleneck
+ * (score.py:82-89,116-117; every step) and in the conditioner (condition.py:173-179,213).
+ *   gx    fp32 [B][T][6H]: x W_ih^T + b_ih, forward (r,z,n) then backward (r,z,n)
+ *   w_hh  fp32 [2][3H][H],  b_hh fp32 [2][3H]
+ *   r = s(gx_r + W_hr h + b_hr); z = s(gx_z + W_hz h + b_hz); n = tanh(gx_n + r*(W_hn h + b_hn));
+ *   h' = (1-z)*n + z*h; h0 = 0; backward direction runs t = T-1..0
+ *   out blocked bf16 [B][2H/8][T][8] = ((h_fwd | h_bwd) + add) * scale   (add blocked or NULL)
+ * ------------------------------------------------------------------------------------------ */
+int ou_gru_bidir(const float* gx, const float* w_hh, const float* b_hh, const void* add, float scale,
+                 void* out, int batch, int t, int hidden, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Mel front-end.  Replaces MelAdapter.compute_mel_spec (condition.py:92-108): zero pad, frame,
+ * periodic Hann, |rFFT|^2 (torchaudio MelSpectrogram power=2, center=False), mel filterbank and
+ * the global energy normalisation.
+ *   ou_mel_power:    x fp32 [B][t] -> mel fp32 [B][n_mels][frames] (un-normalised),
+ *                    energy fp32 [B][frames] = sum_mel mel^2.  frame m = samples
+ *                    [hop*m - pad_left, hop*m - pad_left + n_fft), zero outside [0, t).
+ *                    window fp32 [n_fft]; fb fp32 [n_fft/2+1][n_mels];
+ *                    twiddle fp32 [n_fft][2] = (cos, sin)(2*pi*i/n_fft).
+ *   ou_mel_finalize: per clip scale = 1 / max(sqrt(mean_frames energy), 1e-5); writes the
+ *                    normalised mel as fp32 [B][n_mels][frames] (in place allowed, or NULL) and
+ *                    blocked bf16 [B][n_mels/8][frames][8] (or NULL).
+ * ------------------------------------------------------------------------------------------ */
+int ou_mel_power(const float* x, const float* window, const float* fb, const float* twiddle,
+                 float* mel, float* energy, int batch, int t, int n_fft, int hop, int n_mels,
+                 int pad_left, int frames, void* stream);
+int ou_mel_finalize(const float* mel, const float* energy, float* mel_norm, void* mel_blocked,
+                    int batch, int n_mels, int frames, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * sigma embedding + small dense layers (step-invariant: computed for all steps before the loop).
+ * Replaces SimpleTimeEmbedding.forward / SigmaBlock.forward (sigma_block.py:73-78, 50-57) and the
+ * FiLM projections Linear(g) (score.py:58-66,108,159-164,207).
+ *   ou_sigma_embed_simple: f = 0.5*sigmoid(w*ls + b); out[r][k] = sin(2*pi*f*k), out[r][half+k] =
+ *                          cos(2*pi*f*k), k < half.           log10_sigma fp32 [rows], out [rows][2*half]
+ *   ou_sigma_embed_rff:    out[r][k] = sin(2*pi*freq[k]*ls), out[r][n_rff+k] = cos(...)
+ *   ou_linear_f32:         out[r][c] = act(bias[c] + sum_k w[c][k] * in[r][k]); act = PReLU(slope)
+ *                          if has_prelu.   in [rows][k], w [n][k], out [rows][n] (ld_out >= n)
+ * ------------------------------------------------------------------------------------------ */
+int ou_sigma_embed_simple(const float* log10_sigma, float weight, float bias, float* out, int rows,
+                          int half, void* stream);
+int ou_sigma_embed_rff(const float* log10_sigma, const float* freq, float* out, int rows, int n_rff,
+                       void* stream);
+int ou_linear_f32(const float* in, const float* w, const float* bias, float* out, int rows, int k,
+                  int n, int ld_out, int has_prelu, float slope, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Signal-level pre/post processing of Universe.enhance (universe.py:251-274, 346-357).
+ *   ou_pad_normalize: centred zero pad (universe.py:219-223) + utils.normalize_batch with norm=2
+ *                     (utils/norm.py:47-87): mean / unbiased std over the PADDED clip.
+ *                     mix fp32 [B][t] -> out fp32 [B][t_pad], out[b][pad_left + i] = (mix - mean)*gain,
+ *                     padding = (0 - mean)*gain; gain = level / max(std, 1e-5).
+ *                     stats fp32 [B][2] receives (mean, 1/gain).  One CTA per clip.
+ *   ou_unpad_limit:   unpad, right-pad to t, optional keep_rms rescale to mix_rms[b], peak limiter
+ *                     x/max|x| where max|x| > 1 (universe.py:349-357).  x fp32 [B][t_pad] ->
+ *                     out fp32 [B][t].  mix_rms fp32 [B] or NULL.
+ * ------------------------------------------------------------------------------------------ */
+int ou_pad_normalize(const float* mix, float* out, float* stats, int batch, int t, int t_pad,
+                     int pad_left, float level, void* stream);
+int ou_unpad_limit(const float* x, const float* mix_rms, float* out, int batch, int t_pad,
+                   int pad_left, int t_valid, int t, void* stream);
+
+/* Layout converters between the reference's (B, C, T) fp32 tensors and the blocked bf16 layout
+ * (module-level APIs: ScoreNetwork.forward's `cond` list, ConditionerNetwork's outputs). */
+int ou_pack_blocked(const float* src, void* dst, int batch, int channels, int t, void* stream);
+int ou_unpack_blocked(const void* src, float* dst, int batch, int channels, int t, void* stream);
+
+/* FiLM on (B, C, T) fp32 tensors: out = y[:, :C] * x + y[:, C:]  (blocks.py:53-59, standalone). */
+int ou_film_f32(const float* x, const float* y, float* out, int batch, int channels, int t,
+                void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OU_B200_H */

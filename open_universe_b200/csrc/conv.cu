@@ -1,0 +1,348 @@
+// Fused implicit-GEMM Conv1d over the channel-blocked bf16 layout (see include/ou_b200.h).
+//
+//   ou_conv1d        warp-level tensor-core path (mma.sync m16n8k16 bf16, fp32 accumulate),
+//                    cp.async multi-stage smem pipeline, fused prologue (PReLU on the A tile) and
+//                    epilogue (bias, two adds, FiLM, two PReLUs, depth-to-space scatter).
+//   ou_conv1d_naive  one-thread-per-output fp32 reference of the same contract (tests only).
+//
+// GEMM view: M = output rows j (128 per CTA), N = up*cout (BN per CTA), K = taps * s*cin.
+// smem tiles are K-major "8-channel x 16-byte row" core matrices: A [chunk][row][8], B [tap][chunk][n][8]
+// -- a tap shift is a 16-byte row offset, so one A tile (with taps-1 halo rows) serves all taps.
+#include "common.cuh"
+
+namespace ou {
+
+constexpr int BM = 128;       // GEMM rows per CTA
+constexpr int KB = 32;        // K (channels') per pipeline stage
+constexpr int KCH = KB / 8;   // 16-byte channel chunks per stage
+constexpr int NTHREADS = 256;
+
+struct ConvArgs {
+  ou_conv_params p;
+  int cin_chunks;   // cin / 8
+  int k_chunks;     // s * cin / 8 (valid chunks; beyond -> zero)
+  int n_kblocks;    // kpad / KB
+  int arows;        // BM + taps - 1
+};
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
+  uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+  int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* smem) {
+  uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(s));
+}
+__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0,
+                                         uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, "
+      "{%8,%9}, {%0,%1,%2,%3};\n"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// Epilogue for two adjacent GEMM columns (n, n+1), n even: shared by both kernels.
+__device__ __forceinline__ void epilogue_pair(const ou_conv_params& p, int b, int j, int n, float v0,
+                                              float v1) {
+  if (j >= p.rows || n >= p.n) return;
+  if (p.bias) {
+    v0 += p.bias[n];
+    v1 += p.bias[n + 1];
+  }
+  if (p.out_f32_tm) {
+    float2* dst = reinterpret_cast<float2*>(p.out_f32_tm + ((size_t)b * p.rows + j) * p.n + n);
+    *dst = make_float2(v0, v1);
+    return;
+  }
+  const int ph = n / p.cout;
+  const int co = n - ph * p.cout;
+  const int t = j * p.up + ph;
+  if (t >= p.t_out) return;
+  const size_t off = (((size_t)b * (p.cout >> 3) + (co >> 3)) * p.t_out + t) * 8 + (co & 7);
+  if (p.add1) {
+    float2 a = bf2_to_f2(*reinterpret_cast<const uint32_t*>((const __nv_bfloat16*)p.add1 + off));
+    v0 += a.x;
+    v1 += a.y;
+  }
+  v0 *= p.scale1;
+  v1 *= p.scale1;
+  if (p.add2) {
+    float2 a = bf2_to_f2(*reinterpret_cast<const uint32_t*>((const __nv_bfloat16*)p.add2 + off));
+    v0 += a.x;
+    v1 += a.y;
+  }
+  v0 *= p.scale2;
+  v1 *= p.scale2;
+  if (p.gamma) {
+    const float* g = p.gamma + (size_t)b * p.film_bstride + co;
+    const float* be = p.beta + (size_t)b * p.film_bstride + co;
+    v0 = g[0] * v0 + be[0];
+    v1 = g[1] * v1 + be[1];
+  }
+  if (p.has_prelu_out) {
+    v0 = prelu_f(v0, p.prelu_out);
+    v1 = prelu_f(v1, p.prelu_out);
+  }
+  if (p.has_prelu_out2) {
+    v0 = prelu_f(v0, p.prelu_out2);
+    v1 = prelu_f(v1, p.prelu_out2);
+  }
+  *reinterpret_cast<uint32_t*>((__nv_bfloat16*)p.out + off) = f2_to_bf2(v0, v1);
+}
+
+// ------------------------------------------------------------------------------------------------
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(NTHREADS) conv1d_mma_kernel(const ConvArgs a) {
+  constexpr int WARPS_N = (BN >= 64) ? 2 : 1;
+  constexpr int WARPS_M = 8 / WARPS_N;
+  constexpr int WM = BM / WARPS_M;   // rows per warp: 32 or 16
+  constexpr int WN = BN / WARPS_N;   // cols per warp: 64, 32 or 32
+  constexpr int MT = WM / 16;
+  constexpr int NT = WN / 8;
+  static_assert(NT % 2 == 0, "B fragments are loaded for two n-tiles at a time");
+
+  extern __shared__ __align__(128) uint8_t smem[];
+  const ou_conv_params& p = a.p;
+  const int taps = p.taps;
+  const int arows = a.arows;
+  const int a_stage_bytes = KCH * arows * 16;
+  const int b_stage_bytes = taps * KCH * BN * 16;
+  uint8_t* smA = smem;
+  uint8_t* smB = smem + STAGES * a_stage_bytes;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int wm0 = (warp / WARPS_N) * WM;
+  const int wn0 = (warp % WARPS_N) * WN;
+  const int m0 = blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  const int b = blockIdx.z;
+
+  const __nv_bfloat16* xg = (const __nv_bfloat16*)p.x + (size_t)b * a.cin_chunks * p.t_in * 8;
+  const __nv_bfloat16* wg = (const __nv_bfloat16*)p.w;
+
+  auto load_stage = [&](int kb, int stage) {
+    uint8_t* As = smA + stage * a_stage_bytes;
+    uint8_t* Bs = smB + stage * b_stage_bytes;
+    // A: KCH chunks x arows rows of 16 B; row rr <-> GEMM row j = m0 + rr + tap_off
+    for (int i = tid; i < KCH * arows; i += NTHREADS) {
+      const int c = i / arows, rr = i - c * arows;
+      const int cg = kb * KCH + c;
+      bool valid = cg < a.k_chunks;
+      int r = 0, cic = 0;
+      if (valid) {
+        r = cg / a.cin_chunks;
+        cic = cg - r * a.cin_chunks;
+      }
+      const int j = m0 + rr + p.tap_off;
+      const long t = (long)j * p.s + r;
+      valid = valid && j >= 0 && t < p.t_in;
+      const __nv_bfloat16* src = valid ? xg + ((size_t)cic * p.t_in + t) * 8 : xg;
+      cp_async16(As + (size_t)i * 16, src, valid);
+    }
+    // B: taps x KCH chunks x BN columns of 16 B (always in-bounds: weights are zero padded)
+    for (int i = tid; i < taps * KCH * BN; i += NTHREADS) {
+      const int n = i % BN;
+      const int qc = i / BN;
+      const int c = qc % KCH, q = qc / KCH;
+      const size_t src = (((size_t)q * (p.kpad >> 3) + kb * KCH + c) * p.npad + n0 + n) * 8;
+      cp_async16(Bs + (size_t)i * 16, wg + src, true);
+    }
+  };
+
+  float acc[MT][NT][4];
+#pragma unroll
+  for (int i = 0; i < MT; i++)
+#pragma unroll
+    for (int jn = 0; jn < NT; jn++)
+#pragma unroll
+      for (int k = 0; k < 4; k++) acc[i][jn][k] = 0.f;
+
+  const int nkb = a.n_kblocks;
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; s++) {
+    if (s < nkb) load_stage(s, s);
+    cp_async_commit();
+  }
+
+  // ldmatrix lane roles
+  const int l8 = lane & 7, lq = lane >> 3;
+  const int a_row = (lq & 1) * 8 + l8;   // row within the 16-row fragment
+  const int a_chk = lq >> 1;             // 0/1: which 8-channel half of the k16 step
+  const int b_col = (lq >> 1) * 8 + l8;  // column within the 16-column pair of n-tiles
+  const int b_chk = lq & 1;
+
+  for (int kb = 0; kb < nkb; kb++) {
+    const int stage = kb % STAGES;
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    {
+      const int nk = kb + STAGES - 1;
+      if (nk < nkb) load_stage(nk, nk % STAGES);
+      cp_async_commit();
+    }
+    uint8_t* As = smA + stage * a_stage_bytes;
+    const uint8_t* Bs = smB + stage * b_stage_bytes;
+    if (p.has_prelu_in) {
+      const float slope = p.prelu_in;
+      for (int i = tid; i < KCH * arows; i += NTHREADS) {
+        uint4 v = *reinterpret_cast<uint4*>(As + (size_t)i * 16);
+        uint32_t* w = reinterpret_cast<uint32_t*>(&v);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          float2 f = bf2_to_f2(w[k]);
+          w[k] = f2_to_bf2(prelu_f(f.x, slope), prelu_f(f.y, slope));
+        }
+        *reinterpret_cast<uint4*>(As + (size_t)i * 16) = v;
+      }
+      __syncthreads();
+    }
+    for (int q = 0; q < taps; q++) {
+#pragma unroll
+      for (int kk = 0; kk < KB / 16; kk++) {
+        uint32_t af[MT][4];
+#pragma unroll
+        for (int mt = 0; mt < MT; mt++) {
+          const uint8_t* src =
+              As + ((size_t)(kk * 2 + a_chk) * arows + wm0 + mt * 16 + a_row + q) * 16;
+          ldmatrix_x4(af[mt], src);
+        }
+#pragma unroll
+        for (int np = 0; np < NT / 2; np++) {
+          uint32_t bf[4];
+          const uint8_t* src =
+              Bs + ((size_t)(q * KCH + kk * 2 + b_chk) * BN + wn0 + np * 16 + b_col) * 16;
+          ldmatrix_x4(bf, src);
+#pragma unroll
+          for (int mt = 0; mt < MT; mt++) {
+            mma_bf16(acc[mt][np * 2], af[mt], bf[0], bf[1]);
+            mma_bf16(acc[mt][np * 2 + 1], af[mt], bf[2], bf[3]);
+          }
+        }
+      }
+    }
+  }
+  cp_async_wait<0>();
+
+  const int g = lane >> 2, tq = lane & 3;
+#pragma unroll
+  for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+    for (int nt = 0; nt < NT; nt++) {
+      const int j = m0 + wm0 + mt * 16 + g;
+      const int n = n0 + wn0 + nt * 8 + tq * 2;
+      epilogue_pair(p, b, j, n, acc[mt][nt][0], acc[mt][nt][1]);
+      epilogue_pair(p, b, j + 8, n, acc[mt][nt][2], acc[mt][nt][3]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void conv1d_naive_kernel(const ConvArgs a) {
+  const ou_conv_params& p = a.p;
+  const int half_n = p.n >> 1;
+  const long total = (long)p.batch * p.rows * half_n;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long)gridDim.x * blockDim.x) {
+    const int np = idx % half_n;
+    const long rest = idx / half_n;
+    const int j = rest % p.rows;
+    const int b = rest / p.rows;
+    const int n = np * 2;
+    const __nv_bfloat16* xg = (const __nv_bfloat16*)p.x + (size_t)b * a.cin_chunks * p.t_in * 8;
+    const __nv_bfloat16* wg = (const __nv_bfloat16*)p.w;
+    float v0 = 0.f, v1 = 0.f;
+    for (int q = 0; q < p.taps; q++) {
+      const int jj = j + p.tap_off + q;
+      if (jj < 0) continue;
+      for (int r = 0; r < p.s; r++) {
+        const long t = (long)jj * p.s + r;
+        if (t >= p.t_in) continue;
+        for (int ci = 0; ci < p.cin; ci++) {
+          float x = __bfloat162float(xg[((size_t)(ci >> 3) * p.t_in + t) * 8 + (ci & 7)]);
+          if (p.has_prelu_in) x = __bfloat162float(__float2bfloat16(prelu_f(x, p.prelu_in)));
+          const int cp = r * p.cin + ci;
+          const size_t wo = (((size_t)q * (p.kpad >> 3) + (cp >> 3)) * p.npad + n) * 8 + (cp & 7);
+          v0 += x * __bfloat162float(wg[wo]);
+          v1 += x * __bfloat162float(wg[wo + 8]);
+        }
+      }
+    }
+    epilogue_pair(p, b, j, n, v0, v1);
+  }
+}
+
+static int validate(const ou_conv_params* p, ConvArgs* a) {
+  OU_REQUIRE(p != nullptr, "ou_conv1d: null params");
+  OU_REQUIRE(p->x && p->w, "ou_conv1d: null x / w");
+  OU_REQUIRE((p->out != nullptr) != (p->out_f32_tm != nullptr),
+             "ou_conv1d: exactly one of out / out_f32_tm must be set");
+  OU_REQUIRE(p->batch > 0 && p->cin > 0 && p->t_in > 0 && p->rows > 0, "ou_conv1d: empty problem");
+  OU_REQUIRE(p->cin % 8 == 0 && p->cout % 8 == 0, "ou_conv1d: channels must be multiples of 8");
+  OU_REQUIRE(p->s >= 1 && p->up >= 1 && p->taps >= 1 && p->taps <= 8, "ou_conv1d: bad s/up/taps");
+  OU_REQUIRE(p->n == p->up * p->cout, "ou_conv1d: n != up*cout");
+  OU_REQUIRE(p->kpad % 32 == 0 && p->kpad >= p->s * p->cin, "ou_conv1d: bad kpad");
+  OU_REQUIRE(p->npad % 32 == 0 && p->npad >= p->n, "ou_conv1d: bad npad");
+  OU_REQUIRE(p->out_f32_tm == nullptr ||
+                 (!p->add1 && !p->add2 && !p->gamma && !p->has_prelu_out && !p->has_prelu_out2 &&
+                  p->up == 1),
+             "ou_conv1d: fp32 time-major output takes no epilogue");
+  OU_REQUIRE(p->out_f32_tm != nullptr || p->t_out > 0, "ou_conv1d: t_out");
+  OU_REQUIRE((p->gamma == nullptr) == (p->beta == nullptr), "ou_conv1d: gamma/beta");
+  a->p = *p;
+  a->cin_chunks = p->cin / 8;
+  a->k_chunks = p->s * p->cin / 8;
+  a->n_kblocks = p->kpad / KB;
+  a->arows = BM + p->taps - 1;
+  return OU_OK;
+}
+
+template <int BN, int STAGES>
+static int launch_mma(const ConvArgs& a, cudaStream_t st) {
+  const ou_conv_params& p = a.p;
+  const size_t smem = (size_t)STAGES * (KCH * a.arows * 16 + p.taps * KCH * BN * 16);
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv1d_mma_kernel<BN, STAGES>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("ou_conv1d: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
+      return OU_ERR_CUDA;
+    }
+    configured = smem;
+  }
+  dim3 grid(ceil_div(p.rows, BM), p.npad / BN, p.batch);
+  conv1d_mma_kernel<BN, STAGES><<<grid, NTHREADS, smem, st>>>(a);
+  return check_launch("ou_conv1d");
+}
+
+}  // namespace ou
+
+extern "C" int ou_conv1d(const ou_conv_params* p, void* stream) {
+  ou::ConvArgs a;
+  int rc = ou::validate(p, &a);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (p->npad % 128 == 0) return ou::launch_mma<128, 3>(a, st);
+  if (p->npad % 64 == 0) return ou::launch_mma<64, 3>(a, st);
+  return ou::launch_mma<32, 3>(a, st);
+}
+
+extern "C" int ou_conv1d_naive(const ou_conv_params* p, void* stream) {
+  ou::ConvArgs a;
+  int rc = ou::validate(p, &a);
+  if (rc) return rc;
+  const long total = (long)p->batch * p->rows * (p->n / 2);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  ou::conv1d_naive_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(a);
+  return ou::check_launch("ou_conv1d_naive");
+}

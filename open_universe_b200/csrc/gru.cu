@@ -1,0 +1,189 @@
+// Bidirectional GRU recurrence as a persistent thread-block-cluster kernel (see ou_b200.h).
+//
+// One cluster of CS CTAs owns one (direction, group of BG clips).  The 3H x H recurrent matrix is
+// split by hidden unit across the cluster and kept REGISTER-resident for the whole sequence
+// (each thread holds a 64-wide slice of one gate row), so a time step costs no weight traffic at
+// all: h_{t-1} (fp32, BG x H) is read from shared memory as warp-broadcast float4s, partial dot
+// products are combined through shared memory, the owning CTA applies the gate math in fp32 and
+// pushes its slice of h_t into every CTA of the cluster through distributed shared memory; one
+// cluster barrier per step.  Everything is fp32 (the recurrence is the precision-critical part).
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace ou {
+
+constexpr int GRU_BG = 4;    // clips per cluster
+constexpr int GRU_KPT = 64;  // recurrent-matrix columns held per thread
+
+struct GruArgs {
+  const float* gx;
+  const float* w_hh;
+  const float* b_hh;
+  const __nv_bfloat16* add;
+  __nv_bfloat16* out;
+  float scale;
+  int batch, t;
+};
+
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }
+
+template <int H, int CS>
+__global__ void __launch_bounds__(3 * (H / CS) * (H / GRU_KPT)) gru_cluster_kernel(const GruArgs a) {
+  constexpr int BG = GRU_BG;
+  constexpr int KPT = GRU_KPT;
+  constexpr int HS = H / CS;       // hidden units owned by this CTA
+  constexpr int ROWS = 3 * HS;     // gate rows owned by this CTA
+  constexpr int KS = H / KPT;      // split of the dot product across threads
+  constexpr int NT = ROWS * KS;
+  static_assert(H % CS == 0 && H % KPT == 0, "bad GRU shape");
+  static_assert(HS * BG <= NT, "not enough threads for the gate stage");
+
+  __shared__ __align__(16) float h_buf[2][BG][H];
+  __shared__ float part[KS][ROWS][BG];
+
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int cid = blockIdx.x / CS;
+  const int dir = cid & 1;
+  const int b0 = (cid >> 1) * BG;
+  const int tid = threadIdx.x;
+  const int ks = tid / ROWS;
+  const int row = tid - ks * ROWS;
+  const int gate = row / HS;
+  const int u = row - gate * HS;
+  const int T = a.t;
+
+  // register-resident slice of W_hh: row (gate*H + rank*HS + u), columns [ks*KPT, ks*KPT + KPT)
+  float w[KPT];
+  {
+    const float4* src = reinterpret_cast<const float4*>(
+        a.w_hh + ((size_t)dir * 3 * H + (size_t)gate * H + rank * HS + u) * H + ks * KPT);
+#pragma unroll
+    for (int k = 0; k < KPT / 4; k++) {
+      float4 v = src[k];
+      w[4 * k] = v.x, w[4 * k + 1] = v.y, w[4 * k + 2] = v.z, w[4 * k + 3] = v.w;
+    }
+  }
+  for (int i = tid; i < 2 * BG * H; i += NT) (&h_buf[0][0][0])[i] = 0.f;
+
+  // gate-stage role: one thread per (owned unit, clip)
+  const bool fin = tid < HS * BG;
+  const int fb = tid % BG, fu = tid / BG;
+  const int hu = rank * HS + fu;             // unit index within the direction
+  const bool fvalid = fin && (b0 + fb) < a.batch;
+  float bhr = 0.f, bhz = 0.f, bhn = 0.f;
+  const float* gxp = nullptr;
+  size_t out_base = 0;
+  if (fvalid) {
+    const float* bh = a.b_hh + (size_t)dir * 3 * H;
+    bhr = bh[hu], bhz = bh[H + hu], bhn = bh[2 * H + hu];
+    gxp = a.gx + (size_t)(b0 + fb) * T * 6 * H + (size_t)dir * 3 * H + hu;
+    const int ch = dir * H + hu;
+    out_base = (((size_t)(b0 + fb) * (2 * H / 8) + (ch >> 3)) * T) * 8 + (ch & 7);
+  }
+  cluster.sync();
+
+  for (int step = 0; step < T; step++) {
+    const int t = dir ? (T - 1 - step) : step;
+    const int cur = step & 1;
+    float gxr = 0.f, gxz = 0.f, gxn = 0.f;
+    if (fvalid) {
+      const float* g = gxp + (size_t)t * 6 * H;
+      gxr = __ldg(g), gxz = __ldg(g + H), gxn = __ldg(g + 2 * H);
+    }
+    float acc[BG];
+#pragma unroll
+    for (int bb = 0; bb < BG; bb++) acc[bb] = 0.f;
+#pragma unroll
+    for (int k = 0; k < KPT / 4; k++) {
+#pragma unroll
+      for (int bb = 0; bb < BG; bb++) {
+        const float4 hv = *reinterpret_cast<const float4*>(&h_buf[cur][bb][ks * KPT + 4 * k]);
+        acc[bb] = fmaf(w[4 * k], hv.x, acc[bb]);
+        acc[bb] = fmaf(w[4 * k + 1], hv.y, acc[bb]);
+        acc[bb] = fmaf(w[4 * k + 2], hv.z, acc[bb]);
+        acc[bb] = fmaf(w[4 * k + 3], hv.w, acc[bb]);
+      }
+    }
+#pragma unroll
+    for (int bb = 0; bb < BG; bb++) part[ks][row][bb] = acc[bb];
+    __syncthreads();
+    if (fin) {
+      float hr = bhr, hz = bhz, hn = bhn;
+#pragma unroll
+      for (int k = 0; k < KS; k++) {
+        hr += part[k][fu][fb];
+        hz += part[k][HS + fu][fb];
+        hn += part[k][2 * HS + fu][fb];
+      }
+      const float r = sigmoid_f(gxr + hr);
+      const float z = sigmoid_f(gxz + hz);
+      const float n = tanhf(gxn + r * hn);
+      const float hprev = h_buf[cur][fb][hu];
+      const float hnew = fvalid ? (1.f - z) * n + z * hprev : 0.f;
+      float* slot = &h_buf[cur ^ 1][fb][hu];
+#pragma unroll
+      for (int c = 0; c < CS; c++) *cluster.map_shared_rank(slot, c) = hnew;
+      if (fvalid) {
+        const size_t off = out_base + (size_t)t * 8;
+        float v = hnew;
+        if (a.add) v += __bfloat162float(a.add[off]);
+        a.out[off] = __float2bfloat16(v * a.scale);
+      }
+    }
+    cluster.sync();
+  }
+}
+
+template <int H, int CS>
+static int launch_gru(const GruArgs& a, cudaStream_t st) {
+  constexpr int NT = 3 * (H / CS) * (H / GRU_KPT);
+  auto kern = gru_cluster_kernel<H, CS>;
+  if (CS > 8) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e != cudaSuccess) {
+      set_error("ou_gru_bidir: non-portable cluster size: %s", cudaGetErrorString(e));
+      return OU_ERR_CUDA;
+    }
+  }
+  const int clusters = 2 * ceil_div(a.batch, GRU_BG);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(clusters * CS);
+  cfg.blockDim = dim3(NT);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a);
+  if (e != cudaSuccess) {
+    set_error("ou_gru_bidir: launch H=%d CS=%d: %s", H, CS, cudaGetErrorString(e));
+    return OU_ERR_CUDA;
+  }
+  return check_launch("ou_gru_bidir");
+}
+
+}  // namespace ou
+
+extern "C" int ou_gru_bidir(const float* gx, const float* w_hh, const float* b_hh, const void* add,
+                            float scale, void* out, int batch, int t, int hidden, void* stream) {
+  OU_REQUIRE(gx && w_hh && b_hh && out, "ou_gru_bidir: null pointer");
+  OU_REQUIRE(batch > 0 && t > 0, "ou_gru_bidir: empty problem");
+  ou::GruArgs a{gx, w_hh, b_hh, (const __nv_bfloat16*)add, (__nv_bfloat16*)out, scale, batch, t};
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (hidden) {
+    case 128: return ou::launch_gru<128, 4>(a, st);
+    case 256: return ou::launch_gru<256, 8>(a, st);
+    case 384: return ou::launch_gru<384, 16>(a, st);
+    default:
+      ou::set_error("ou_gru_bidir: hidden size %d has no kernel (128, 256, 384)", hidden);
+      return OU_ERR_UNSUPPORTED;
+  }
+}

@@ -1,0 +1,112 @@
+"""ctypes binding of ``csrc/libou_b200.so`` (C ABI declared in ``include/ou_b200.h``).
+
+Error codes are turned into Python exceptions (``ValueError`` for OU_ERR_INVALID,
+``NotImplementedError`` for OU_ERR_UNSUPPORTED, ``RuntimeError`` otherwise).  There is no
+fallback: if the library is missing it is built with nvcc, and if that is impossible every
+device call raises.
+"""
+import ctypes
+from ctypes import (POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t,
+                    c_void_p)
+from pathlib import Path
+
+LIB_PATH = Path(__file__).resolve().parent.parent / "csrc" / "libou_b200.so"
+OU_ABI_VERSION = 1
+
+
+class ConvParams(Structure):
+    _fields_ = [
+        ("x", c_void_p), ("w", c_void_p), ("bias", c_void_p), ("add1", c_void_p),
+        ("add2", c_void_p), ("gamma", c_void_p), ("beta", c_void_p), ("out", c_void_p),
+        ("out_f32_tm", c_void_p),
+        ("batch", c_int32), ("cin", c_int32), ("t_in", c_int32),
+        ("s", c_int32), ("taps", c_int32), ("tap_off", c_int32),
+        ("n", c_int32), ("cout", c_int32), ("up", c_int32),
+        ("kpad", c_int32), ("npad", c_int32),
+        ("rows", c_int32), ("t_out", c_int32),
+        ("film_bstride", c_int32),
+        ("has_prelu_in", c_int32), ("has_prelu_out", c_int32), ("has_prelu_out2", c_int32),
+        ("prelu_in", c_float), ("prelu_out", c_float), ("prelu_out2", c_float),
+        ("scale1", c_float), ("scale2", c_float),
+    ]
+
+
+# name -> (restype, argtypes); every symbol of include/ou_b200.h
+SIGNATURES = {
+    "ou_abi_version": (c_int, []),
+    "ou_last_error": (c_int, [c_char_p, c_size_t]),
+    "ou_launch_count": (c_int64, []),
+    "ou_conv1d": (c_int, [POINTER(ConvParams), c_void_p]),
+    "ou_conv1d_naive": (c_int, [POINTER(ConvParams), c_void_p]),
+    "ou_input_conv": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                              c_int, c_int, c_void_p]),
+    "ou_output_sde": (c_int, [c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
+                              c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "ou_gru_bidir": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int,
+                             c_int, c_int, c_void_p]),
+    "ou_mel_power": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                             c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "ou_mel_finalize": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                c_void_p]),
+    "ou_sigma_embed_simple": (c_int, [c_void_p, c_float, c_float, c_void_p, c_int, c_int, c_void_p]),
+    "ou_sigma_embed_rff": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "ou_linear_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                              c_int, c_float, c_void_p]),
+    "ou_pad_normalize": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                 c_float, c_void_p]),
+    "ou_unpad_limit": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                               c_void_p]),
+    "ou_pack_blocked": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "ou_unpack_blocked": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "ou_film_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+}
+
+_lib = None
+
+
+class OuError(RuntimeError):
+    pass
+
+
+def load(build_if_missing=True):
+    """Load (building first if necessary) the shared library and declare every prototype."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if build_if_missing:
+        from ..build import build, needs_build
+        if needs_build():
+            build()
+    if not LIB_PATH.exists():
+        raise OuError(f"{LIB_PATH} is missing: build it with `python -m open_universe_b200.build` "
+                      "(there is no CPU or PyTorch fallback)")
+    lib = ctypes.CDLL(str(LIB_PATH))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if lib.ou_abi_version() != OU_ABI_VERSION:
+        raise OuError(f"ABI mismatch: library {lib.ou_abi_version()} vs binding {OU_ABI_VERSION}")
+    _lib = lib
+    return lib
+
+
+def last_error():
+    buf = ctypes.create_string_buffer(512)
+    load().ou_last_error(buf, 512)
+    return buf.value.decode(errors="replace")
+
+
+def check(rc):
+    if rc == 0:
+        return
+    msg = last_error()
+    if rc == -1:
+        raise ValueError(msg)
+    if rc == -3:
+        raise NotImplementedError(msg)
+    raise OuError(f"libou_b200 error {rc}: {msg}")
+
+
+def launch_count():
+    return int(load().ou_launch_count())

@@ -1,0 +1,397 @@
+"""Lowering of the UNIVERSE networks to a flat list of fused device ops.
+
+The networks (reference ``score.py:277-297``, ``condition.py:346-377``) are lowered ONCE per
+(model weights, batch, length) into a ``Program``: named activation buffers plus a list of
+ops, each of which is exactly one CUDA kernel launch of ``csrc/`` through the C ABI
+(``include/ou_b200.h``).  The op list is data: ``engine.runtime`` executes it on the GPU;
+the test-suite executes the *same* list with a PyTorch emulator to check the host-side
+lowering (folding, buffer lengths, epilogue wiring) against the oracle on CPU.
+
+Activation layout in HBM ("blocked"): bf16 ``[B][C/8][T][8]`` -- 8 channels interleaved per
+time step so that one time step of one channel group is a 16-byte vector; a tile of
+consecutive time steps of one channel group is contiguous (TMA / cp.async friendly) and is
+directly the K-major no-swizzle operand layout of the tensor-core MMAs (8 rows x 16 B core
+matrices).  Signals (B, 1, T), FiLM tables, GRU pre-activations and GRU state stay fp32.
+
+Fusion plan per ConvBlock (blocks.py:327-412):
+    [up conv  : PReLU_in -> convT(+lowpass) + bias -> (+skip)/sqrt2                    ]
+    conv1     : PReLU_in -> k5 + bias -> (+sc)/sqrt2 -> FiLM -> PReLU(conv2's)
+    conv2     : k3 + bias -> PReLU(conv3's)
+    conv3     : k3 + bias -> (+h)/sqrt2 [-> PReLU of the single consumer]
+    [down conv: PReLU_in -> (lowpass+)conv stride s + bias                             ]
+Step-invariant work hoisted out of the sampler loop: the decoder's ``signal_cond_proj`` 1x1
+convs (score.py:165-170,189-194) and the sigma-embedding + FiLM projections for all steps.
+"""
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import fold
+from .fold import FoldedConv
+
+SQRT_HALF = 1.0 / math.sqrt(2.0)
+
+
+@dataclass
+class BufSpec:
+    kind: str        # 'blocked' (bf16 [B][C/8][T][8]) | 'f32_tm' (fp32 [B][T][C]) | 'f32_bt' (fp32 [B][T])
+    channels: int
+    length: int
+
+
+@dataclass
+class ConvOp:
+    """One launch of the implicit-GEMM conv kernel (``ou_conv1d``)."""
+    name: str
+    src: str
+    dst: str
+    fc: FoldedConv
+    t_in: int
+    t_out: int
+    rows: int                                 # number of GEMM rows j actually needed
+    add1: Optional[str] = None
+    scale1: float = 1.0
+    add2: Optional[str] = None
+    scale2: float = 1.0
+    film_off: Optional[int] = None            # column offset of gamma in the FiLM table (beta at +cout)
+    prelu_out: Optional[float] = None
+    prelu_out2: Optional[float] = None
+    dst_kind: str = "blocked"
+    packed: Optional[dict] = None             # device tensors filled in by the runtime
+
+
+@dataclass
+class InputConvOp:
+    """(B,1,T) fp32 signal -> blocked bf16 (B,C,T): k-tap 'same' conv of a 1-channel input with an
+    optional per-clip input scale (EDM c_in, universe.py:197-203).  ``ou_input_conv``."""
+    name: str
+    src: str
+    dst: str
+    w: torch.Tensor                            # (C, k) fp32
+    bias: torch.Tensor                         # (C,)
+    t: int
+    use_in_scale: bool = False
+    packed: Optional[dict] = None
+
+
+@dataclass
+class OutputOp:
+    """blocked bf16 (B,C,T) -> net(B,1,T) = k-tap conv to ONE channel + bias, fused with the
+    EDM mix and the reverse-SDE update (universe.py:197-209, 334-343):
+        x_out = ca[b] * x + cb[b] * net + cc[b] * noise      ``ou_output_sde``."""
+    name: str
+    src: str
+    w: torch.Tensor                            # (C, k)
+    bias: float
+    t: int
+    t_out: int                                 # logical signal length (right-padded with zeros)
+    packed: Optional[dict] = None
+
+
+@dataclass
+class GruOp:
+    """Bidirectional GRU recurrence over pre-computed input projections (``ou_gru_bidir``).
+    src: fp32 [B][T][2*3H] (fwd r,z,n | bwd r,z,n, includes b_ih); dst blocked bf16 [B][2H/8][T][8]
+    = (h_fwd | h_bwd) optionally (+ add) * scale."""
+    name: str
+    src: str
+    dst: str
+    w_hh: torch.Tensor                         # (2, 3H, H) fp32
+    b_hh: torch.Tensor                         # (2, 3H)
+    hidden: int
+    t: int
+    add: Optional[str] = None
+    scale: float = 1.0
+    packed: Optional[dict] = None
+
+
+@dataclass
+class MelOp:
+    """(B,1,T) fp32 -> normalised mel 'spectrogram' blocked bf16 (+ fp32 (B,n_mels,F) copy)
+    (condition.py:92-108).  ``ou_mel_power`` + ``ou_mel_finalize``."""
+    name: str
+    src: str
+    dst: str
+    n_fft: int
+    hop: int
+    n_mels: int
+    pad_left: int
+    frames: int
+    t: int
+    window: torch.Tensor                       # (n_fft,)
+    fb: torch.Tensor                           # (n_fft/2+1, n_mels)
+    packed: Optional[dict] = None
+
+
+@dataclass
+class Program:
+    batch: int
+    bufs: Dict[str, BufSpec] = field(default_factory=dict)
+    ops: List[object] = field(default_factory=list)
+    film_cols: int = 0
+    film_layers: List[Tuple[object, int, int]] = field(default_factory=list)  # (linear, offset, cout)
+    outputs: Dict[str, str] = field(default_factory=dict)
+    meta: dict = field(default_factory=dict)
+
+    def buf(self, name, kind, channels, length):
+        spec = BufSpec(kind, channels, length)
+        if name in self.bufs and self.bufs[name] != spec:
+            raise RuntimeError(f"buffer {name} redefined: {self.bufs[name]} vs {spec}")
+        self.bufs[name] = spec
+        return name
+
+    def film(self, linear, cout):
+        off = self.film_cols
+        self.film_layers.append((linear, off, cout))
+        self.film_cols += 2 * cout
+        return off
+
+
+def ceil_div(a, b):
+    return -(-a // b)
+
+
+def add_conv(prog, name, src, dst, fc, t_in, t_out=None, **kw):
+    """Append a ConvOp; derives the output length / GEMM row count from the folded geometry."""
+    if t_out is None:
+        t_out = ceil_div(t_in, fc.s) * fc.up
+    rows = ceil_div(t_out, fc.up)
+    dst_kind = kw.get("dst_kind", "blocked")
+    if dst_kind == "blocked":
+        prog.buf(dst, "blocked", fc.cout, t_out)
+    else:
+        prog.buf(dst, "f32_tm", fc.n, rows)
+    prog.ops.append(ConvOp(name, src, dst, fc, t_in, t_out, rows, **kw))
+    return dst, t_out
+
+
+def lower_conv_block(prog, blk, pfx, src, t_in, *, film_linear=None, input_cond=None, res=None,
+                     length=None, out_prelus=(), raw_cond_out=False, need_tail=True):
+    """Lower one ``ConvBlock`` (blocks.py:327-412).  ``src`` holds the RAW block input.
+    Returns (out, t_out, skip, cond_out) buffer names (``cond_out`` only if ``raw_cond_out``)."""
+    c = blk.n_channels
+    h, t = src, t_in
+    if blk.rate_change_dir == "up":
+        fc = fold.fold_prelu_conv(blk.rate_change_conv)
+        t_up = length if length is not None else t_in * fc.up
+        if ceil_div(t_up, fc.up) > t_in + 1:
+            raise ValueError("target length is more than one frame longer than the upsampled input")
+        h, t = add_conv(prog, pfx + ".up", src, pfx + ".h", fc, t_in, t_up,
+                        add1=res, scale1=SQRT_HALF if res is not None else 1.0)
+    elif res is not None:
+        raise RuntimeError("lowering expects the residual of a rate-preserving block to be "
+                           "pre-added by the producer (GRU epilogue)")
+    fc1 = fold.fold_prelu_conv(blk.conv1)
+    fc2 = fold.fold_prelu_conv(blk.conv2)
+    fc3 = fold.fold_prelu_conv(blk.conv3)
+    film_off = prog.film(film_linear, c) if film_linear is not None else None
+    cond_out = None
+    if raw_cond_out:
+        # the conditioner decoder exports conv1's raw output (condition.py:264-270): keep it raw
+        # and let conv2 apply its PReLU on load
+        cond_out, _ = add_conv(prog, pfx + ".conv1", h, pfx + ".cond", fc1, t)
+        c1 = cond_out
+    else:
+        a2 = fc2.prelu_in
+        fc2 = FoldedConv(fc2.w, fc2.bias, fc2.cin, fc2.cout, 1, 1, fc2.taps, fc2.tap_off, None)
+        c1, _ = add_conv(prog, pfx + ".conv1", h, pfx + ".c1", fc1, t, add1=input_cond,
+                         scale1=SQRT_HALF if input_cond is not None else 1.0, film_off=film_off,
+                         prelu_out=a2)
+    if not need_tail:
+        return None, t, None, cond_out
+    a3 = fc3.prelu_in
+    fc3 = FoldedConv(fc3.w, fc3.bias, fc3.cin, fc3.cout, 1, 1, fc3.taps, fc3.tap_off, None)
+    c2, _ = add_conv(prog, pfx + ".conv2", c1, pfx + ".c2", fc2, t, prelu_out=a3)
+    po = list(out_prelus) + [None, None]
+    is_down = blk.rate_change_dir == "down"
+    v, _ = add_conv(prog, pfx + ".conv3", c2, pfx + ".v", fc3, t, add1=h, scale1=SQRT_HALF,
+                    prelu_out=None if is_down else po[0], prelu_out2=None if is_down else po[1])
+    if is_down:
+        fcr = fold.fold_prelu_conv(blk.rate_change_conv)
+        out, t_out = add_conv(prog, pfx + ".down", v, pfx + ".out", fcr, t)
+        return out, t_out, v, cond_out
+    return v, t, v, cond_out
+
+
+def fold_gru_layer(gru, layer):
+    """torch.nn.GRU parameters of one bidirectional layer -> (input-projection conv, W_hh, b_hh)."""
+    sfx = f"_l{layer}"
+    w_ih = torch.cat([getattr(gru, "weight_ih" + sfx), getattr(gru, "weight_ih" + sfx + "_reverse")])
+    b_ih = torch.cat([getattr(gru, "bias_ih" + sfx), getattr(gru, "bias_ih" + sfx + "_reverse")])
+    w_hh = torch.stack([getattr(gru, "weight_hh" + sfx), getattr(gru, "weight_hh" + sfx + "_reverse")])
+    b_hh = torch.stack([getattr(gru, "bias_hh" + sfx), getattr(gru, "bias_hh" + sfx + "_reverse")])
+    return (fold.fold_linear_as_conv(w_ih, b_ih), w_hh.detach().float().contiguous(),
+            b_hh.detach().float().contiguous())
+
+
+def lower_gru(prog, gru, pfx, src, t, *, add_last=None, scale_last=1.0):
+    """Bidirectional multi-layer GRU over a blocked (B, C, T) buffer (score.py:116, condition.py:213)."""
+    h = src
+    for layer in range(gru.num_layers):
+        fc, w_hh, b_hh = fold_gru_layer(gru, layer)
+        gx, _ = add_conv(prog, f"{pfx}.l{layer}.xproj", h, f"{pfx}.gx", fc, t, dst_kind="f32_tm")
+        last = layer == gru.num_layers - 1
+        dst = prog.buf(f"{pfx}.l{layer}.out", "blocked", 2 * gru.hidden_size, t)
+        prog.ops.append(GruOp(f"{pfx}.l{layer}", gx, dst, w_hh, b_hh, gru.hidden_size, t,
+                              add=add_last if last else None, scale=scale_last if last else 1.0))
+        h = dst
+    return h
+
+
+# --------------------------------------------------------------------------------- score network
+def lower_score_network(net, batch, t):
+    """ScoreNetwork.forward (score.py:277-297) for a (batch, 1, t) input.
+
+    Program inputs : 'x' (fp32 signal), 'sc{lvl}' (pre-projected conditioning, see
+    ``lower_cond_projection``); tables: FiLM (rows x film_cols), in_scale, coefficients.
+    Program output : the OutputOp (net output fused with the EDM / SDE update)."""
+    if net.precoding is not None:
+        raise NotImplementedError("precoding is not used by any shipped config")
+    prog = Program(batch)
+    c0 = net.input_conv.out_channels
+    prog.buf("x", "f32_bt", 1, t)
+    w_in = net.input_conv.weight.detach().float()[:, 0, :].contiguous()
+    prog.buf("enc.in", "blocked", c0, t)
+    prog.ops.append(InputConvOp("input_conv", "x", "enc.in", w_in,
+                                net.input_conv.bias.detach().float().contiguous(), t,
+                                use_in_scale=True))
+    enc, dec = net.encoder, net.decoder
+    h, tl = "enc.in", t
+    skips, lengths = [], []
+    for i, (blk, lin) in enumerate(zip(enc.ds_modules, enc.cond_proj)):
+        lengths.append(tl)
+        h, tl, skip, _ = lower_conv_block(prog, blk, f"enc.{i}", h, tl, film_linear=lin)
+        skips.append(skip)
+    if enc.seq_model == "gru":
+        if enc.gru_conv_sandwich:
+            raise NotImplementedError("encoder_gru_conv_sandwich is false in every shipped config")
+        # decoder block 0's "(h + res)/sqrt2" (blocks.py:376) is folded into the GRU epilogue when
+        # that block does not change the rate (extra_conv_block=True); otherwise the up conv adds it
+        first = dec.up_modules[0]
+        if first.rate_change_dir == "none":
+            h = lower_gru(prog, enc.gru, "gru", h, tl, add_last=skips[-1], scale_last=SQRT_HALF)
+        else:
+            h = lower_gru(prog, enc.gru, "gru", h, tl)
+    elif enc.seq_model != "none":
+        raise ValueError("Values for 'seq_model' can be gru|attention|none")
+    skips, lengths = skips[::-1], lengths[::-1]
+    n_dec = len(dec.up_modules)
+    for lvl, (blk, lin) in enumerate(zip(dec.up_modules, dec.noise_cond_proj)):
+        last = lvl == n_dec - 1
+        po = ()
+        if last:
+            po = (fold.prelu_slope(net.prelu), fold.prelu_slope(net.output_conv.prelu))
+        cs = blk.n_channels
+        prog.buf(f"sc{lvl}", "blocked", cs, lengths[lvl])
+        if blk.rate_change_dir == "none":
+            if enc.seq_model != "gru":
+                raise NotImplementedError("rate-preserving decoder block without GRU")
+            h, tl, _, _ = lower_conv_block(prog, blk, f"dec.{lvl}", h, tl, film_linear=lin,
+                                           input_cond=f"sc{lvl}", out_prelus=po)
+        else:
+            h, tl, _, _ = lower_conv_block(prog, blk, f"dec.{lvl}", h, tl, film_linear=lin,
+                                           input_cond=f"sc{lvl}", res=skips[lvl],
+                                           length=lengths[lvl], out_prelus=po)
+    oc = net.output_conv
+    if oc.conv.out_channels != 1:
+        raise NotImplementedError("output_channels != 1")
+    w_out = fold.effective_weight(oc.conv)[0].float().contiguous()      # (C, k)
+    b_out = float(oc.conv.bias.detach()[0].item()) if oc.conv.bias is not None else 0.0
+    prog.ops.append(OutputOp("output_conv", h, w_out, b_out, tl, t))
+    prog.meta["lengths"] = lengths
+    prog.meta["cond_channels"] = [b.n_channels for b in dec.up_modules]
+    return prog
+
+
+def lower_cond_projection(net, batch, lengths):
+    """Step-invariant 1x1 ``signal_cond_proj`` convs (score.py:165-170,189-194,206): run once per
+    ``enhance()`` on the conditioner's output instead of once per step.  'cond{lvl}' -> 'sc{lvl}'."""
+    prog = Program(batch)
+    for lvl, (proj, tl) in enumerate(zip(net.decoder.signal_cond_proj, lengths)):
+        fc = fold.fold_same_conv(proj)
+        prog.buf(f"cond{lvl}", "blocked", fc.cin, tl)
+        add_conv(prog, f"signal_cond_proj.{lvl}", f"cond{lvl}", f"sc{lvl}", fc, tl)
+    return prog
+
+
+# --------------------------------------------------------------------------------- conditioner
+def lower_conditioner(net, batch, t, need_signal_tail=True):
+    """ConditionerNetwork.forward (condition.py:346-377) for (batch, 1, t) inputs 'x' and 'x_wav'.
+    Outputs: 'cond{lvl}' raw conv1 outputs of the decoder blocks, 'h' latent, 'y_hat'."""
+    if net.precoding is not None:
+        raise NotImplementedError("precoding is not used by any shipped config")
+    prog = Program(batch)
+    prog.buf("x", "f32_bt", 1, t)
+    prog.buf("x_wav", "f32_bt", 1, t)
+    mel = net.input_mel
+    hop = mel.ds_factor
+    frames = ceil_div(t, hop)
+    prog.buf("mel", "blocked", mel.n_mels, frames)
+    prog.ops.append(MelOp("mel", "x_wav", "mel", mel.n_fft, hop, mel.n_mels, mel.pad_left, frames,
+                          t, mel.mel_spec.spectrogram.window.detach().float(),
+                          mel.mel_spec.mel_scale.fb.detach().float()))
+    fcm = fold.fold_same_conv(mel.conv)
+    m0, _ = add_conv(prog, "mel.conv", "mel", "mel.c", fcm, frames)
+    x_mel, _, _, _ = lower_conv_block(prog, mel.conv_block, "mel.block", m0, frames)
+
+    c0 = net.input_conv.out_channels
+    w_in = fold.effective_weight(net.input_conv)[:, 0, :].float().contiguous()
+    prog.buf("enc.in", "blocked", c0, t)
+    prog.ops.append(InputConvOp("input_conv", "x", "enc.in", w_in,
+                                net.input_conv.bias.detach().float().contiguous(), t))
+    enc = net.encoder
+    h, tl = "enc.in", t
+    lengths = []
+    acc = x_mel
+    n_sum = 1
+    st_outs = []
+    for i, blk in enumerate(enc.ds_modules):
+        lengths.append(tl)
+        h, tl_next, skip, _ = lower_conv_block(prog, blk, f"enc.{i}", h, tl)
+        st = enc.st_convs[i] if i < len(enc.st_convs) else None
+        if st is not None:
+            fcs = fold.fold_down_conv(st)
+            acc, t_st = add_conv(prog, f"enc.st{i}", skip, f"enc.st{i}.sum", fcs, tl, add1=acc,
+                                 scale1=1.0)
+            if t_st != frames:
+                raise ValueError("st_conv output length does not match the mel frame count")
+            n_sum += 1
+            st_outs.append(acc)
+        tl = tl_next
+    # out = (x_mel + sum(st_convs) + x) / sqrt(n+1)   (condition.py:202-206): the running sum is
+    # carried through the st_conv epilogues; the last op producing ``h`` adds it and scales.
+    n_sum += 1
+    last = next((op for op in reversed(prog.ops) if isinstance(op, ConvOp) and op.dst == h), None)
+    if last is None or last.add2 is not None:
+        raise RuntimeError("unexpected producer of the encoder output")
+    if tl != frames:
+        raise ValueError("encoder output length does not match the mel frame count")
+    last.add2, last.scale2 = acc, 1.0 / math.sqrt(n_sum)
+    if enc.seq_model != "gru":
+        raise ValueError("Values for 'seq_model' can be gru|attention")
+    out1, _, _, _ = lower_conv_block(prog, enc.conv_block1, "enc.cb1", h, tl)
+    g = lower_gru(prog, enc.gru, "gru", out1, tl,
+                  add_last=out1 if enc.with_gru_residual else None,
+                  scale_last=SQRT_HALF if enc.with_gru_residual else 1.0)
+    lat, _, _, _ = lower_conv_block(prog, enc.conv_block2, "enc.cb2", g, tl)
+    prog.outputs["h"] = lat
+    lengths = lengths[::-1]
+    dec = net.decoder
+    y, _, _, _ = lower_conv_block(prog, dec.input_conv_block, "dec.in", lat, tl)
+    n_up = len(dec.up_modules)
+    for lvl, (blk, length) in enumerate(zip(dec.up_modules, lengths)):
+        last_blk = lvl == n_up - 1
+        y, tl, _, cond = lower_conv_block(prog, blk, f"dec.{lvl}", y, tl, length=length,
+                                          raw_cond_out=True,
+                                          need_tail=need_signal_tail or not last_blk)
+        prog.outputs[f"cond{lvl}"] = cond
+    if need_signal_tail:
+        if net.output_conv is not None:
+            fco = fold.fold_same_conv(net.output_conv)
+            y, _ = add_conv(prog, "output_conv", y, "y_hat", fco, tl)
+        prog.outputs["y_hat"] = y
+    prog.meta["lengths"] = lengths
+    prog.meta["t_final"] = tl
+    return prog

@@ -1,0 +1,499 @@
+"""GPU executor: runs ``engine.program`` op lists through the C ABI of ``libou_b200.so``.
+
+PyTorch is used for device memory (``torch.empty`` / ``Tensor.data_ptr``), the current CUDA
+stream and tiny host-side scalar math only; every FLOP of the networks is issued by a kernel of
+``csrc/``.  There is NO CPU path: any entry point called with non-CUDA tensors raises.
+"""
+import math
+from ctypes import byref, c_void_p
+
+import torch
+
+from . import fold, lib
+from . import program as P
+
+
+class NoCudaPathError(RuntimeError):
+    pass
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise NoCudaPathError(
+                "open_universe_b200 computes on CUDA devices only (sm_100a kernels through "
+                "libou_b200.so); there is no CPU fallback -- move the model and inputs to 'cuda'")
+
+
+def _stream():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return c_void_p(t.data_ptr()) if t is not None else c_void_p(0)
+
+
+def round_up(a, b):
+    return -(-a // b) * b
+
+
+# ------------------------------------------------------------------------------------ packing
+def choose_npad(n):
+    if n >= 128:
+        return round_up(n, 128)
+    if n > 32:
+        return round_up(n, 64)
+    return 32
+
+
+def pack_conv_weights(fc, device):
+    """(N, taps, K) fp32 -> bf16 [taps][kpad/8][npad][8] (layout of ou_conv_params.w)."""
+    n, taps, k = fc.w.shape
+    kpad, npad = round_up(k, 32), choose_npad(n)
+    w = torch.zeros(taps, kpad, npad, dtype=torch.float32, device=device)
+    w[:, :k, :n] = fc.w.to(device).permute(1, 2, 0)
+    w = w.reshape(taps, kpad // 8, 8, npad).permute(0, 1, 3, 2).contiguous()
+    return {"w": w.to(torch.bfloat16), "bias": fc.bias.to(device).contiguous(), "kpad": kpad,
+            "npad": npad}
+
+
+def alloc_buffers(prog, device, skip=()):
+    bufs = {}
+    b = prog.batch
+    for name, spec in prog.bufs.items():
+        if name in skip:
+            continue
+        if spec.kind == "blocked":
+            bufs[name] = torch.empty(b, spec.channels // 8, spec.length, 8, dtype=torch.bfloat16,
+                                     device=device)
+        elif spec.kind == "f32_tm":
+            bufs[name] = torch.empty(b, spec.length, spec.channels, dtype=torch.float32,
+                                     device=device)
+        elif spec.kind == "f32_bt":
+            bufs[name] = None   # supplied by the caller
+        else:
+            raise ValueError(spec.kind)
+    return bufs
+
+
+def prepare_ops(prog, device):
+    """Upload packed weights / small tables for every op of a program."""
+    for op in prog.ops:
+        if isinstance(op, P.ConvOp):
+            op.packed = pack_conv_weights(op.fc, device)
+        elif isinstance(op, P.InputConvOp):
+            op.packed = {"w": op.w.to(device).contiguous(), "bias": op.bias.to(device).contiguous()}
+        elif isinstance(op, P.OutputOp):
+            op.packed = {"w": op.w.to(device).contiguous()}
+        elif isinstance(op, P.GruOp):
+            op.packed = {"w_hh": op.w_hh.to(device).contiguous(),
+                         "b_hh": op.b_hh.to(device).contiguous()}
+        elif isinstance(op, P.MelOp):
+            i = torch.arange(op.n_fft, dtype=torch.float64)
+            ang = 2.0 * math.pi * i / op.n_fft
+            tw = torch.stack([torch.cos(ang), torch.sin(ang)], dim=1).float()
+            op.packed = {"window": op.window.to(device).contiguous(),
+                         "fb": op.fb.to(device).contiguous(), "twiddle": tw.to(device).contiguous(),
+                         "mel": torch.empty(prog.batch, op.n_mels, op.frames, dtype=torch.float32,
+                                            device=device),
+                         "energy": torch.empty(prog.batch, op.frames, dtype=torch.float32,
+                                               device=device)}
+
+
+# ------------------------------------------------------------------------------------ op launch
+def launch_conv(op, bufs, batch, gamma=None, beta=None, film_bstride=0, naive=False):
+    fc, pk = op.fc, op.packed
+    prm = lib.ConvParams()
+    prm.x = bufs[op.src].data_ptr()
+    prm.w = pk["w"].data_ptr()
+    prm.bias = pk["bias"].data_ptr()
+    prm.add1 = bufs[op.add1].data_ptr() if op.add1 else None
+    prm.add2 = bufs[op.add2].data_ptr() if op.add2 else None
+    prm.gamma = gamma
+    prm.beta = beta
+    if op.dst_kind == "blocked":
+        prm.out, prm.out_f32_tm = bufs[op.dst].data_ptr(), None
+    else:
+        prm.out, prm.out_f32_tm = None, bufs[op.dst].data_ptr()
+    prm.batch, prm.cin, prm.t_in = batch, fc.cin, op.t_in
+    prm.s, prm.taps, prm.tap_off = fc.s, fc.taps, fc.tap_off
+    prm.n, prm.cout, prm.up = fc.n, fc.cout, fc.up
+    prm.kpad, prm.npad = pk["kpad"], pk["npad"]
+    prm.rows, prm.t_out = op.rows, op.t_out
+    prm.film_bstride = film_bstride
+    prm.has_prelu_in = fc.prelu_in is not None
+    prm.prelu_in = fc.prelu_in or 0.0
+    prm.has_prelu_out = op.prelu_out is not None
+    prm.prelu_out = op.prelu_out or 0.0
+    prm.has_prelu_out2 = op.prelu_out2 is not None
+    prm.prelu_out2 = op.prelu_out2 or 0.0
+    prm.scale1, prm.scale2 = op.scale1, op.scale2
+    fn = lib.load().ou_conv1d_naive if naive else lib.load().ou_conv1d
+    lib.check(fn(byref(prm), _stream()))
+
+
+class Executor:
+    """A lowered program bound to device buffers."""
+
+    def __init__(self, prog, device, external=()):
+        self.prog = prog
+        self.device = device
+        self.batch = prog.batch
+        prepare_ops(prog, device)
+        self.bufs = alloc_buffers(prog, device, skip=external)
+        self.naive = False   # tests: route ConvOps through the fp32 CUDA-core reference kernel
+
+    def run(self, film=None, film_bstride=0, in_scale=None, coef=None, noise=None, xout=None,
+            net_out=None):
+        L = lib.load()
+        bufs, B = self.bufs, self.batch
+        for op in self.prog.ops:
+            if isinstance(op, P.ConvOp):
+                gamma = beta = None
+                if op.film_off is not None:
+                    base = film.data_ptr() + 4 * op.film_off
+                    gamma, beta = base, base + 4 * op.fc.cout
+                launch_conv(op, bufs, B, gamma, beta, film_bstride, self.naive)
+            elif isinstance(op, P.InputConvOp):
+                c, k = op.packed["w"].shape
+                lib.check(L.ou_input_conv(_ptr(bufs[op.src]), _ptr(op.packed["w"]),
+                                          _ptr(op.packed["bias"]),
+                                          _ptr(in_scale if op.use_in_scale else None),
+                                          _ptr(bufs[op.dst]), B, op.t, c, k, _stream()))
+            elif isinstance(op, P.OutputOp):
+                c, k = op.packed["w"].shape
+                lib.check(L.ou_output_sde(_ptr(bufs[op.src]), _ptr(op.packed["w"]), op.bias,
+                                          _ptr(coef), _ptr(bufs["x"]), _ptr(noise), _ptr(xout),
+                                          _ptr(net_out), B, c, k, op.t, op.t_out, _stream()))
+            elif isinstance(op, P.GruOp):
+                lib.check(L.ou_gru_bidir(_ptr(bufs[op.src]), _ptr(op.packed["w_hh"]),
+                                         _ptr(op.packed["b_hh"]),
+                                         _ptr(bufs[op.add] if op.add else None), op.scale,
+                                         _ptr(bufs[op.dst]), B, op.t, op.hidden, _stream()))
+            elif isinstance(op, P.MelOp):
+                pk = op.packed
+                lib.check(L.ou_mel_power(_ptr(bufs[op.src]), _ptr(pk["window"]), _ptr(pk["fb"]),
+                                         _ptr(pk["twiddle"]), _ptr(pk["mel"]), _ptr(pk["energy"]),
+                                         B, op.t, op.n_fft, op.hop, op.n_mels, op.pad_left,
+                                         op.frames, _stream()))
+                lib.check(L.ou_mel_finalize(_ptr(pk["mel"]), _ptr(pk["energy"]), _ptr(pk["mel"]),
+                                            _ptr(bufs[op.dst]), B, op.n_mels, op.frames, _stream()))
+            else:
+                raise TypeError(op)
+
+
+# ------------------------------------------------------------------------------------ layouts
+def pack_blocked(x):
+    """(B, C, T) fp32 -> blocked bf16 [B][C/8][T][8]."""
+    require_cuda(x)
+    b, c, t = x.shape
+    x = x.contiguous().float()
+    out = torch.empty(b, c // 8, t, 8, dtype=torch.bfloat16, device=x.device)
+    lib.check(lib.load().ou_pack_blocked(_ptr(x), _ptr(out), b, c, t, _stream()))
+    return out
+
+
+def unpack_blocked(xb):
+    """blocked bf16 [B][C/8][T][8] -> (B, C, T) fp32."""
+    require_cuda(xb)
+    b, c8, t, _ = xb.shape
+    out = torch.empty(b, c8 * 8, t, dtype=torch.float32, device=xb.device)
+    lib.check(lib.load().ou_unpack_blocked(_ptr(xb), _ptr(out), b, c8 * 8, t, _stream()))
+    return out
+
+
+# ------------------------------------------------------------------------------------ caching
+def weights_version(module):
+    """Cheap fingerprint that changes whenever a parameter / buffer is written in place, replaced,
+    or moved (EMA swap in eval()/train(), load_state_dict, .to())."""
+    v = 0
+    for t in list(module.parameters()) + list(module.buffers()):
+        v = (v * 1000003 + t._version + (t.data_ptr() & 0xFFFFFFFF)) & 0xFFFFFFFFFFFF
+    return v
+
+
+def _cache(module):
+    c = module.__dict__.get("_ou_cache")
+    ver = weights_version(module)
+    if c is None or c["version"] != ver:
+        c = {"version": ver, "runners": {}}
+        module.__dict__["_ou_cache"] = c
+    return c["runners"]
+
+
+# ------------------------------------------------------------------------------------ sigma embedding
+def embedding_spec(sb, device):
+    """Device-resident parameters of a SigmaBlock / SimpleTimeEmbedding (sigma_block.py:36-78)."""
+    if hasattr(sb, "freq"):
+        return ("rff", sb.freq.detach().float().to(device).contiguous(), [
+            (lyr.lin.weight.detach().float().to(device).contiguous(),
+             lyr.lin.bias.detach().float().to(device).contiguous(), fold.prelu_slope(lyr.prelu))
+            for lyr in (sb.layer1, sb.layer2, sb.layer3)])
+    return ("simple", float(sb.weight.detach().reshape(-1)[0].item()),
+            float(sb.bias.detach().reshape(-1)[0].item()))
+
+
+def sigma_embedding(spec, dim, log10_sigma):
+    L = lib.load()
+    ls = log10_sigma.contiguous().float()
+    device = ls.device
+    rows = ls.numel()
+    if spec[0] == "simple":
+        g = torch.empty(rows, dim, dtype=torch.float32, device=device)
+        lib.check(L.ou_sigma_embed_simple(_ptr(ls), spec[1], spec[2], _ptr(g), rows, dim // 2,
+                                          _stream()))
+        return g
+    _, freq, layers = spec
+    cur = torch.empty(rows, 2 * freq.numel(), dtype=torch.float32, device=device)
+    lib.check(L.ou_sigma_embed_rff(_ptr(ls), _ptr(freq), _ptr(cur), rows, freq.numel(), _stream()))
+    for w, b, slope in layers:
+        nxt = torch.empty(rows, w.shape[0], dtype=torch.float32, device=device)
+        lib.check(L.ou_linear_f32(_ptr(cur), _ptr(w), _ptr(b), _ptr(nxt), rows, w.shape[1],
+                                  w.shape[0], w.shape[0], 1, slope, _stream()))
+        cur = nxt
+    return cur
+
+
+# ------------------------------------------------------------------------------------ score net
+class ScoreRunner:
+    """ScoreNetwork lowered for a fixed (batch, length) and bound to device buffers."""
+
+    def __init__(self, net, batch, t, device):
+        self.batch, self.t, self.device = batch, t, device
+        with torch.no_grad():
+            self.prog = P.lower_score_network(net, batch, t)
+            self.proj = P.lower_cond_projection(net, batch, self.prog.meta["lengths"])
+            self.exe = Executor(self.prog, device)
+            # the projection program writes straight into the score program's 'sc{lvl}' buffers
+            self.proj_exe = Executor(self.proj, device,
+                                     external=[n for n in self.proj.bufs if n.startswith("sc")])
+            for name in self.proj.bufs:
+                if name.startswith("sc"):
+                    self.proj_exe.bufs[name] = self.exe.bufs[name]
+            self._prepare_embedding(net, device)
+        self.film = None
+        self.cond_lengths = self.prog.meta["lengths"]
+        self.cond_channels = self.prog.meta["cond_channels"]
+
+    def _prepare_embedding(self, net, device):
+        self.dim = net.noise_cond_dim
+        self.embed = embedding_spec(net.sigma_block, device)
+        ws, bs = [], []
+        for lin, off, cout in self.prog.film_layers:
+            assert off == sum(w.shape[0] for w in ws)
+            ws.append(fold.effective_weight(lin).float())
+            bs.append(lin.bias.detach().float())
+        self.film_w = torch.cat(ws).to(device).contiguous()
+        self.film_b = torch.cat(bs).to(device).contiguous()
+        self.film_cols = self.prog.film_cols
+
+    def sigma_embedding(self, log10_sigma):
+        """(rows,) fp32 log10 sigma -> (rows, noise_cond_dim) embedding g."""
+        return sigma_embedding(self.embed, self.dim, log10_sigma)
+
+    def set_sigmas(self, net_sigma):
+        """net_sigma: (rows,) sigma values fed to the network (after the EDM noise scaling).
+        Builds the FiLM table for all rows in two launches (embedding + one dense layer)."""
+        g = self.sigma_embedding(torch.log10(net_sigma.float()))
+        rows = g.shape[0]
+        film = torch.empty(rows, self.film_cols, dtype=torch.float32, device=self.device)
+        lib.check(lib.load().ou_linear_f32(_ptr(g), _ptr(self.film_w), _ptr(self.film_b), _ptr(film),
+                                           rows, self.dim, self.film_cols, self.film_cols, 0, 0.0,
+                                           _stream()))
+        self.film = film
+        return film
+
+    def set_cond(self, cond_blocked):
+        """cond_blocked: list of blocked bf16 conditioning tensors (coarsest first).  Runs the
+        step-invariant signal_cond_proj 1x1 convs once."""
+        for lvl, c in enumerate(cond_blocked):
+            want = (self.batch, self.cond_channels[lvl] // 8, self.cond_lengths[lvl], 8)
+            if tuple(c.shape) != want:
+                raise ValueError(f"conditioning tensor {lvl} has blocked shape {tuple(c.shape)}, "
+                                 f"expected {want}")
+            self.proj_exe.bufs[f"cond{lvl}"] = c
+        self.proj_exe.run()
+
+    def step(self, x, film_row, per_clip_film, in_scale=None, coef=None, noise=None, xout=None,
+             net_out=None):
+        """One network evaluation.  x: (B,1,T) fp32.  film_row: first row of the FiLM table to use
+        (one row shared by all clips, or B consecutive rows if per_clip_film)."""
+        self.exe.bufs["x"] = x
+        film = self.film[film_row:]
+        self.exe.run(film=film, film_bstride=self.film_cols if per_clip_film else 0,
+                     in_scale=in_scale, coef=coef, noise=noise, xout=xout, net_out=net_out)
+
+
+def get_score_runner(net, batch, t, device):
+    runners = _cache(net)
+    key = ("score", batch, t, str(device))
+    if key not in runners:
+        runners[key] = ScoreRunner(net, batch, t, device)
+    return runners[key]
+
+
+def score_forward(net, x, sigma, cond):
+    """ScoreNetwork.forward(x, sigma, cond) on reference-layout tensors (score.py:277-297)."""
+    require_cuda(x, sigma, *cond)
+    b, c, t = x.shape
+    if c != 1:
+        raise ValueError("ScoreNetwork expects a (B, 1, T) input")
+    r = get_score_runner(net, b, t, x.device)
+    with torch.no_grad():
+        r.set_sigmas(sigma.reshape(-1))
+        r.set_cond([pack_blocked(ci) for ci in cond])
+        out = torch.empty(b, 1, t, dtype=torch.float32, device=x.device)
+        r.step(x.contiguous().float(), 0, True, net_out=out)
+    return out
+
+
+# ------------------------------------------------------------------------------------ conditioner
+class ConditionerRunner:
+    def __init__(self, net, batch, t, device, need_signal_tail=True):
+        self.batch, self.t, self.device = batch, t, device
+        with torch.no_grad():
+            self.prog = P.lower_conditioner(net, batch, t, need_signal_tail)
+            self.exe = Executor(self.prog, device)
+        self.n_cond = len([k for k in self.prog.outputs if k.startswith("cond")])
+
+    def run(self, x, x_wav=None):
+        self.exe.bufs["x"] = x
+        self.exe.bufs["x_wav"] = x if x_wav is None else x_wav
+        self.exe.run()
+        out = self.prog.outputs
+        cond = [self.exe.bufs[out[f"cond{i}"]] for i in range(self.n_cond)]
+        y_hat = self.exe.bufs[out["y_hat"]] if "y_hat" in out else None
+        return cond, y_hat, self.exe.bufs[out["h"]]
+
+
+def get_conditioner_runner(net, batch, t, device, need_signal_tail=True):
+    runners = _cache(net)
+    key = ("cond", batch, t, str(device), need_signal_tail)
+    if key not in runners:
+        runners[key] = ConditionerRunner(net, batch, t, device, need_signal_tail)
+    return runners[key]
+
+
+def conditioner_forward(net, x, x_wav=None):
+    """ConditionerNetwork.forward on reference-layout tensors -> (conditions, y_hat, h) fp32."""
+    require_cuda(x, x_wav)
+    b, c, t = x.shape
+    if c != 1:
+        raise ValueError("ConditionerNetwork expects a (B, 1, T) input")
+    r = get_conditioner_runner(net, b, t, x.device, True)
+    with torch.no_grad():
+        cond, y_hat, h = r.run(x.contiguous().float(),
+                               None if x_wav is None else x_wav.contiguous().float())
+        cond = [unpack_blocked(ci) for ci in cond]
+        y_hat = unpack_blocked(y_hat)
+        y_hat = torch.nn.functional.pad(y_hat, (0, t - y_hat.shape[-1]))
+        return cond, y_hat, unpack_blocked(h)
+
+
+def compute_mel_spec(mel_adapter, x):
+    """MelAdapter.compute_mel_spec (condition.py:92-108): (B,1,T) -> (B, n_mels, frames) fp32."""
+    require_cuda(x)
+    b, _, t = x.shape
+    hop = mel_adapter.ds_factor
+    frames = P.ceil_div(t, hop)
+    prog = P.Program(b)
+    op = P.MelOp("mel", "x", "mel", mel_adapter.n_fft, hop, mel_adapter.n_mels, mel_adapter.pad_left,
+                 frames, t, mel_adapter.mel_spec.spectrogram.window.detach().float(),
+                 mel_adapter.mel_spec.mel_scale.fb.detach().float())
+    prog.ops.append(op)
+    prepare_ops(prog, x.device)
+    pk = op.packed
+    L = lib.load()
+    xc = x.contiguous().float()
+    lib.check(L.ou_mel_power(_ptr(xc), _ptr(pk["window"]), _ptr(pk["fb"]), _ptr(pk["twiddle"]),
+                             _ptr(pk["mel"]), _ptr(pk["energy"]), b, t, op.n_fft, hop, op.n_mels,
+                             op.pad_left, frames, _stream()))
+    lib.check(L.ou_mel_finalize(_ptr(pk["mel"]), _ptr(pk["energy"]), _ptr(pk["mel"]), None, b,
+                                op.n_mels, frames, _stream()))
+    return pk["mel"]
+
+
+# ------------------------------------------------------------------------------------ block-level
+def conv_block_forward(blk, h, noise_cond=None, input_cond=None, res=None, length=None):
+    """ConvBlock.forward on (B, C, T) fp32 tensors -> (h_out, skip, cond_out)  (blocks.py:327-412).
+    Layer-level entry point (parity tests, LoRA-style consumers); the networks never call it."""
+    require_cuda(h, noise_cond, input_cond, res)
+    b, c, t = h.shape
+    prog = P.Program(b)
+    prog.buf("in", "blocked", c, t)
+    src = "in"
+    bufs_in = {"in": pack_blocked(h)}
+    if res is not None and blk.rate_change_dir == "none":
+        # rate-preserving block: the network lowering folds this add into the producer; do it here
+        bufs_in["in"] = pack_blocked((h + res) * P.SQRT_HALF)
+        res = None
+    film_lin = None
+    if noise_cond is not None:
+        film_lin = _FilmPassthrough(blk.n_channels)
+    if input_cond is not None:
+        prog.buf("icond", "blocked", blk.n_channels, input_cond.shape[-1])
+        bufs_in["icond"] = pack_blocked(input_cond)
+    if res is not None:
+        prog.buf("res", "blocked", blk.n_channels, res.shape[-1])
+        bufs_in["res"] = pack_blocked(res)
+    with torch.no_grad():
+        out, _, skip, cond = P.lower_conv_block(
+            prog, blk, "blk", src, t, film_linear=film_lin,
+            input_cond="icond" if input_cond is not None else None,
+            res="res" if res is not None else None, length=length, raw_cond_out=True)
+        exe = Executor(prog, h.device, external=list(bufs_in))
+        exe.bufs.update(bufs_in)
+        film = noise_cond.contiguous().float() if noise_cond is not None else None
+        exe.run(film=film, film_bstride=2 * blk.n_channels)
+        return (unpack_blocked(exe.bufs[out]), unpack_blocked(exe.bufs[skip]),
+                unpack_blocked(exe.bufs[cond]))
+
+
+class _FilmPassthrough:
+    """Marker so that ``lower_conv_block`` allocates FiLM columns when the caller passes the
+    already-projected (B, 2C) vector (ConvBlock.forward's ``noise_cond``)."""
+
+    def __init__(self, c):
+        self.c = c
+
+
+def prelu_conv_forward(pc, x):
+    """PReLU_Conv.forward on a (B, C, T) fp32 tensor (blocks.py:205-227)."""
+    require_cuda(x)
+    if pc.act_type != "prelu":
+        raise NotImplementedError("only act_type='prelu' has a kernel")
+    b, c, t = x.shape
+    if pc.stride == 1 and pc.padding != "same":
+        raise NotImplementedError("stride-1 PReLU_Conv is only used with padding='same' upstream")
+    prog = P.Program(b)
+    prog.buf("in", "blocked", c, t)
+    with torch.no_grad():
+        fc = fold.fold_prelu_conv(pc)
+        dst, _ = P.add_conv(prog, "pc", "in", "out", fc, t)
+        exe = Executor(prog, x.device, external=["in"])
+        exe.bufs["in"] = pack_blocked(x)
+        exe.run()
+        return unpack_blocked(exe.bufs[dst])
+
+
+def film(x, y):
+    require_cuda(x, y)
+    b, c, t = x.shape
+    out = torch.empty_like(x, dtype=torch.float32)
+    lib.check(lib.load().ou_film_f32(_ptr(x.contiguous().float()), _ptr(y.contiguous().float()),
+                                     _ptr(out), b, c, t, _stream()))
+    return out
+
+
+def lowpass(x, taps):
+    raise NotImplementedError(
+        "BinomialAntiAlias is folded into the rate-change conv weights (engine.fold); it has no "
+        "standalone kernel")
+
+
+def sigma_embed(block, log10_sigma):
+    """sigma_block(log10 sigma) -> (B, noise_cond_dim) fp32 (sigma_block.py:50-57, 73-78)."""
+    require_cuda(log10_sigma)
+    with torch.no_grad():
+        return sigma_embedding(embedding_spec(block, log10_sigma.device), block.n_dim,
+                               log10_sigma.reshape(-1))

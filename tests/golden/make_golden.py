@@ -29,6 +29,12 @@ torch.set_num_threads(8)
 _models = {}
 
 
+def _named_model_parameters(model):
+    """Names in the order of model.model_parameters()."""
+    by_id = {id(p): k for k, p in model.named_parameters()}
+    return [(by_id[id(p)], p) for p in model.model_parameters()]
+
+
 def get_model(name):
     if name in _models:
         return _models[name]
@@ -41,6 +47,10 @@ def get_model(name):
         "class": type(model).__name__,
         "manifest": manifest,
         "buffers": sorted(k for k in manifest if k not in param_names),
+        # order matters: torch_ema stores its shadow params as a positional list in the order
+        # of Universe.model_parameters() (universe.py:130-133, universe_gan.py:136-143)
+        "ema_param_order": [k for k, _ in _named_model_parameters(model)],
+        "state_dict_order": [k for k in sd if not k.startswith("loss_")],
         "n_loss_keys": sum(k.startswith("loss_") for k in sd),
     }
     (HERE / f"{name}_manifest.json").write_text(json.dumps(meta, indent=0, sort_keys=True))
