@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""bench.py -- headline metric of BASELINE.json: audio-seconds/sec of UNIVERSE++ 16 kHz enhance().
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one full ``model.enhance()`` call on one batch of synthetic clips
+(BASELINE.json configs[1]: 32 clips x 8 s, 64 diffusion steps, per GPU -- weak scaling: every
+rank enhances its own 32 clips; with N>1 the results are all-gathered once per call as in
+``open_universe_b200.parallel``).  Weights are random-init UNIVERSE++ 16 kHz (the reference's
+init scheme, seeded); inputs are 0.05 * white noise (north_star: "synthetic white-noise inputs").
+
+Printed JSON (one line, rank 0):
+  value        audio-s/s with inputs resident in HBM (device-timed, max over ranks)
+  e2e          same metric through the public API with HOST buffers: pinned host -> device copy
+               of the batch and device -> host copy of the result inside the timed region
+  roofline     tensor-pipe roofline of the dominant kernel (fused implicit-GEMM conv), from CUDA
+               events recorded around every launch of it on the launching stream
+  cpu_baseline the CPU oracle (port of the reference path) timed on this box's host cores on a
+               bounded sample, extrapolated with the affine step model of BASELINE.md 3b
+``--impl reference`` times that CPU path alone (rank 0 only) and prints the same line shape.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+FS = 16000
+CLIP_SECONDS = 8.0
+BATCH = 32
+DIFFUSION_STEPS = 64
+METRIC = "audio-seconds/sec (RTF) UNIVERSE++ 16k enhance, batch32x8s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--seconds", type=float, default=CLIP_SECONDS)
+    ap.add_argument("--diffusion-steps", type=int, default=DIFFUSION_STEPS)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-kernel-events", action="store_true")
+    return ap.parse_args()
+
+
+def workload(args):
+    return {"workload": f"UNIVERSE++ 16 kHz enhance(), {args.batch} x {args.seconds:g} s clips per GPU, "
+                        f"{args.diffusion_steps} diffusion steps (BASELINE.json configs[1])",
+            "batch_per_gpu": args.batch, "clip_seconds": args.seconds,
+            "diffusion_steps": args.diffusion_steps, "fs": FS,
+            "weights": "random init (reference init scheme, seed 0)",
+            "l2": "no explicit flush: one step streams > 4 GB of activations, >> 126 MB L2"}
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return d.get("bf16_tflops_sustained", 1377.1), d.get("hbm_gbs", 6543.7), "measured"
+    return 1400.0, 6650.0, "fallback"
+
+
+# --------------------------------------------------------------------------------- CPU reference
+def cpu_affine_sample(n_lo=2, n_hi=4, seconds=CLIP_SECONDS, diffusion_steps=DIFFUSION_STEPS, batch=BATCH):
+    """Time the CPU oracle on 1 clip at two small step counts and extrapolate with t = a + b*N
+    (cost is exactly affine in N: one conditioner pass + N identical score passes)."""
+    import torch
+    from open_universe_b200.config import builtin_config, instantiate
+    from oracle.universe_oracle import UniverseOracle
+    torch.set_num_threads(os.cpu_count())
+    torch.manual_seed(0)
+    cfg = builtin_config("universepp_16k").model
+    model = instantiate(cfg, _recursive_=False)
+    o = UniverseOracle(cfg, model.state_dict())
+    g = torch.Generator().manual_seed(0)
+    mix = 0.05 * torch.randn(1, int(FS * seconds), generator=g)
+    times = {}
+    with torch.no_grad():
+        for n in (n_lo, n_hi):
+            t0 = time.perf_counter()
+            o.enhance(mix, n_steps=n, rng=torch.Generator().manual_seed(1028282))
+            times[n] = time.perf_counter() - t0
+    b = (times[n_hi] - times[n_lo]) / (n_hi - n_lo)
+    a = times[n_lo] - n_lo * b
+    t_clip = a + b * diffusion_steps
+    return {"value": seconds / t_clip, "t_clip_s": t_clip, "t_batch_s": t_clip * batch,
+            "fit": {"a_s": a, "b_s_per_step": b, "raw_s": {str(k): v for k, v in times.items()}},
+            "cores": os.cpu_count()}
+
+
+def cpu_baseline_block(args):
+    s = cpu_affine_sample(seconds=args.seconds, diffusion_steps=args.diffusion_steps, batch=args.batch)
+    return {"value": round(s["value"], 5), "unit": "audio-s/s", "cores": s["cores"], "kind": "port",
+            "sample": f"oracle/universe_oracle.py on CPU (torch, {s['cores']} threads): 1 clip x "
+                      f"{args.seconds:g} s at 2 and 4 diffusion steps, affine fit t=a+b*N "
+                      f"(a={s['fit']['a_s']:.2f}s, b={s['fit']['b_s_per_step']:.2f}s/step) extrapolated to "
+                      f"{args.diffusion_steps} steps; per-clip cost, batch scales linearly",
+            "fit": s["fit"]}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; the
+    reference itself is pure Python/PyTorch and cannot travel to the GPU box)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals, fits = [], []
+    for i in range(args.warmup + args.steps):
+        s = cpu_affine_sample(seconds=args.seconds, diffusion_steps=args.diffusion_steps,
+                              batch=args.batch)
+        if i >= args.warmup:
+            vals.append(s)
+    v = statistics.median(x["value"] for x in vals)
+    t_batch = statistics.median(x["t_batch_s"] for x in vals)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(v, 5), "unit": "audio-s/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(t_batch * 1e3, 1), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload(args),
+        "cpu_baseline": {"value": round(v, 5), "unit": "audio-s/s", "cores": os.cpu_count(),
+                         "kind": "port",
+                         "sample": "each step: 1 clip x 8 s at 2 and 4 diffusion steps on all host "
+                                   "threads, affine fit extrapolated to 64 steps; ms_per_step is the "
+                                   "projected time of the full 32-clip batch"},
+        "e2e": {"value": round(v, 5), "unit": "audio-s/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                 "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                power.append(float(r[2]))
+                for name, val in zip(names, r[3:7]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            except (ValueError, IndexError):
+                continue
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from open_universe_b200.config import builtin_config, instantiate
+    from open_universe_b200.engine import lib, runtime
+    from open_universe_b200.engine import program as P
+    from open_universe_b200 import parallel
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib.load()
+
+    torch.manual_seed(0)
+    model = instantiate(builtin_config("universepp_16k").model, _recursive_=False)
+    model.eval(no_ema=True)
+    model = model.to(dev)
+    B, T, NS = args.batch, int(FS * args.seconds), args.diffusion_steps
+    g = torch.Generator().manual_seed(100 + rank)
+    host_mix = (0.05 * torch.randn(B, T, generator=g)).pin_memory()
+    host_out = torch.empty(B, T).pin_memory()
+    dev_mix = host_mix.to(dev)
+    rng = torch.Generator(device=dev).manual_seed(1028282 + rank)
+
+    def step_resident():
+        y = model.enhance(dev_mix, n_steps=NS, rng=rng)
+        if world > 1:
+            y = parallel.gather_rows(y, B, B * world)
+        return y
+
+    def step_e2e():
+        x = host_mix.to(dev, non_blocking=True)
+        y = model.enhance(x, n_steps=NS, rng=rng)
+        if world > 1:
+            y = parallel.gather_rows(y, B, B * world)[rank * B:(rank + 1) * B]
+        host_out.copy_(y, non_blocking=True)
+        return host_out
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, k, profile=False):
+        barrier()
+        runtime.PROFILE = [] if profile else None
+        launches0 = lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = lib.launch_count() - launches0
+        prof, runtime.PROFILE = runtime.PROFILE, None
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+            c = torch.tensor([launches], device=dev, dtype=torch.int64)
+            dist.all_reduce(c, op=dist.ReduceOp.SUM)
+            launches = int(c.item())
+        return ms, launches, prof
+
+    for _ in range(args.warmup):
+        step_resident()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms, launches, prof = timed(step_resident, args.steps, profile=not args.no_kernel_events)
+    clocks = sampler.stop() if sampler else None
+    step_e2e()
+    ms_e2e, _, _ = timed(step_e2e, args.steps)
+
+    audio_s = B * args.seconds * world
+    value = audio_s / (ms / args.steps / 1e3)
+    e2e_value = audio_s / (ms_e2e / args.steps / 1e3)
+
+    tflops_peak, hbm_peak, which = peaks()
+    roof = None
+    if prof:
+        tot_ms = sum(e0.elapsed_time(e1) for _, e0, e1 in prof)
+        algo = sum(op.flops_algo for op, _, _ in prof)
+        execd = sum(op.flops_exec for op, _, _ in prof)
+        n = len(prof)
+        achieved = algo / (tot_ms * 1e-3) / 1e12
+        roof = {"kernel": "conv1d_mma_kernel (fused implicit-GEMM Conv1d, all launches of the timed region)",
+                "bound": "tensor", "achieved": round(achieved, 2), "peak": tflops_peak,
+                "unit": "TFLOP/s", "frac": round(achieved / tflops_peak, 4), "traffic": None,
+                "peak_source": f"{which} bf16_tflops_sustained (kernel timed inside a long step)",
+                "launches": n, "avg_launch_us": round(tot_ms * 1e3 / n, 2),
+                "algorithmic_gflop_per_launch": round(algo / n / 1e9, 3),
+                "executed_tflops": round(execd / (tot_ms * 1e-3) / 1e12, 2),
+                "share_of_step": round(tot_ms / ms, 4)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": round(value, 2), "unit": "audio-s/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 2),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic", "config": workload(args), "clocks": clocks,
+            "e2e": {"value": round(e2e_value, 2), "unit": "audio-s/s",
+                    "h2d_bytes_per_step": B * T * 4 * world, "d2h_bytes_per_step": B * T * 4 * world,
+                    "ms_per_step": round(ms_e2e / args.steps, 2)},
+            "gpu_launches": launches, "roofline": roof,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_block(args)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -59,6 +59,8 @@ class ConvOp:
     prelu_out: Optional[float] = None
     prelu_out2: Optional[float] = None
     dst_kind: str = "blocked"
+    flops_exec: float = 0.0                   # FLOPs the kernel executes (folded low-pass included)
+    flops_algo: float = 0.0                   # FLOPs of the reference graph for the same layer
     packed: Optional[dict] = None             # device tensors filled in by the runtime
 
 
@@ -163,7 +165,17 @@ def add_conv(prog, name, src, dst, fc, t_in, t_out=None, **kw):
         prog.buf(dst, "blocked", fc.cout, t_out)
     else:
         prog.buf(dst, "f32_tm", fc.n, rows)
-    prog.ops.append(ConvOp(name, src, dst, fc, t_in, t_out, rows, **kw))
+    op = ConvOp(name, src, dst, fc, t_in, t_out, rows, **kw)
+    op.flops_exec = 2.0 * prog.batch * rows * fc.n * fc.taps * fc.s * fc.cin
+    if fc.taps == 3 and (fc.s > 1 or fc.up > 1):
+        # anti-alias low-pass folded into the rate-change conv: the reference graph runs a k=s
+        # conv (1/3 of the folded taps) plus a (2s+1)-tap depthwise FIR (blocks.py:205-227)
+        rate = max(fc.s, fc.up)
+        fir = fc.cin * t_in if fc.s > 1 else fc.cout * t_out
+        op.flops_algo = op.flops_exec / 3.0 + 2.0 * prog.batch * (2 * rate + 1) * fir
+    else:
+        op.flops_algo = op.flops_exec
+    prog.ops.append(op)
     return dst, t_out
 
 

@@ -101,6 +101,10 @@ def prepare_ops(prog, device):
 
 
 # ------------------------------------------------------------------------------------ op launch
+# bench.py sets this to a list to time every conv launch with CUDA events on the launching stream
+PROFILE = None
+
+
 def launch_conv(op, bufs, batch, gamma=None, beta=None, film_bstride=0, naive=False):
     fc, pk = op.fc, op.packed
     prm = lib.ConvParams()
@@ -129,6 +133,13 @@ def launch_conv(op, bufs, batch, gamma=None, beta=None, film_bstride=0, naive=Fa
     prm.prelu_out2 = op.prelu_out2 or 0.0
     prm.scale1, prm.scale2 = op.scale1, op.scale2
     fn = lib.load().ou_conv1d_naive if naive else lib.load().ou_conv1d
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        lib.check(fn(byref(prm), _stream()))
+        e1.record()
+        PROFILE.append((op, e0, e1))
+        return
     lib.check(fn(byref(prm), _stream()))
 
 

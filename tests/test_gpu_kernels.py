@@ -1,0 +1,221 @@
+"""Per-kernel parity on the GPU: every C-ABI entry point against the PyTorch emulator / oracle.
+
+Tolerances: bit-level agreement is not expected for floating point -- the tensor-core kernel
+accumulates in a different order than ATen.  The kernel and the emulator round to bf16 at the
+SAME points, so they agree to ~1e-3 of the tensor RMS (a few bf16 ulp flips); fp32-only kernels
+agree to ~1e-5.
+"""
+import math
+
+import pytest
+import torch
+
+from common import rel_rms
+from oracle import emulator as E
+from oracle import universe_oracle as O
+from open_universe_b200.engine import lib, program as P, runtime as R
+from open_universe_b200.engine.fold import FoldedConv
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def bf(x):
+    return x.to(torch.bfloat16).float()
+
+
+def rand_fc(g, cin, cout, s=1, up=1, taps=1, tap_off=0, prelu_in=None):
+    w = torch.randn(up * cout, taps, s * cin, generator=g) / math.sqrt(taps * s * cin)
+    return FoldedConv(w, 0.1 * torch.randn(up * cout, generator=g), cin, cout, s, up, taps, tap_off,
+                      prelu_in)
+
+
+CONV_CASES = [
+    # cin, cout, s, up, taps, off, t_in, B, options
+    dict(cin=32, cout=32, taps=5, off=-2, t=1000, B=2, prelu_in=0.2, film=True, prelu_out=0.3),
+    dict(cin=64, cout=64, taps=3, off=-1, t=777, B=1, add1=True, prelu_out=0.1, prelu_out2=-0.2),
+    dict(cin=128, cout=128, taps=5, off=-2, t=300, B=3, add1=True, add2=True),
+    dict(cin=512, cout=512, taps=3, off=-1, t=51, B=2, prelu_in=0.25),
+    dict(cin=32, cout=64, s=2, taps=3, off=-1, t=1001, B=2, prelu_in=0.25),          # anti-aliased down
+    dict(cin=256, cout=512, s=5, taps=1, off=0, t=403, B=1, prelu_in=0.3),           # plain down
+    dict(cin=64, cout=32, up=2, taps=3, off=-1, t=500, B=2, prelu_in=0.2, add1=True, t_out=999),
+    dict(cin=512, cout=256, up=5, taps=1, off=0, t=40, B=1, add1=True),              # plain up
+    dict(cin=32, cout=512, s=160, taps=1, off=0, t=3200, B=2, prelu_in=0.25, add1=True),  # st_conv
+    dict(cin=80, cout=512, taps=3, off=-1, t=60, B=1),                               # mel conv (K pad)
+    dict(cin=48, cout=96, s=2, taps=3, off=-1, t=601, B=1, prelu_in=0.25),           # 24 kHz widths
+    dict(cin=96, cout=48, up=2, taps=3, off=-1, t=300, B=1, add1=True),
+    dict(cin=512, cout=1536, taps=1, off=0, t=100, B=2, f32_tm=True),                # GRU x-proj
+]
+
+
+@pytest.mark.parametrize("c", CONV_CASES, ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items()))
+def test_conv1d_vs_emulator(c):
+    g = torch.Generator().manual_seed(1234)
+    B, cin, cout, t = c["B"], c["cin"], c["cout"], c["t"]
+    s, up = c.get("s", 1), c.get("up", 1)
+    fc = rand_fc(g, cin, cout, s, up, c["taps"], c["off"], c.get("prelu_in"))
+    prog = P.Program(B)
+    prog.buf("in", "blocked", cin, t)
+    kw = {}
+    t_out = c.get("t_out")
+    if c.get("f32_tm"):
+        kw["dst_kind"] = "f32_tm"
+    dst, t_out = P.add_conv(prog, "c", "in", "out", fc, t, t_out, **kw)
+    op = prog.ops[0]
+    x = bf(torch.randn(B, cin, t, generator=g))
+    inputs = {"in": x}
+    for name in ("add1", "add2"):
+        if c.get(name):
+            prog.buf(name, "blocked", cout, t_out)
+            setattr(op, name, name)
+            inputs[name] = bf(torch.randn(B, cout, t_out, generator=g))
+    op.scale1, op.scale2 = 0.7071, 0.5 if c.get("add2") else 1.0
+    film = None
+    if c.get("film"):
+        op.film_off = 0
+        film = torch.randn(B, 2 * cout, generator=g)
+    op.prelu_out, op.prelu_out2 = c.get("prelu_out"), c.get("prelu_out2")
+
+    bufs, _, _ = E.run_program(prog, inputs, film=film, quant=True)
+    want = bufs["out"]
+
+    exe = R.Executor(prog, DEV, external=list(inputs))
+    for k, v in inputs.items():
+        exe.bufs[k] = R.pack_blocked(v.to(DEV))
+    film_d = film.to(DEV).contiguous() if film is not None else None
+    for naive in (True, False):
+        exe.naive = naive
+        exe.run(film=film_d, film_bstride=2 * cout)
+        got = exe.bufs["out"]
+        got = got.float().cpu() if c.get("f32_tm") else R.unpack_blocked(got).cpu()
+        assert got.shape == want.shape
+        err = rel_rms(got, want)
+        assert err < 3e-3, (naive, err)
+
+
+@pytest.mark.parametrize("hidden,B,T,add", [(256, 5, 37, True), (128, 2, 20, False),
+                                            (384, 3, 25, True), (256, 32, 801, True)])
+def test_gru_vs_explicit(hidden, B, T, add):
+    g = torch.Generator().manual_seed(7)
+    H = hidden
+    gx = torch.randn(B, T, 6 * H, generator=g)
+    w_hh = torch.randn(2, 3 * H, H, generator=g) / math.sqrt(H)
+    b_hh = 0.1 * torch.randn(2, 3 * H, generator=g)
+    addt = bf(torch.randn(B, 2 * H, T, generator=g)) if add else None
+    op = P.GruOp("g", "gx", "out", w_hh, b_hh, H, T, add="add" if add else None, scale=0.7071)
+    bufs = {"gx": gx}
+    if add:
+        bufs["add"] = addt
+    E.run_gru(op, bufs, quant=False)
+    want = bufs["out"]
+    out = torch.empty(B, 2 * H // 8, T, 8, dtype=torch.bfloat16, device=DEV)
+    lib.check(lib.load().ou_gru_bidir(R._ptr(gx.to(DEV)), R._ptr(w_hh.to(DEV)), R._ptr(b_hh.to(DEV)),
+                                      R._ptr(R.pack_blocked(addt.to(DEV)) if add else None), 0.7071,
+                                      R._ptr(out), B, T, H, R._stream()))
+    got = R.unpack_blocked(out).cpu()
+    assert rel_rms(got, want) < 3e-3   # bf16 output rounding only
+
+
+@pytest.mark.parametrize("fs_cfg", [dict(n_fft=640, hop=160, n_mels=80), dict(n_fft=960, hop=240, n_mels=128)])
+@pytest.mark.parametrize("T", [3200, 5003])
+def test_mel_vs_oracle(fs_cfg, T):
+    g = torch.Generator().manual_seed(3)
+    B = 2
+    x = 0.05 * torch.randn(B, 1, T, generator=g)
+    rates = [2, 4, 4, 5] if fs_cfg["hop"] == 160 else [2, 3, 5, 8]
+    cfg = dict(rate_factors=rates, n_mel_oversample=4, n_mels=fs_cfg["n_mels"])
+    want = O.mel_spec(cfg, x)
+
+    class Mel:  # minimal MelAdapter view
+        pass
+    from open_universe_b200.networks.universe.condition import MelAdapter
+    m = MelAdapter(fs_cfg["n_mels"], 64, fs_cfg["hop"], 4).to(DEV)
+    got = m.compute_mel_spec(x.to(DEV)).cpu()
+    assert got.shape == want.shape
+    assert rel_rms(got, want) < 2e-5
+
+
+@pytest.mark.parametrize("T,tot", [(8000, 160), (4800, 160), (7000, 240)])
+def test_pad_normalize_and_unpad(T, tot):
+    g = torch.Generator().manual_seed(5)
+    B = 3
+    mix = 0.3 * torch.randn(B, 1, T, generator=g) + 0.01
+    pad = tot - T % tot
+    t_pad = T + pad
+    level = 10 ** (-26 / 20)
+    xp = torch.nn.functional.pad(mix, (pad // 2, pad - pad // 2))
+    xp = xp - xp.mean(dim=(1, 2), keepdim=True)
+    want = xp * (level / xp.std(dim=(1, 2), keepdim=True).clamp(min=1e-5))
+    out = torch.empty(B, 1, t_pad, device=DEV)
+    L = lib.load()
+    lib.check(L.ou_pad_normalize(R._ptr(mix.to(DEV)), R._ptr(out), None, B, T, t_pad, pad // 2, level,
+                                 R._stream()))
+    assert rel_rms(out.cpu(), want) < 1e-5
+    # unpad + keep_rms + limiter
+    x = 30.0 * want * torch.tensor([1.0, 0.001, 100.0])[:, None, None]
+    mix_rms = mix.square().mean(dim=(-2, -1)).sqrt()
+    for keep in (False, True):
+        y = x[..., pad // 2: -(pad - pad // 2)]
+        if keep:
+            y = y * (mix_rms[:, None, None] / y.square().mean(dim=(-2, -1), keepdim=True).sqrt().clamp(min=1e-5))
+        sc = y.abs().max(dim=-1, keepdim=True).values
+        y = torch.where(sc > 1.0, y / sc, y)
+        o = torch.empty(B, 1, T, device=DEV)
+        lib.check(L.ou_unpad_limit(R._ptr(x.to(DEV).contiguous()), R._ptr(mix_rms.to(DEV)) if keep else None,
+                                   R._ptr(o), B, t_pad, pad // 2, T, T, R._stream()))
+        assert rel_rms(o.cpu(), y) < 1e-5
+
+
+def test_input_and_output_kernels():
+    g = torch.Generator().manual_seed(9)
+    B, T, C = 2, 1003, 32
+    x = torch.randn(B, 1, T, generator=g)
+    w = torch.randn(C, 3, generator=g)
+    b = torch.randn(C, generator=g)
+    sc = torch.tensor([0.5, 2.0])
+    want = torch.nn.functional.conv1d(x * sc[:, None, None], w[:, None, :], b, padding="same")
+    out = torch.empty(B, C // 8, T, 8, dtype=torch.bfloat16, device=DEV)
+    L = lib.load()
+    lib.check(L.ou_input_conv(R._ptr(x.to(DEV)), R._ptr(w.to(DEV)), R._ptr(b.to(DEV)), R._ptr(sc.to(DEV)),
+                              R._ptr(out), B, T, C, 3, R._stream()))
+    assert rel_rms(R.unpack_blocked(out).cpu(), bf(want)) < 1e-3
+    # output conv + SDE update
+    src = bf(torch.randn(B, C, T - 3, generator=g))
+    wo = torch.randn(C, 3, generator=g) / 10
+    coef = torch.randn(B, 3, generator=g)
+    noise = torch.randn(B, 1, T, generator=g)
+    net = torch.nn.functional.conv1d(src, wo[None], None, padding="same") + 0.3
+    net = torch.nn.functional.pad(net, (0, 3))
+    xnew = coef[:, 0, None, None] * x + coef[:, 1, None, None] * net + coef[:, 2, None, None] * noise
+    xo = torch.empty(B, 1, T, device=DEV)
+    no = torch.empty(B, 1, T, device=DEV)
+    lib.check(L.ou_output_sde(R._ptr(R.pack_blocked(src.to(DEV))), R._ptr(wo.to(DEV)), 0.3,
+                              R._ptr(coef.to(DEV)), R._ptr(x.to(DEV)), R._ptr(noise.to(DEV)), R._ptr(xo),
+                              R._ptr(no), B, C, 3, T - 3, T, R._stream()))
+    assert rel_rms(no.cpu(), net) < 1e-5
+    assert rel_rms(xo.cpu(), xnew) < 1e-5
+
+
+def test_sigma_embeddings_and_linear():
+    from open_universe_b200.networks.universe.sigma_block import SigmaBlock, SimpleTimeEmbedding
+    torch.manual_seed(0)
+    ls = torch.log10(torch.tensor([5.0, 0.3, 0.0005, 0.0125]))
+    s = SimpleTimeEmbedding(512)
+    with torch.no_grad():
+        s.weight.fill_(0.7)
+        s.bias.fill_(0.2)
+    sd = {"p.weight": s.weight.detach(), "p.bias": s.bias.detach()}
+    want = O.sigma_embedding({"time_embedding": "simple", "noise_cond_dim": 512}, sd, "p", ls)
+    got = s.to(DEV)(ls.to(DEV)).cpu()
+    assert (got - want).abs().max() < 2e-4      # fp32 phase up to ~800 rad: 1 ulp of phase = 6e-5
+    r = SigmaBlock(32, 512)
+    sd = {"p." + k: v.detach() for k, v in r.state_dict().items()}
+    want = O.sigma_embedding({"noise_cond_dim": 512}, sd, "p", ls)
+    got = r.to(DEV)(ls.to(DEV)).cpu()
+    assert rel_rms(got, want) < 1e-3
+
+
+def test_cpu_tensors_raise():
+    from open_universe_b200.config import builtin_config, instantiate
+    with pytest.raises(R.NoCudaPathError):
+        R.pack_blocked(torch.zeros(1, 8, 4))
