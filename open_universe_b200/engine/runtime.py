@@ -491,8 +491,8 @@ def film(x, y):
     require_cuda(x, y)
     b, c, t = x.shape
     out = torch.empty_like(x, dtype=torch.float32)
-    lib.check(lib.load().ou_film_f32(_ptr(x.contiguous().float()), _ptr(y.contiguous().float()),
-                                     _ptr(out), b, c, t, _stream()))
+    xc, yc = x.contiguous().float(), y.contiguous().float()   # keep alive across the launch
+    lib.check(lib.load().ou_film_f32(_ptr(xc), _ptr(yc), _ptr(out), b, c, t, _stream()))
     return out
 
 

@@ -109,9 +109,12 @@ def test_gru_vs_explicit(hidden, B, T, add):
     E.run_gru(op, bufs, quant=False)
     want = bufs["out"]
     out = torch.empty(B, 2 * H // 8, T, 8, dtype=torch.bfloat16, device=DEV)
-    lib.check(lib.load().ou_gru_bidir(R._ptr(gx.to(DEV)), R._ptr(w_hh.to(DEV)), R._ptr(b_hh.to(DEV)),
-                                      R._ptr(R.pack_blocked(addt.to(DEV)) if add else None), 0.7071,
+    # keep every device tensor referenced until the kernel has run (raw pointers are passed)
+    d_gx, d_w, d_b = gx.to(DEV), w_hh.to(DEV), b_hh.to(DEV)
+    d_add = R.pack_blocked(addt.to(DEV)) if add else None
+    lib.check(lib.load().ou_gru_bidir(R._ptr(d_gx), R._ptr(d_w), R._ptr(d_b), R._ptr(d_add), 0.7071,
                                       R._ptr(out), B, T, H, R._stream()))
+    torch.cuda.synchronize()
     got = R.unpack_blocked(out).cpu()
     assert rel_rms(got, want) < 3e-3   # bf16 output rounding only
 
@@ -148,8 +151,10 @@ def test_pad_normalize_and_unpad(T, tot):
     want = xp * (level / xp.std(dim=(1, 2), keepdim=True).clamp(min=1e-5))
     out = torch.empty(B, 1, t_pad, device=DEV)
     L = lib.load()
-    lib.check(L.ou_pad_normalize(R._ptr(mix.to(DEV)), R._ptr(out), None, B, T, t_pad, pad // 2, level,
+    d_mix = mix.to(DEV)
+    lib.check(L.ou_pad_normalize(R._ptr(d_mix), R._ptr(out), None, B, T, t_pad, pad // 2, level,
                                  R._stream()))
+    torch.cuda.synchronize()
     assert rel_rms(out.cpu(), want) < 1e-5
     # unpad + keep_rms + limiter
     x = 30.0 * want * torch.tensor([1.0, 0.001, 100.0])[:, None, None]
@@ -161,8 +166,10 @@ def test_pad_normalize_and_unpad(T, tot):
         sc = y.abs().max(dim=-1, keepdim=True).values
         y = torch.where(sc > 1.0, y / sc, y)
         o = torch.empty(B, 1, T, device=DEV)
-        lib.check(L.ou_unpad_limit(R._ptr(x.to(DEV).contiguous()), R._ptr(mix_rms.to(DEV)) if keep else None,
-                                   R._ptr(o), B, t_pad, pad // 2, T, T, R._stream()))
+        d_x, d_rms = x.to(DEV).contiguous(), mix_rms.to(DEV)
+        lib.check(L.ou_unpad_limit(R._ptr(d_x), R._ptr(d_rms) if keep else None, R._ptr(o), B, t_pad,
+                                   pad // 2, T, T, R._stream()))
+        torch.cuda.synchronize()
         assert rel_rms(o.cpu(), y) < 1e-5
 
 
@@ -176,8 +183,10 @@ def test_input_and_output_kernels():
     want = torch.nn.functional.conv1d(x * sc[:, None, None], w[:, None, :], b, padding="same")
     out = torch.empty(B, C // 8, T, 8, dtype=torch.bfloat16, device=DEV)
     L = lib.load()
-    lib.check(L.ou_input_conv(R._ptr(x.to(DEV)), R._ptr(w.to(DEV)), R._ptr(b.to(DEV)), R._ptr(sc.to(DEV)),
-                              R._ptr(out), B, T, C, 3, R._stream()))
+    d_x, d_w, d_b, d_sc = x.to(DEV), w.to(DEV), b.to(DEV), sc.to(DEV)
+    lib.check(L.ou_input_conv(R._ptr(d_x), R._ptr(d_w), R._ptr(d_b), R._ptr(d_sc), R._ptr(out), B, T, C,
+                              3, R._stream()))
+    torch.cuda.synchronize()
     assert rel_rms(R.unpack_blocked(out).cpu(), bf(want)) < 1e-3
     # output conv + SDE update
     src = bf(torch.randn(B, C, T - 3, generator=g))
@@ -189,9 +198,10 @@ def test_input_and_output_kernels():
     xnew = coef[:, 0, None, None] * x + coef[:, 1, None, None] * net + coef[:, 2, None, None] * noise
     xo = torch.empty(B, 1, T, device=DEV)
     no = torch.empty(B, 1, T, device=DEV)
-    lib.check(L.ou_output_sde(R._ptr(R.pack_blocked(src.to(DEV))), R._ptr(wo.to(DEV)), 0.3,
-                              R._ptr(coef.to(DEV)), R._ptr(x.to(DEV)), R._ptr(noise.to(DEV)), R._ptr(xo),
-                              R._ptr(no), B, C, 3, T - 3, T, R._stream()))
+    d_src, d_wo, d_coef, d_noise = R.pack_blocked(src.to(DEV)), wo.to(DEV), coef.to(DEV), noise.to(DEV)
+    lib.check(L.ou_output_sde(R._ptr(d_src), R._ptr(d_wo), 0.3, R._ptr(d_coef), R._ptr(d_x), R._ptr(d_noise),
+                              R._ptr(xo), R._ptr(no), B, C, 3, T - 3, T, R._stream()))
+    torch.cuda.synchronize()
     assert rel_rms(no.cpu(), net) < 1e-5
     assert rel_rms(xo.cpu(), xnew) < 1e-5
 
