@@ -8,6 +8,8 @@
 // GEMM view: M = output rows j (128 per CTA), N = up*cout (BN per CTA), K = taps * s*cin.
 // smem tiles are K-major "8-channel x 16-byte row" core matrices: A [chunk][row][8], B [tap][chunk][n][8]
 // -- a tap shift is a 16-byte row offset, so one A tile (with taps-1 halo rows) serves all taps.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace ou {
@@ -326,11 +328,31 @@ static int launch_mma(const ConvArgs& a, cudaStream_t st) {
 
 }  // namespace ou
 
+namespace ou {
+namespace tc {
+int launch(const ou_conv_params* p, cudaStream_t st);
+}
+// OU_CONV_IMPL=mma forces the warp-level mma.sync kernel everywhere (debugging / A-B timing);
+// default: tcgen05 kernel wherever its geometry applies (stride-1 input), mma.sync otherwise.
+static bool use_tc() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = getenv("OU_CONV_IMPL");
+    cached = (e && e[0] == 'm') ? 0 : 1;
+  }
+  return cached == 1;
+}
+}  // namespace ou
+
 extern "C" int ou_conv1d(const ou_conv_params* p, void* stream) {
   ou::ConvArgs a;
   int rc = ou::validate(p, &a);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
+  if (ou::use_tc()) {
+    rc = ou::tc::launch(p, st);
+    if (rc != OU_ERR_UNSUPPORTED) return rc;
+  }
   if (p->npad % 128 == 0) return ou::launch_mma<128, 3>(a, st);
   if (p->npad % 64 == 0) return ou::launch_mma<64, 3>(a, st);
   return ou::launch_mma<32, 3>(a, st);
