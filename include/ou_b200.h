@@ -188,6 +188,10 @@ int ou_unpack_blocked(const void* src, float* dst, int batch, int channels, int 
 int ou_film_f32(const float* x, const float* y, float* out, int batch, int channels, int t,
                 void* stream);
 
+/* Debug hook: when set to a device buffer of 4*64*4 int64, CTA 0 of the tcgen05 conv kernel stamps
+ * clock64() per warp role / tile / event into it (tools/trace_conv.py).  NULL disables. */
+int ou_debug_set_trace(void* device_buffer);
+
 #ifdef __cplusplus
 }
 #endif

@@ -46,7 +46,13 @@ struct TcArgs {
   uint32_t a_stage_bytes, b_stage_bytes;
   uint32_t idesc;
   uint32_t tmem_cols;
+  long long* trace;    // debug: [role 0..3][tile 0..63][event 0..3] clock64 stamps of CTA 0 (or NULL)
 };
+
+__device__ __forceinline__ void trace_ev(const TcArgs& a, int role, int tile_i, int ev) {
+  if (a.trace != nullptr && blockIdx.x == 0 && tile_i < 64)
+    a.trace[(role * 64 + tile_i) * 4 + ev] = clock64();
+}
 
 // ------------------------------------------------------------------------------------ PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -274,7 +280,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const TcArgs a) 
       const __nv_bfloat16* wg = (const __nv_bfloat16*)p.w;
       Ring ra, rb;
       bool b_loaded = false;
-      for (int mt = mt0; mt < a.total_m_tiles; mt += mt_stride) {
+      int ti = 0;
+      for (int mt = mt0; mt < a.total_m_tiles; mt += mt_stride, ti++) {
         const int b = mt / a.m_tiles;
         const int m0 = (mt - b * a.m_tiles) * BM;
         const __nv_bfloat16* xg = (const __nv_bfloat16*)p.x + (size_t)b * a.cin_chunks * p.t_in * 8;
@@ -300,6 +307,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const TcArgs a) 
             rb.advance(a.b_stages);
           }
           mbar_wait(smem_u32(&empty_a[ra.stage]), ra.phase ^ 1);
+          if (kb == 0) trace_ev(a, 0, ti, 0);
           const uint32_t bar = smem_u32(&full_a[ra.stage]);
           int nvalid = a.cin_chunks - kb * a.kb_chunks;
           nvalid = nvalid > a.kb_chunks ? a.kb_chunks : (nvalid < 0 ? 0 : nvalid);
@@ -313,6 +321,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const TcArgs a) 
             }
           }
           ra.advance(a.a_stages);
+          if (kb == a.n_kblocks - 1) trace_ev(a, 0, ti, 1);
         }
         b_loaded = true;
       }
@@ -323,9 +332,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const TcArgs a) 
     int acc = 0;
     uint32_t acc_phase = 0;
     bool b_waited = false;
-    for (int mt = mt0; mt < a.total_m_tiles; mt += mt_stride) {
+    int ti = 0;
+    for (int mt = mt0; mt < a.total_m_tiles; mt += mt_stride, ti++) {
       mbar_wait(smem_u32(&tmem_empty[acc]), acc_phase ^ 1);
       tc_fence_after();
+      if (lane == 0) trace_ev(a, 1, ti, 0);
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * a.bn);
       for (int kb = 0; kb < a.n_kblocks; kb++) {
         int bstage;
@@ -339,6 +350,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const TcArgs a) 
         mbar_wait(smem_u32(&ready_a[ra.stage]), ra.phase);
         tc_fence_after();
         if (lane == 0) {
+          if (kb == 0) trace_ev(a, 1, ti, 1);
+          if (kb == a.n_kblocks - 1) trace_ev(a, 1, ti, 2);
           const uint32_t a_base = smem_u32(smA + (size_t)ra.stage * a.a_stage_bytes);
           const uint32_t b_base = smem_u32(smB + (size_t)bstage * a.b_stage_bytes);
           for (int q = 0; q < taps; q++) {
@@ -352,7 +365,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const TcArgs a) 
           }
           umma_commit(smem_u32(&empty_a[ra.stage]));
           if (!a.resident) umma_commit(smem_u32(&empty_b[rb.stage]));
-          if (kb == a.n_kblocks - 1) umma_commit(smem_u32(&tmem_full[acc]));
+          if (kb == a.n_kblocks - 1) {
+            umma_commit(smem_u32(&tmem_full[acc]));
+            trace_ev(a, 1, ti, 3);
+          }
         }
         __syncwarp();
         ra.advance(a.a_stages);
@@ -368,7 +384,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const TcArgs a) 
     Ring ra;
     const bool do_prelu = p.has_prelu_in != 0;
     const float slope = p.prelu_in;
-    for (int mt = mt0; mt < a.total_m_tiles; mt += mt_stride) {
+    int ti = 0;
+    for (int mt = mt0; mt < a.total_m_tiles; mt += mt_stride, ti++) {
       const int b = mt / a.m_tiles;
       const int m0 = (mt - b * a.m_tiles) * BM;
       const int j0 = m0 + p.tap_off;
@@ -378,6 +395,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const TcArgs a) 
       const bool interior = (r_lo == 0 && r_hi == a.arows);
       for (int kb = 0; kb < a.n_kblocks; kb++) {
         mbar_wait(smem_u32(&full_a[ra.stage]), ra.phase);
+        if (xt == 0 && kb == 0) trace_ev(a, 2, ti, 0);
+        if (xt == 0 && kb == a.n_kblocks - 1) trace_ev(a, 2, ti, 1);
         uint8_t* As = smA + (size_t)ra.stage * a.a_stage_bytes;
         int nvalid = a.cin_chunks - kb * a.kb_chunks;
         nvalid = nvalid > a.kb_chunks ? a.kb_chunks : (nvalid < 0 ? 0 : nvalid);
@@ -403,6 +422,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const TcArgs a) 
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&ready_a[ra.stage]));
+        if (xt == 0 && kb == a.n_kblocks - 1) trace_ev(a, 2, ti, 2);
         ra.advance(a.a_stages);
       }
     }
@@ -412,12 +432,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const TcArgs a) 
     const int row = quarter * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int mt = mt0; mt < a.total_m_tiles; mt += mt_stride) {
+    int ti = 0;
+    for (int mt = mt0; mt < a.total_m_tiles; mt += mt_stride, ti++) {
       const int b = mt / a.m_tiles;
       const int m0 = (mt - b * a.m_tiles) * BM;
       const int j = m0 + row;
+      if (row == 0) trace_ev(a, 3, ti, 0);
       mbar_wait(smem_u32(&tmem_full[acc]), acc_phase);
       tc_fence_after();
+      if (row == 0) trace_ev(a, 3, ti, 1);
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * a.bn);
       for (int c0 = 0; c0 < a.bn; c0 += 32) {
         uint32_t r[32];
@@ -428,6 +451,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const TcArgs a) 
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&tmem_empty[acc]));
+          if (row == 0) trace_ev(a, 3, ti, 2);
         }
         if (j < p.rows) {
 #pragma unroll
@@ -437,6 +461,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const TcArgs a) 
           }
         }
       }
+      if (row == 0) trace_ev(a, 3, ti, 3);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -449,6 +474,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv1d_tc_kernel(const TcArgs a) 
 
 // ------------------------------------------------------------------------------------ host side
 static int g_num_sms = 0;
+long long* g_trace = nullptr;
 
 int plan(const ou_conv_params* p, TcArgs* a) {
   if (p->s != 1) return OU_ERR_UNSUPPORTED;
@@ -531,6 +557,7 @@ int launch(const ou_conv_params* p, cudaStream_t st) {
   if (per < 1) per = 1;
   if (per > a.total_m_tiles) per = a.total_m_tiles;
   a.ctas_per_ntile = per;
+  a.trace = g_trace;
   dim3 grid(per * a.n_ntiles);
   conv1d_tc_kernel<<<grid, NTHREADS, smem, st>>>(a);
   return check_launch("ou_conv1d(tc)");
@@ -538,3 +565,8 @@ int launch(const ou_conv_params* p, cudaStream_t st) {
 
 }  // namespace tc
 }  // namespace ou
+
+extern "C" int ou_debug_set_trace(void* device_buffer) {
+  ou::tc::g_trace = (long long*)device_buffer;
+  return OU_OK;
+}

@@ -15,7 +15,6 @@ namespace cg = cooperative_groups;
 
 namespace ou {
 
-constexpr int GRU_BG = 4;    // clips per cluster
 constexpr int GRU_KPT = 64;  // recurrent-matrix columns held per thread
 
 struct GruArgs {
@@ -28,11 +27,12 @@ struct GruArgs {
   int batch, t;
 };
 
-__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }
+// __expf has ~2 ulp error: |error| of the gates ~1e-7, far below the bf16 output rounding
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + __expf(-x)); }
+__device__ __forceinline__ float tanh_f(float x) { return 2.f / (1.f + __expf(-2.f * x)) - 1.f; }
 
-template <int H, int CS>
+template <int H, int CS, int BG>
 __global__ void __launch_bounds__(3 * (H / CS) * (H / GRU_KPT)) gru_cluster_kernel(const GruArgs a) {
-  constexpr int BG = GRU_BG;
   constexpr int KPT = GRU_KPT;
   constexpr int HS = H / CS;       // hidden units owned by this CTA
   constexpr int ROWS = 3 * HS;     // gate rows owned by this CTA
@@ -86,13 +86,19 @@ __global__ void __launch_bounds__(3 * (H / CS) * (H / GRU_KPT)) gru_cluster_kern
   }
   cluster.sync();
 
+  // input pre-activations are prefetched one step ahead (they come from HBM / L2)
+  float gxr = 0.f, gxz = 0.f, gxn = 0.f;
+  if (fvalid) {
+    const float* g = gxp + (size_t)(dir ? T - 1 : 0) * 6 * H;
+    gxr = __ldg(g), gxz = __ldg(g + H), gxn = __ldg(g + 2 * H);
+  }
   for (int step = 0; step < T; step++) {
     const int t = dir ? (T - 1 - step) : step;
     const int cur = step & 1;
-    float gxr = 0.f, gxz = 0.f, gxn = 0.f;
-    if (fvalid) {
-      const float* g = gxp + (size_t)t * 6 * H;
-      gxr = __ldg(g), gxz = __ldg(g + H), gxn = __ldg(g + 2 * H);
+    float nxr = 0.f, nxz = 0.f, nxn = 0.f;
+    if (fvalid && step + 1 < T) {
+      const float* g = gxp + (size_t)(dir ? t - 1 : t + 1) * 6 * H;
+      nxr = __ldg(g), nxz = __ldg(g + H), nxn = __ldg(g + 2 * H);
     }
     float acc[BG];
 #pragma unroll
@@ -111,6 +117,7 @@ __global__ void __launch_bounds__(3 * (H / CS) * (H / GRU_KPT)) gru_cluster_kern
 #pragma unroll
     for (int bb = 0; bb < BG; bb++) part[ks][row][bb] = acc[bb];
     __syncthreads();
+    float h_buf_own_new = 0.f;
     if (fin) {
       float hr = bhr, hz = bhz, hn = bhn;
 #pragma unroll
@@ -121,27 +128,32 @@ __global__ void __launch_bounds__(3 * (H / CS) * (H / GRU_KPT)) gru_cluster_kern
       }
       const float r = sigmoid_f(gxr + hr);
       const float z = sigmoid_f(gxz + hz);
-      const float n = tanhf(gxn + r * hn);
+      const float n = tanh_f(gxn + r * hn);
       const float hprev = h_buf[cur][fb][hu];
       const float hnew = fvalid ? (1.f - z) * n + z * hprev : 0.f;
+      h_buf_own_new = hnew;
       float* slot = &h_buf[cur ^ 1][fb][hu];
 #pragma unroll
       for (int c = 0; c < CS; c++) *cluster.map_shared_rank(slot, c) = hnew;
-      if (fvalid) {
-        const size_t off = out_base + (size_t)t * 8;
-        float v = hnew;
-        if (a.add) v += __bfloat162float(a.add[off]);
-        a.out[off] = __float2bfloat16(v * a.scale);
-      }
     }
-    cluster.sync();
+    // split cluster barrier: release the DSMEM pushes, do the global store, then acquire
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    if (fvalid) {
+      const float hnew = h_buf_own_new;
+      const size_t off = out_base + (size_t)t * 8;
+      float v = hnew;
+      if (a.add) v += __bfloat162float(a.add[off]);
+      a.out[off] = __float2bfloat16(v * a.scale);
+    }
+    gxr = nxr, gxz = nxz, gxn = nxn;
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
   }
 }
 
-template <int H, int CS>
-static int launch_gru(const GruArgs& a, cudaStream_t st) {
+template <int H, int CS, int BG>
+static int launch_gru_bg(const GruArgs& a, cudaStream_t st) {
   constexpr int NT = 3 * (H / CS) * (H / GRU_KPT);
-  auto kern = gru_cluster_kernel<H, CS>;
+  auto kern = gru_cluster_kernel<H, CS, BG>;
   if (CS > 8) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     if (e != cudaSuccess) {
@@ -149,7 +161,7 @@ static int launch_gru(const GruArgs& a, cudaStream_t st) {
       return OU_ERR_CUDA;
     }
   }
-  const int clusters = 2 * ceil_div(a.batch, GRU_BG);
+  const int clusters = 2 * ceil_div(a.batch, BG);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(clusters * CS);
   cfg.blockDim = dim3(NT);
@@ -168,6 +180,47 @@ static int launch_gru(const GruArgs& a, cudaStream_t st) {
     return OU_ERR_CUDA;
   }
   return check_launch("ou_gru_bidir");
+}
+
+// How many clusters of CS CTAs can be co-resident (GPC granularity: 14 x 8 on a 148-SM B200).
+template <int H, int CS>
+static int max_clusters() {
+  static int cached = 0;
+  if (cached) return cached;
+  constexpr int NT = 3 * (H / CS) * (H / GRU_KPT);
+  auto kern = gru_cluster_kernel<H, CS, 4>;
+  if (CS > 8) cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(CS * 64);
+  cfg.blockDim = dim3(NT);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n < 2) {
+    cudaGetLastError();
+    n = 2 * (148 / CS / 2);
+  }
+  cached = n;
+  return cached;
+}
+
+// Pick the clips-per-cluster so that all clusters run in ONE wave (the recurrence is latency
+// bound: a second wave doubles the time, a wider cluster only adds FMA work).
+template <int H, int CS>
+static int launch_gru(const GruArgs& a, cudaStream_t st) {
+  const int groups_max = max_clusters<H, CS>() / 2;
+  int bg = ceil_div(a.batch, groups_max > 0 ? groups_max : 1);
+  if (bg <= 2) return launch_gru_bg<H, CS, 2>(a, st);
+  if (bg == 3) return launch_gru_bg<H, CS, 3>(a, st);
+  if (bg == 4) return launch_gru_bg<H, CS, 4>(a, st);
+  if (bg == 5) return launch_gru_bg<H, CS, 5>(a, st);
+  if (bg == 6) return launch_gru_bg<H, CS, 6>(a, st);
+  return launch_gru_bg<H, CS, 8>(a, st);
 }
 
 }  // namespace ou
