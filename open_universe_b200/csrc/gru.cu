@@ -215,12 +215,18 @@ template <int H, int CS>
 static int launch_gru(const GruArgs& a, cudaStream_t st) {
   const int groups_max = max_clusters<H, CS>() / 2;
   int bg = ceil_div(a.batch, groups_max > 0 ? groups_max : 1);
+  constexpr int NT = 3 * (H / CS) * (H / GRU_KPT);
+  constexpr int BG_MAX = NT / (H / CS);   // the gate stage needs one thread per (unit, clip)
   if (bg <= 2) return launch_gru_bg<H, CS, 2>(a, st);
   if (bg == 3) return launch_gru_bg<H, CS, 3>(a, st);
   if (bg == 4) return launch_gru_bg<H, CS, 4>(a, st);
   if (bg == 5) return launch_gru_bg<H, CS, 5>(a, st);
-  if (bg == 6) return launch_gru_bg<H, CS, 6>(a, st);
-  return launch_gru_bg<H, CS, 8>(a, st);
+  if constexpr (BG_MAX >= 8) {
+    if (bg == 6) return launch_gru_bg<H, CS, 6>(a, st);
+    return launch_gru_bg<H, CS, 8>(a, st);
+  } else {
+    return launch_gru_bg<H, CS, 6>(a, st);
+  }
 }
 
 }  // namespace ou
