@@ -14,8 +14,9 @@
  *   - all pointers are DEVICE pointers unless stated otherwise;
  *   - ou_last_error() returns a thread-local human-readable message for the last failure.
  *
- * Activation layout ("blocked"): bf16 [B][C/8][T][8] -- channel c of time step t of clip b lives at
- *   ((b * (C/8) + c/8) * T + t) * 8 + c%8.   C must be a multiple of 8.
+ * Activation layout ("blocked"): bf16 [B][C/CB][T][CB], CB = largest of {64, 32, 16} dividing C --
+ *   channel c of time step t of clip b lives at ((b * (C/CB) + c/CB) * T + t) * CB + c%CB
+ *   (channels-last within blocks of CB channels; C must be a multiple of 16).
  * Signals are fp32 [B][T]; GRU pre-activations fp32 time-major [B][T][N].
  */
 #ifndef OU_B200_H
@@ -61,18 +62,21 @@ int64_t ou_launch_count(void);
  *   y = ((acc + bias[n] + add1[co][t]) * scale1 + add2[co][t]) * scale2
  *   y = gamma[b][co] * y + beta[b][co]                    (if gamma != NULL)
  *   y = PReLU(PReLU(y, prelu_out), prelu_out2)            (each if enabled)
- *   out (blocked bf16 [B][cout/8][t_out][8])  or  out_f32_tm (fp32 [B][rows][n], no add/film/prelu)
+ *   out (blocked bf16 (B, cout, t_out))  or  out_f32_tm (fp32 [B][rows][n], no add/film/prelu)
  * ------------------------------------------------------------------------------------------ */
 typedef struct ou_conv_params {
-  const void* x;          /* blocked bf16 [B][cin/8][t_in][8]                                  */
+  const void* x;          /* blocked bf16 (B, cin, t_in)                                  */
   const void* w;          /* packed bf16 [taps][kpad/8][npad][8]; element (q, c', n_) = W[n_][q][c'],
-                             zero padded; kpad % 32 == 0, npad % 32 == 0                        */
+                             zero padded; kpad % 32 == 0, npad % 32 == 0 (mma.sync / naive path) */
+  const void* w_tc;       /* same weights packed for the tcgen05 path, or NULL: bf16
+                             [taps][cin/CB][npad][CB], CB = channel block of the input layout;
+                             only used when s == 1                                              */
   const float* bias;      /* fp32 [n] or NULL                                                   */
-  const void* add1;       /* blocked bf16 [B][cout/8][t_out][8] or NULL                         */
-  const void* add2;       /* blocked bf16 [B][cout/8][t_out][8] or NULL                         */
+  const void* add1;       /* blocked bf16 (B, cout, t_out) or NULL                         */
+  const void* add2;       /* blocked bf16 (B, cout, t_out) or NULL                         */
   const float* gamma;     /* fp32, element (b, co) at gamma[b*film_bstride + co], or NULL       */
   const float* beta;      /* fp32, same indexing                                                */
-  void* out;              /* blocked bf16 [B][cout/8][t_out][8] or NULL                         */
+  void* out;              /* blocked bf16 (B, cout, t_out) or NULL                         */
   float* out_f32_tm;      /* fp32 [B][rows][n] or NULL (exactly one of out / out_f32_tm)        */
   int32_t batch, cin, t_in;
   int32_t s, taps, tap_off;
@@ -96,7 +100,7 @@ int ou_conv1d_naive(const ou_conv_params* p, void* stream);
  * Replaces ScoreNetwork.input_conv (score.py:239-241,285) + `w_in * x` of _edm_score_wrapper
  * (universe.py:197-203), and ConditionerNetwork.input_conv (condition.py:290-295,361).
  *   out[co][t] = bias[co] + sum_k w[co][k] * in_scale[b] * x[b][t + k - k/2]
- * x fp32 [B][t]; w fp32 [cout][k]; in_scale fp32 [B] or NULL; out blocked bf16 [B][cout/8][t][8].
+ * x fp32 [B][t]; w fp32 [cout][k]; in_scale fp32 [B] or NULL; out blocked bf16 (B, cout, t).
  * ------------------------------------------------------------------------------------------ */
 int ou_input_conv(const float* x, const float* w, const float* bias, const float* in_scale,
                   void* out, int batch, int t, int cout, int k, void* stream);
@@ -107,7 +111,7 @@ int ou_input_conv(const float* x, const float* w, const float* bias, const float
  * (universe.py:204-206) and the reverse-SDE update (universe.py:337-339, 342-343):
  *   net[b][t]  = bias + sum_{ci,k} w[ci][k] * src[ci][t + k - k/2]      (t < t_src, else 0)
  *   xout[b][t] = ca[b]*x[b][t] + cb[b]*net[b][t] + cc[b]*noise[b][t]    (t < t_sig)
- * src blocked bf16 [B][cin/8][t_src][8] (already activated by the producer); w fp32 [cin][k];
+ * src blocked bf16 (B, cin, t_src) (already activated by the producer); w fp32 [cin][k];
  * coef fp32 [B][3] = (ca, cb, cc) or NULL; noise fp32 [B][t_sig] or NULL; net_out fp32 [B][t_sig]
  * or NULL; x / xout fp32 [B][t_sig] (may alias) or NULL when coef is NULL.
  * ------------------------------------------------------------------------------------------ */
@@ -122,7 +126,7 @@ int ou_output_sde(const void* src, const float* w, float bias, const float* coef
  *   w_hh  fp32 [2][3H][H],  b_hh fp32 [2][3H]
  *   r = s(gx_r + W_hr h + b_hr); z = s(gx_z + W_hz h + b_hz); n = tanh(gx_n + r*(W_hn h + b_hn));
  *   h' = (1-z)*n + z*h; h0 = 0; backward direction runs t = T-1..0
- *   out blocked bf16 [B][2H/8][T][8] = ((h_fwd | h_bwd) + add) * scale   (add blocked or NULL)
+ *   out blocked bf16 (B, 2H, T) = ((h_fwd | h_bwd) + add) * scale   (add blocked or NULL)
  * ------------------------------------------------------------------------------------------ */
 int ou_gru_bidir(const float* gx, const float* w_hh, const float* b_hh, const void* add, float scale,
                  void* out, int batch, int t, int hidden, void* stream);
@@ -138,7 +142,7 @@ int ou_gru_bidir(const float* gx, const float* w_hh, const float* b_hh, const vo
  *                    twiddle fp32 [n_fft][2] = (cos, sin)(2*pi*i/n_fft).
  *   ou_mel_finalize: per clip scale = 1 / max(sqrt(mean_frames energy), 1e-5); writes the
  *                    normalised mel as fp32 [B][n_mels][frames] (in place allowed, or NULL) and
- *                    blocked bf16 [B][n_mels/8][frames][8] (or NULL).
+ *                    blocked bf16 (B, n_mels, frames) (or NULL).
  * ------------------------------------------------------------------------------------------ */
 int ou_mel_power(const float* x, const float* window, const float* fb, const float* twiddle,
                  float* mel, float* energy, int batch, int t, int n_fft, int hop, int n_mels,

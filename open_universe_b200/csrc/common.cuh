@@ -35,6 +35,17 @@ inline int check_launch(const char* what) {
 
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// Blocked ("channels-last in blocks") activation layout: bf16 [B][C/CB][T][CB] with
+// CB = largest of {64, 32, 16} dividing C.  One time step of one channel block is a CB*2-byte
+// row (128 B for CB = 64) -- exactly a K-major, 128B-swizzle-able tensor-core operand row.
+__host__ __device__ inline int cl_cb(int channels) {
+  return (channels % 64 == 0) ? 64 : ((channels % 32 == 0) ? 32 : 16);
+}
+// element offset of channel c (any) of time step t of clip b
+__host__ __device__ inline size_t cl_off(int b, int c, int t, int channels, int t_len, int cb) {
+  return (((size_t)b * (channels / cb) + c / cb) * t_len + t) * cb + (c % cb);
+}
+
 __device__ __forceinline__ float prelu_f(float x, float a) { return x >= 0.f ? x : a * x; }
 
 __device__ __forceinline__ float2 bf2_to_f2(uint32_t v) {

@@ -69,7 +69,7 @@ __device__ __forceinline__ void epilogue_pair(const ou_conv_params& p, int b, in
   const int co = n - ph * p.cout;
   const int t = j * p.up + ph;
   if (t >= p.t_out) return;
-  const size_t off = (((size_t)b * (p.cout >> 3) + (co >> 3)) * p.t_out + t) * 8 + (co & 7);
+  const size_t off = cl_off(b, co, t, p.cout, p.t_out, cl_cb(p.cout));
   if (p.add1) {
     float2 a = bf2_to_f2(*reinterpret_cast<const uint32_t*>((const __nv_bfloat16*)p.add1 + off));
     v0 += a.x;
@@ -131,6 +131,7 @@ __global__ void __launch_bounds__(NTHREADS) conv1d_mma_kernel(const ConvArgs a) 
 
   const __nv_bfloat16* xg = (const __nv_bfloat16*)p.x + (size_t)b * a.cin_chunks * p.t_in * 8;
   const __nv_bfloat16* wg = (const __nv_bfloat16*)p.w;
+  const int cbi = cl_cb(p.cin);
 
   auto load_stage = [&](int kb, int stage) {
     uint8_t* As = smA + stage * a_stage_bytes;
@@ -148,7 +149,8 @@ __global__ void __launch_bounds__(NTHREADS) conv1d_mma_kernel(const ConvArgs a) 
       const int j = m0 + rr + p.tap_off;
       const long t = (long)j * p.s + r;
       valid = valid && j >= 0 && t < p.t_in;
-      const __nv_bfloat16* src = valid ? xg + ((size_t)cic * p.t_in + t) * 8 : xg;
+      const __nv_bfloat16* src =
+          valid ? xg + ((size_t)((cic * 8) / cbi) * p.t_in + t) * cbi + ((cic * 8) % cbi) : xg;
       cp_async16(As + (size_t)i * 16, src, valid);
     }
     // B: taps x KCH chunks x BN columns of 16 B (always in-bounds: weights are zero padded)
@@ -261,6 +263,7 @@ __global__ void conv1d_naive_kernel(const ConvArgs a) {
     const int n = np * 2;
     const __nv_bfloat16* xg = (const __nv_bfloat16*)p.x + (size_t)b * a.cin_chunks * p.t_in * 8;
     const __nv_bfloat16* wg = (const __nv_bfloat16*)p.w;
+    const int cbi = cl_cb(p.cin);
     float v0 = 0.f, v1 = 0.f;
     for (int q = 0; q < p.taps; q++) {
       const int jj = j + p.tap_off + q;
@@ -269,7 +272,7 @@ __global__ void conv1d_naive_kernel(const ConvArgs a) {
         const long t = (long)jj * p.s + r;
         if (t >= p.t_in) continue;
         for (int ci = 0; ci < p.cin; ci++) {
-          float x = __bfloat162float(xg[((size_t)(ci >> 3) * p.t_in + t) * 8 + (ci & 7)]);
+          float x = __bfloat162float(xg[((size_t)(ci / cbi) * p.t_in + t) * cbi + (ci % cbi)]);
           if (p.has_prelu_in) x = __bfloat162float(__float2bfloat16(prelu_f(x, p.prelu_in)));
           const int cp = r * p.cin + ci;
           const size_t wo = (((size_t)q * (p.kpad >> 3) + (cp >> 3)) * p.npad + n) * 8 + (cp & 7);
@@ -288,7 +291,7 @@ static int validate(const ou_conv_params* p, ConvArgs* a) {
   OU_REQUIRE((p->out != nullptr) != (p->out_f32_tm != nullptr),
              "ou_conv1d: exactly one of out / out_f32_tm must be set");
   OU_REQUIRE(p->batch > 0 && p->cin > 0 && p->t_in > 0 && p->rows > 0, "ou_conv1d: empty problem");
-  OU_REQUIRE(p->cin % 8 == 0 && p->cout % 8 == 0, "ou_conv1d: channels must be multiples of 8");
+  OU_REQUIRE(p->cin % 16 == 0 && p->cout % 16 == 0, "ou_conv1d: channels must be multiples of 16");
   OU_REQUIRE(p->s >= 1 && p->up >= 1 && p->taps >= 1 && p->taps <= 8, "ou_conv1d: bad s/up/taps");
   OU_REQUIRE(p->n == p->up * p->cout, "ou_conv1d: n != up*cout");
   OU_REQUIRE(p->kpad % 32 == 0 && p->kpad >= p->s * p->cin, "ou_conv1d: bad kpad");

@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(3 * (H / CS) * (H / GRU_KPT)) gru_cluster_kern
     bhr = bh[hu], bhz = bh[H + hu], bhn = bh[2 * H + hu];
     gxp = a.gx + (size_t)(b0 + fb) * T * 6 * H + (size_t)dir * 3 * H + hu;
     const int ch = dir * H + hu;
-    out_base = (((size_t)(b0 + fb) * (2 * H / 8) + (ch >> 3)) * T) * 8 + (ch & 7);
+    out_base = cl_off(b0 + fb, ch, 0, 2 * H, T, cl_cb(2 * H));
   }
   cluster.sync();
 
@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(3 * (H / CS) * (H / GRU_KPT)) gru_cluster_kern
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     if (fvalid) {
       const float hnew = h_buf_own_new;
-      const size_t off = out_base + (size_t)t * 8;
+      const size_t off = out_base + (size_t)t * cl_cb(2 * H);
       float v = hnew;
       if (a.add) v += __bfloat162float(a.add[off]);
       a.out[off] = __float2bfloat16(v * a.scale);

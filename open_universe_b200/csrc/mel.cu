@@ -84,7 +84,7 @@ __global__ void mel_finalize_kernel(const float* __restrict__ mel, const float* 
     const int j = i / frames, m = i - j * frames;
     if (mel_norm) mel_norm[(size_t)b * n_mels * frames + i] = v;
     if (blocked)
-      blocked[(((size_t)b * (n_mels / 8) + (j >> 3)) * frames + m) * 8 + (j & 7)] = __float2bfloat16(v);
+      blocked[cl_off(b, j, m, n_mels, frames, cl_cb(n_mels))] = __float2bfloat16(v);
   }
 }
 
@@ -149,7 +149,7 @@ extern "C" int ou_mel_finalize(const float* mel, const float* energy, float* mel
                                void* mel_blocked, int batch, int n_mels, int frames, void* stream) {
   OU_REQUIRE(mel && energy && (mel_norm || mel_blocked), "ou_mel_finalize: null pointer");
   OU_REQUIRE(batch > 0 && n_mels > 0 && frames > 0, "ou_mel_finalize: bad shape");
-  OU_REQUIRE(mel_blocked == nullptr || n_mels % 8 == 0, "ou_mel_finalize: n_mels % 8 != 0");
+  OU_REQUIRE(mel_blocked == nullptr || n_mels % 16 == 0, "ou_mel_finalize: n_mels % 16 != 0");
   ou::mel_finalize_kernel<<<batch, 512, 0, (cudaStream_t)stream>>>(
       mel, energy, mel_norm, (__nv_bfloat16*)mel_blocked, n_mels, frames);
   return ou::check_launch("ou_mel_finalize");

@@ -38,7 +38,7 @@ __global__ void input_conv_kernel(const float* __restrict__ x, const float* __re
       }
       v[h] = f2_to_bf2(o[0], o[1]);
     }
-    uint4* dst = reinterpret_cast<uint4*>(out + (((size_t)b * (cout / 8) + c8) * t_len + t) * 8);
+    uint4* dst = reinterpret_cast<uint4*>(out + cl_off(b, c8 * 8, t, cout, t_len, cl_cb(cout)));
     *dst = make_uint4(v[0], v[1], v[2], v[3]);
   }
 }
@@ -59,12 +59,12 @@ __global__ void output_sde_kernel(const __nv_bfloat16* __restrict__ src, const f
   if (t < t_src) {
     net = bias;
     const int half = k / 2;
+    const int cb = cl_cb(cin);
     for (int c8 = 0; c8 < cin / 8; c8++) {
-      const __nv_bfloat16* base = src + ((size_t)b * (cin / 8) + c8) * t_src * 8;
       for (int i = 0; i < k; i++) {
         const int tt = t + i - half;
         if (tt < 0 || tt >= t_src) continue;
-        const uint4 v = *reinterpret_cast<const uint4*>(base + (size_t)tt * 8);
+        const uint4 v = *reinterpret_cast<const uint4*>(src + cl_off(b, c8 * 8, tt, cin, t_src, cb));
         const uint32_t* pv = reinterpret_cast<const uint32_t*>(&v);
 #pragma unroll
         for (int h = 0; h < 4; h++) {
@@ -181,7 +181,7 @@ __global__ void pack_blocked_kernel(const float* __restrict__ src, __nv_bfloat16
   for (int e = 0; e < 8; e++) f[e] = src[((size_t)b * channels + c8 * 8 + e) * t_len + t];
   uint4 v = make_uint4(f2_to_bf2(f[0], f[1]), f2_to_bf2(f[2], f[3]), f2_to_bf2(f[4], f[5]),
                        f2_to_bf2(f[6], f[7]));
-  *reinterpret_cast<uint4*>(dst + (((size_t)b * (channels / 8) + c8) * t_len + t) * 8) = v;
+  *reinterpret_cast<uint4*>(dst + cl_off(b, c8 * 8, t, channels, t_len, cl_cb(channels))) = v;
 }
 
 __global__ void unpack_blocked_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst,
@@ -190,7 +190,7 @@ __global__ void unpack_blocked_kernel(const __nv_bfloat16* __restrict__ src, flo
   const int c8 = blockIdx.y, b = blockIdx.z;
   if (t >= t_len) return;
   const uint4 v =
-      *reinterpret_cast<const uint4*>(src + (((size_t)b * (channels / 8) + c8) * t_len + t) * 8);
+      *reinterpret_cast<const uint4*>(src + cl_off(b, c8 * 8, t, channels, t_len, cl_cb(channels)));
   const uint32_t* pv = reinterpret_cast<const uint32_t*>(&v);
 #pragma unroll
   for (int h = 0; h < 4; h++) {
@@ -215,7 +215,7 @@ __global__ void film_f32_kernel(const float* __restrict__ x, const float* __rest
 extern "C" int ou_input_conv(const float* x, const float* w, const float* bias, const float* in_scale,
                              void* out, int batch, int t, int cout, int k, void* stream) {
   OU_REQUIRE(x && w && out, "ou_input_conv: null pointer");
-  OU_REQUIRE(batch > 0 && t > 0 && cout > 0 && cout % 8 == 0, "ou_input_conv: bad shape");
+  OU_REQUIRE(batch > 0 && t > 0 && cout > 0 && cout % 16 == 0, "ou_input_conv: bad shape");
   OU_REQUIRE(k >= 1 && k <= 7 && (k & 1), "ou_input_conv: kernel size must be odd and <= 7");
   dim3 grid(ou::ceil_div(t, 256), batch);
   const size_t smem = (size_t)(cout * k + cout) * sizeof(float);
@@ -228,7 +228,7 @@ extern "C" int ou_output_sde(const void* src, const float* w, float bias, const 
                              const float* x, const float* noise, float* xout, float* net_out,
                              int batch, int cin, int k, int t_src, int t_sig, void* stream) {
   OU_REQUIRE(src && w, "ou_output_sde: null pointer");
-  OU_REQUIRE(batch > 0 && t_src > 0 && t_sig >= t_src && cin % 8 == 0, "ou_output_sde: bad shape");
+  OU_REQUIRE(batch > 0 && t_src > 0 && t_sig >= t_src && cin % 16 == 0, "ou_output_sde: bad shape");
   OU_REQUIRE(k >= 1 && (k & 1), "ou_output_sde: kernel size must be odd");
   OU_REQUIRE(coef == nullptr || (x && xout), "ou_output_sde: coef needs x and xout");
   OU_REQUIRE(coef || net_out, "ou_output_sde: nothing to write");
@@ -261,7 +261,7 @@ extern "C" int ou_unpad_limit(const float* x, const float* mix_rms, float* out, 
 extern "C" int ou_pack_blocked(const float* src, void* dst, int batch, int channels, int t,
                                void* stream) {
   OU_REQUIRE(src && dst, "ou_pack_blocked: null pointer");
-  OU_REQUIRE(batch > 0 && t > 0 && channels > 0 && channels % 8 == 0, "ou_pack_blocked: bad shape");
+  OU_REQUIRE(batch > 0 && t > 0 && channels > 0 && channels % 16 == 0, "ou_pack_blocked: bad shape");
   dim3 grid(ou::ceil_div(t, 256), channels / 8, batch);
   ou::pack_blocked_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, channels, t);
   return ou::check_launch("ou_pack_blocked");
@@ -270,7 +270,7 @@ extern "C" int ou_pack_blocked(const float* src, void* dst, int batch, int chann
 extern "C" int ou_unpack_blocked(const void* src, float* dst, int batch, int channels, int t,
                                  void* stream) {
   OU_REQUIRE(src && dst, "ou_unpack_blocked: null pointer");
-  OU_REQUIRE(batch > 0 && t > 0 && channels > 0 && channels % 8 == 0, "ou_unpack_blocked: bad shape");
+  OU_REQUIRE(batch > 0 && t > 0 && channels > 0 && channels % 16 == 0, "ou_unpack_blocked: bad shape");
   dim3 grid(ou::ceil_div(t, 256), channels / 8, batch);
   ou::unpack_blocked_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src, dst,
                                                                     channels, t);

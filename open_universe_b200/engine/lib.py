@@ -16,7 +16,7 @@ OU_ABI_VERSION = 1
 
 class ConvParams(Structure):
     _fields_ = [
-        ("x", c_void_p), ("w", c_void_p), ("bias", c_void_p), ("add1", c_void_p),
+        ("x", c_void_p), ("w", c_void_p), ("w_tc", c_void_p), ("bias", c_void_p), ("add1", c_void_p),
         ("add2", c_void_p), ("gamma", c_void_p), ("beta", c_void_p), ("out", c_void_p),
         ("out_f32_tm", c_void_p),
         ("batch", c_int32), ("cin", c_int32), ("t_in", c_int32),

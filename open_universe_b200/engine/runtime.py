@@ -46,15 +46,36 @@ def choose_npad(n):
     return 32
 
 
+def channel_block(c):
+    """Channel block CB of the blocked activation layout [B][C/CB][T][CB] (csrc/common.cuh cl_cb)."""
+    if c % 16:
+        raise ValueError(f"blocked tensors need a multiple of 16 channels, got {c}")
+    return 64 if c % 64 == 0 else (32 if c % 32 == 0 else 16)
+
+
+def alloc_blocked(b, c, t, device):
+    cb = channel_block(c)
+    return torch.empty(b, c // cb, t, cb, dtype=torch.bfloat16, device=device)
+
+
 def pack_conv_weights(fc, device):
-    """(N, taps, K) fp32 -> bf16 [taps][kpad/8][npad][8] (layout of ou_conv_params.w)."""
+    """(N, taps, K) fp32 -> bf16 [taps][kpad/8][npad][8] (ou_conv_params.w, mma.sync / naive kernels)
+    and, for stride-1 geometry, [taps][cin/CB][npad][CB] K-major tiles (ou_conv_params.w_tc, tcgen05)."""
     n, taps, k = fc.w.shape
     kpad, npad = round_up(k, 32), choose_npad(n)
+    src = fc.w.to(device).permute(1, 2, 0)                       # (taps, K, N)
     w = torch.zeros(taps, kpad, npad, dtype=torch.float32, device=device)
-    w[:, :k, :n] = fc.w.to(device).permute(1, 2, 0)
+    w[:, :k, :n] = src
     w = w.reshape(taps, kpad // 8, 8, npad).permute(0, 1, 3, 2).contiguous()
-    return {"w": w.to(torch.bfloat16), "bias": fc.bias.to(device).contiguous(), "kpad": kpad,
-            "npad": npad}
+    out = {"w": w.to(torch.bfloat16), "bias": fc.bias.to(device).contiguous(), "kpad": kpad,
+           "npad": npad, "w_tc": None}
+    if fc.s == 1:
+        cb = channel_block(fc.cin)
+        wt = torch.zeros(taps, k, npad, dtype=torch.float32, device=device)
+        wt[:, :, :n] = src
+        wt = wt.reshape(taps, k // cb, cb, npad).permute(0, 1, 3, 2).contiguous()
+        out["w_tc"] = wt.to(torch.bfloat16)
+    return out
 
 
 def alloc_buffers(prog, device, skip=()):
@@ -64,8 +85,7 @@ def alloc_buffers(prog, device, skip=()):
         if name in skip:
             continue
         if spec.kind == "blocked":
-            bufs[name] = torch.empty(b, spec.channels // 8, spec.length, 8, dtype=torch.bfloat16,
-                                     device=device)
+            bufs[name] = alloc_blocked(b, spec.channels, spec.length, device)
         elif spec.kind == "f32_tm":
             bufs[name] = torch.empty(b, spec.length, spec.channels, dtype=torch.float32,
                                      device=device)
@@ -110,6 +130,7 @@ def launch_conv(op, bufs, batch, gamma=None, beta=None, film_bstride=0, naive=Fa
     prm = lib.ConvParams()
     prm.x = bufs[op.src].data_ptr()
     prm.w = pk["w"].data_ptr()
+    prm.w_tc = pk["w_tc"].data_ptr() if pk["w_tc"] is not None else None
     prm.bias = pk["bias"].data_ptr()
     prm.add1 = bufs[op.add1].data_ptr() if op.add1 else None
     prm.add2 = bufs[op.add2].data_ptr() if op.add2 else None
@@ -195,21 +216,21 @@ class Executor:
 
 # ------------------------------------------------------------------------------------ layouts
 def pack_blocked(x):
-    """(B, C, T) fp32 -> blocked bf16 [B][C/8][T][8]."""
+    """(B, C, T) fp32 -> blocked bf16 [B][C/CB][T][CB]."""
     require_cuda(x)
     b, c, t = x.shape
     x = x.contiguous().float()
-    out = torch.empty(b, c // 8, t, 8, dtype=torch.bfloat16, device=x.device)
+    out = alloc_blocked(b, c, t, x.device)
     lib.check(lib.load().ou_pack_blocked(_ptr(x), _ptr(out), b, c, t, _stream()))
     return out
 
 
 def unpack_blocked(xb):
-    """blocked bf16 [B][C/8][T][8] -> (B, C, T) fp32."""
+    """blocked bf16 [B][C/CB][T][CB] -> (B, C, T) fp32."""
     require_cuda(xb)
-    b, c8, t, _ = xb.shape
-    out = torch.empty(b, c8 * 8, t, dtype=torch.float32, device=xb.device)
-    lib.check(lib.load().ou_unpack_blocked(_ptr(xb), _ptr(out), b, c8 * 8, t, _stream()))
+    b, nblk, t, cb = xb.shape
+    out = torch.empty(b, nblk * cb, t, dtype=torch.float32, device=xb.device)
+    lib.check(lib.load().ou_unpack_blocked(_ptr(xb), _ptr(out), b, nblk * cb, t, _stream()))
     return out
 
 
@@ -318,7 +339,8 @@ class ScoreRunner:
         """cond_blocked: list of blocked bf16 conditioning tensors (coarsest first).  Runs the
         step-invariant signal_cond_proj 1x1 convs once."""
         for lvl, c in enumerate(cond_blocked):
-            want = (self.batch, self.cond_channels[lvl] // 8, self.cond_lengths[lvl], 8)
+            cb = channel_block(self.cond_channels[lvl])
+            want = (self.batch, self.cond_channels[lvl] // cb, self.cond_lengths[lvl], cb)
             if tuple(c.shape) != want:
                 raise ValueError(f"conditioning tensor {lvl} has blocked shape {tuple(c.shape)}, "
                                  f"expected {want}")

@@ -122,7 +122,7 @@ def test_gru_vs_explicit(hidden, B, T, add):
         bufs["add"] = addt
     E.run_gru(op, bufs, quant=False)
     want = bufs["out"]
-    out = torch.empty(B, 2 * H // 8, T, 8, dtype=torch.bfloat16, device=DEV)
+    out = R.alloc_blocked(B, 2 * H, T, DEV)
     # keep every device tensor referenced until the kernel has run (raw pointers are passed)
     d_gx, d_w, d_b = gx.to(DEV), w_hh.to(DEV), b_hh.to(DEV)
     d_add = R.pack_blocked(addt.to(DEV)) if add else None
@@ -195,7 +195,7 @@ def test_input_and_output_kernels():
     b = torch.randn(C, generator=g)
     sc = torch.tensor([0.5, 2.0])
     want = torch.nn.functional.conv1d(x * sc[:, None, None], w[:, None, :], b, padding="same")
-    out = torch.empty(B, C // 8, T, 8, dtype=torch.bfloat16, device=DEV)
+    out = R.alloc_blocked(B, C, T, DEV)
     L = lib.load()
     d_x, d_w, d_b, d_sc = x.to(DEV), w.to(DEV), b.to(DEV), sc.to(DEV)
     lib.check(L.ou_input_conv(R._ptr(d_x), R._ptr(d_w), R._ptr(d_b), R._ptr(d_sc), R._ptr(out), B, T, C,
