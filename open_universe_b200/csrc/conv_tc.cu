@@ -2,28 +2,33 @@
 // ou_conv1d for stride-1 input geometry (conv1/conv2/conv3, transposed up convs, 1x1s, GRU input
 // projections: > 80 % of the FLOPs of a score step).  Contract: include/ou_b200.h.
 //
-// Persistent, warp-specialised CTA (one per SM):
-//   warp 0      producer   : TMA tensor loads (cp.async.bulk.tensor, UTMALDG) global -> smem rings
-//                            in the hardware 128B/64B/32B swizzle; out-of-range rows ("same"
-//                            padding, tile overrun) are zero-filled by the TMA unit
-//   warp 1      MMA issuer : one elected lane issues tcgen05.mma.cta_group::1.kind::f16
-//                            (bf16 x bf16 -> fp32 in TMEM); tcgen05.commit frees smem stages and
-//                            publishes accumulators; owns the TMEM allocation
-//   warps 2-5   transform  : only for layers with a fused input PReLU: element-wise pass over each
-//                            landed A stage, fence.proxy.async, hand-over to the MMA warp
-//   warps 6-9   epilogue   : tcgen05.ld accumulator rows -> registers; bias / FiLM staged in smem,
-//                            residual vectors prefetched before the accumulator is ready; 16-byte
-//                            bf16 stores in the blocked layout (or fp32 time-major)
+// Persistent, warp-specialised CTA (one per SM, 448 threads):
+//   warp 0       producer   : TMA tensor loads (cp.async.bulk.tensor, UTMALDG) global -> smem rings
+//                             in the hardware 128B/64B/32B swizzle; rows outside the sequence ("same"
+//                             padding, tile overrun) are zero-filled by the TMA unit
+//   warp 1       MMA issuer : tcgen05.mma.cta_group::1.kind::f16 (bf16 x bf16 -> fp32 in TMEM) issued
+//                             by one lane from straight-line code (taps / K steps are template
+//                             parameters: the issue loop is pure scalar latency); tcgen05.commit frees
+//                             smem stages and publishes accumulators; owns the TMEM allocation
+//   warps 2-5    transform  : only for layers with a fused input PReLU: element-wise pass over each
+//                             landed A stage, fence.proxy.async, hand-over to the MMA warp
+//   warps 6-13   epilogue   : tcgen05.ld accumulator rows -> registers; every per-column constant
+//                             (bias, FiLM gamma/beta, residual scales) is folded into three smem
+//                             coefficient vectors so a column costs  y = c0*(acc+add1) + c2*add2 + c1;
+//                             residual vectors are prefetched before the accumulator is ready;
+//                             16-byte bf16 stores in the blocked layout (or fp32 time-major)
 // TMEM holds two accumulator buffers (2 x BN columns): the epilogue of tile i overlaps the MMAs of
 // tile i+1.
 //
 // Operand layout: the blocked activation layout [B][C/CB][T][CB] makes one time step of one
 // channel block a contiguous CB*2-byte row, i.e. a K-major operand row; a TMA box of (CB channels x
 // 128+taps-1 time steps) lands as the canonical swizzled K-major tile.  A conv tap is a shift by
-// whole rows: the A descriptor's start address advances by q rows (base_offset carries the swizzle
-// phase), so ONE staged tile feeds all taps.  Weights are pre-packed per (tap, K block) as
-// [npad][CB] K-major tiles; a CTA's N-slice stays resident in shared memory across all its M tiles
-// when it fits (C <= 128), otherwise it streams from L2 through a ring.
+// whole rows: the A descriptor's start address advances by q rows (the hardware swizzle is a
+// function of the shared-memory address bits, so base_offset stays 0 -- verified on B200 against
+// the fp32 reference kernel for the 128B, 64B and 32B modes), and ONE staged tile feeds all taps.
+// Weights are pre-packed per (tap, K block) as [npad][CB] K-major tiles; a CTA's N-slice stays
+// resident in shared memory across all its M tiles when it fits (C <= 128), otherwise it streams
+// from L2 through a ring.
 #include <cuda.h>
 
 #include <cstdlib>
@@ -34,8 +39,8 @@ namespace ou {
 namespace tc {
 
 constexpr int BM = 128;
-constexpr int NTHREADS = 320;
-constexpr int XF_WARP0 = 2, EPI_WARP0 = 6;
+constexpr int XF_WARP0 = 2, EPI_WARP0 = 6, N_EPI_WARPS = 8;
+constexpr int NTHREADS = (EPI_WARP0 + N_EPI_WARPS) * 32;   // 448
 constexpr int MAX_A_STAGES = 8, MAX_B_STAGES = 16;
 
 struct TcArgs {
@@ -43,8 +48,7 @@ struct TcArgs {
   int cb;              // channels per K block (= channel block of the input layout: 64 / 32 / 16)
   int row_bytes;       // cb * 2
   int n_kblocks;       // cin / cb
-  int arows;           // rows per A stage: BM + taps - 1 (shared by all taps) or BM (per-tap mode)
-  int a_per_tap;       // 1: one A stage per (K block, tap) loaded at shifted coordinates
+  int arows;           // rows per A stage: BM + taps - 1
   int bn;              // N per CTA tile
   int n_ntiles;        // npad / bn
   int m_tiles;         // ceil(rows / BM) per clip
@@ -56,9 +60,19 @@ struct TcArgs {
   uint32_t a_tx_bytes, b_tx_bytes;         // bytes one TMA box delivers
   uint32_t idesc;
   uint32_t tmem_cols;
-  uint32_t desc_hi;    // descriptor bits [32,64) without base_offset: SBO, version, layout type
-  int base_off_mode;   // 1: base_offset = (start_address >> 7) & 7   0: always 0
+  uint32_t desc_hi;    // descriptor bits [32,64): SBO, version, layout type (base_offset = 0)
   long long* trace;    // debug: [role 0..3][tile 0..63][event 0..3] clock64 stamps of CTA 0 (or NULL)
+};
+
+// Everything the warp roles share, resolved once per CTA (shared-memory addresses are 32-bit).
+struct Ctx {
+  uint32_t smA, smB;                         // stage rings
+  uint32_t full_a, ready_a, empty_a;         // barrier arrays (8 bytes per stage)
+  uint32_t full_b, empty_b;
+  uint32_t tmem_full, tmem_empty;            // [2]
+  uint32_t coef;                             // fp32 [2 buffers][c0 | c1 | c2][bn]
+  uint32_t tmem_base;
+  int nt, n0, mt0, mt_stride;
 };
 
 __device__ __forceinline__ void trace_ev(const TcArgs& a, int role, int tile_i, int ev) {
@@ -146,16 +160,13 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
                : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,"
-      "%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
         "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
-        "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),
-        "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]),
-        "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        "=r"(r[15])
       : "r"(taddr)
       : "memory");
 }
@@ -169,15 +180,25 @@ __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
                : "l"(p));
   return v;
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
-
-// K-major swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1):
-//   [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major: 1) | [32,46) SBO>>4 (8 rows)
-//   [46,48) version=1 | [49,52) base_offset | [61,64) layout (2 = 128B, 4 = 64B, 6 = 32B swizzle)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t desc_hi, int base_off_mode) {
-  uint32_t hi = desc_hi;
-  if (base_off_mode) hi |= ((saddr >> 7) & 7u) << (49 - 32);
-  return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)hi << 32);
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_f1(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_u4(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void epi_bar_sync() {
+  asm volatile("bar.sync 1, %0;" ::"n"(N_EPI_WARPS * 32) : "memory");
 }
 
 struct Ring {
@@ -191,322 +212,410 @@ struct Ring {
   }
 };
 
+// ================================================================================ producer
+__device__ __forceinline__ void producer_role(const TcArgs& a, const Ctx& c, const CUtensorMap* tm_a,
+                                              const CUtensorMap* tm_w) {
+  const ou_conv_params& p = a.p;
+  Ring ra, rb;
+  bool b_loaded = false;
+  const int taps = p.taps;
+  int ti = 0;
+  for (int mt = c.mt0; mt < a.total_m_tiles; mt += c.mt_stride, ti++) {
+    const int b = mt / a.m_tiles;
+    const int m0 = (mt - b * a.m_tiles) * BM;
+    for (int kb = 0; kb < a.n_kblocks; kb++) {
+      mbar_wait(c.empty_a + 8u * ra.stage, ra.phase ^ 1);
+      if (kb == 0) trace_ev(a, 0, ti, 0);
+      mbar_arrive_expect_tx(c.full_a + 8u * ra.stage, a.a_tx_bytes);
+      // rows [m0 + tap_off, +arows) of clip b, channel block kb; TMA zero-fills rows outside [0, T)
+      tma_load_4d(c.smA + ra.stage * a.a_stage_bytes, tm_a, 0, m0 + p.tap_off, kb, b,
+                  c.full_a + 8u * ra.stage);
+      ra.advance(a.a_stages);
+      if (!(a.resident && b_loaded)) {
+        for (int q = 0; q < taps; q++) {
+          mbar_wait(c.empty_b + 8u * rb.stage, rb.phase ^ 1);
+          mbar_arrive_expect_tx(c.full_b + 8u * rb.stage, a.b_tx_bytes);
+          tma_load_3d(c.smB + rb.stage * a.b_stage_bytes, tm_w, 0, c.n0, q * a.n_kblocks + kb,
+                      c.full_b + 8u * rb.stage);
+          rb.advance(a.b_stages);
+        }
+      }
+    }
+    trace_ev(a, 0, ti, 1);
+    b_loaded = true;
+  }
+}
+
+// ================================================================================ MMA issuer
+// Executed by the whole warp (uniform control flow, cheap uniform-datapath address math); only the
+// tcgen05 instructions themselves are issued by lane 0.
+template <int TAPS, int K16>
+__device__ __forceinline__ void mma_role(const TcArgs& a, const Ctx& c, bool use_xf, int lane) {
+  Ring ra, rb;
+  int acc = 0;
+  uint32_t acc_phase = 0;
+  bool b_waited = false;
+  const uint32_t a_stride = a.a_stage_bytes, b_stride = a.b_stage_bytes;
+  const uint32_t row_units = (uint32_t)a.row_bytes >> 4;   // tap shift in 16-byte descriptor units
+  const uint64_t hi64 = (uint64_t)a.desc_hi << 32;
+  const uint32_t idesc = a.idesc;
+  const bool resident = a.resident != 0;
+  const int n_kblocks = a.n_kblocks, a_stages = a.a_stages, b_stages = a.b_stages;
+  const uint32_t a_ready = use_xf ? c.ready_a : c.full_a;
+  const bool issuer = lane == 0;
+  int ti = 0;
+  for (int mt = c.mt0; mt < a.total_m_tiles; mt += c.mt_stride, ti++) {
+    mbar_wait(c.tmem_empty + 8u * acc, acc_phase ^ 1);
+    tc_fence_after();
+    if (issuer) trace_ev(a, 1, ti, 0);
+    const uint32_t d_tmem = c.tmem_base + (uint32_t)(acc * a.bn);
+    uint32_t accumulate = 0;
+    for (int kb = 0; kb < n_kblocks; kb++) {
+      mbar_wait(a_ready + 8u * ra.stage, ra.phase);
+      tc_fence_after();
+      if (issuer && kb == 0) trace_ev(a, 1, ti, 1);
+      const uint32_t a_lo0 = (((c.smA + ra.stage * a_stride) >> 4) & 0x3FFFu) | (1u << 16);
+#pragma unroll
+      for (int q = 0; q < TAPS; q++) {
+        int bstage;
+        if (resident) {
+          bstage = kb * TAPS + q;
+          if (!b_waited) {
+            mbar_wait(c.full_b + 8u * bstage, 0);
+            tc_fence_after();
+          }
+        } else {
+          bstage = rb.stage;
+          mbar_wait(c.full_b + 8u * bstage, rb.phase);
+          tc_fence_after();
+        }
+        const uint32_t b_lo = (((c.smB + bstage * b_stride) >> 4) & 0x3FFFu) | (1u << 16);
+        const uint32_t a_lo = a_lo0 + q * row_units;
+        if (issuer) {
+#pragma unroll
+          for (int kk = 0; kk < K16; kk++) {
+            // k16 step inside the swizzled row: +32 bytes = +2 descriptor address units
+            umma_f16(d_tmem, hi64 | (a_lo + 2 * kk), hi64 | (b_lo + 2 * kk), idesc, accumulate);
+            accumulate = 1;
+          }
+          if (!resident) umma_commit(c.empty_b + 8u * bstage);
+        }
+        if (!resident) rb.advance(b_stages);
+      }
+      if (issuer) umma_commit(c.empty_a + 8u * ra.stage);
+      ra.advance(a_stages);
+    }
+    if (issuer) {
+      umma_commit(c.tmem_full + 8u * acc);
+      trace_ev(a, 1, ti, 3);
+    }
+    __syncwarp();
+    b_waited = true;
+    acc ^= 1;
+    if (acc == 0) acc_phase ^= 1;
+  }
+}
+
+// ================================================================================ transform
+__device__ __forceinline__ uint4 prelu_vec(uint4 v, float slope) {
+  uint32_t* w = reinterpret_cast<uint32_t*>(&v);
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const float2 f = bf2_to_f2(w[k]);
+    w[k] = f2_to_bf2(prelu_f(f.x, slope), prelu_f(f.y, slope));
+  }
+  return v;
+}
+
+__device__ __forceinline__ void transform_role(const TcArgs& a, const Ctx& c, int xt, int lane) {
+  Ring ra;
+  const float slope = a.p.prelu_in;
+  const int nvec = (int)(a.a_tx_bytes >> 4);
+  int ti = 0;
+  for (int mt = c.mt0; mt < a.total_m_tiles; mt += c.mt_stride, ti++) {
+    for (int kb = 0; kb < a.n_kblocks; kb++) {
+      mbar_wait(c.full_a + 8u * ra.stage, ra.phase);
+      if (xt == 0 && kb == 0) trace_ev(a, 2, ti, 0);
+      const uint32_t base = c.smA + ra.stage * a.a_stage_bytes;
+      int i = xt;
+      for (; i + 3 * 128 < nvec; i += 4 * 128) {   // 4 independent vectors in flight
+        uint4 v0 = lds_u4(base + (uint32_t)i * 16), v1 = lds_u4(base + (uint32_t)(i + 128) * 16);
+        uint4 v2 = lds_u4(base + (uint32_t)(i + 256) * 16), v3 = lds_u4(base + (uint32_t)(i + 384) * 16);
+        sts_u4(base + (uint32_t)i * 16, prelu_vec(v0, slope));
+        sts_u4(base + (uint32_t)(i + 128) * 16, prelu_vec(v1, slope));
+        sts_u4(base + (uint32_t)(i + 256) * 16, prelu_vec(v2, slope));
+        sts_u4(base + (uint32_t)(i + 384) * 16, prelu_vec(v3, slope));
+      }
+      for (; i < nvec; i += 128) sts_u4(base + (uint32_t)i * 16, prelu_vec(lds_u4(base + (uint32_t)i * 16), slope));
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(c.ready_a + 8u * ra.stage);
+      if (xt == 0 && kb == a.n_kblocks - 1) trace_ev(a, 2, ti, 2);
+      ra.advance(a.a_stages);
+    }
+  }
+}
+
+// ================================================================================ epilogue
+// NADD: number of residual inputs (0, 1: add1, 2: add1 + add2); NPRELU: output PReLUs (0, 1, 2).
+// Eight warps: warp pair (w, w+4) shares TMEM lane quarter w%4 and splits every 32-column chunk
+// into two 16-column halves.
+template <int NADD, int NPRELU, bool F32TM>
+__device__ __forceinline__ void epilogue_role(const TcArgs& a, const Ctx& c, int warp, int lane) {
+  const ou_conv_params& p = a.p;
+  const int quarter = warp & 3;
+  const int half = (warp - EPI_WARP0) >> 2;
+  const int row = quarter * 32 + lane;
+  const int et = threadIdx.x - EPI_WARP0 * 32;   // 0..255
+  const int bn = a.bn;
+  const int cout = p.cout, up = p.up, t_out = p.t_out, n_total = p.n;
+  const int cbo = cl_cb(cout);
+  const int cbo_shift = cbo == 64 ? 6 : (cbo == 32 ? 5 : 4);
+  const size_t blk_stride = (size_t)t_out * cbo;
+  const int n0 = c.n0;
+  const int n0_ph = n0 / cout, n0_co = n0 - n0_ph * cout;
+  const __nv_bfloat16* add1 = (const __nv_bfloat16*)p.add1;
+  const __nv_bfloat16* add2 = (const __nv_bfloat16*)p.add2;
+  __nv_bfloat16* outp = (__nv_bfloat16*)p.out;
+  const float s1 = p.scale1, s2 = p.scale2;
+  const float slope1 = p.prelu_out, slope2 = p.prelu_out2;
+  const bool has_film = p.gamma != nullptr;
+
+  int acc = 0;
+  uint32_t acc_phase = 0;
+  int ti = 0;
+  for (int mt = c.mt0; mt < a.total_m_tiles; mt += c.mt_stride, ti++) {
+    const int b = mt / a.m_tiles;
+    const int m0 = (mt - b * a.m_tiles) * BM;
+    const int j = m0 + row;
+    const bool row_ok = j < p.rows;
+    // per-column coefficients: y = c0*(acc + add1) + c2*add2 + c1   (see header comment)
+    const uint32_t coef = c.coef + (uint32_t)(acc * 3 * bn) * 4u;
+    if (ti < 2 || has_film) {
+      for (int i = et; i < bn; i += N_EPI_WARPS * 32) {
+        const int n = n0 + i;
+        float g = 1.f, be = 0.f, bias = 0.f;
+        if (n < n_total) {
+          const int co = n % cout;
+          if (has_film) {
+            g = p.gamma[(size_t)b * p.film_bstride + co];
+            be = p.beta[(size_t)b * p.film_bstride + co];
+          }
+          if (p.bias) bias = p.bias[n];
+        }
+        const float c0 = F32TM ? 1.f : g * s1 * s2;
+        sts_f1(coef + 4u * i, c0);
+        sts_f1(coef + 4u * (bn + i), F32TM ? bias : fmaf(c0, bias, be));
+        sts_f1(coef + 4u * (2 * bn + i), g * s2);
+      }
+      epi_bar_sync();   // coefficients visible to all eight epilogue warps
+    }
+    if (row == 0 && half == 0) trace_ev(a, 3, ti, 0);
+
+    const size_t clip_base = (size_t)b * cout * t_out;
+    const int t_row = j * up;
+    // element offset of the 8-channel output vector at tile column nl (multiple of 8), or -1
+    auto out_offset = [&](int nl) -> long {
+      int co = n0_co + nl, ph = n0_ph;
+      while (co >= cout) co -= cout, ph++;
+      const int t = t_row + ph;
+      if (!row_ok || n0 + nl >= n_total || t >= t_out) return -1;
+      return (long)(clip_base + (size_t)(co >> cbo_shift) * blk_stride + (size_t)t * cbo + (co & (cbo - 1)));
+    };
+    uint4 pre1[2], pre2[2];
+    auto prefetch = [&](int col) {
+#pragma unroll
+      for (int g = 0; g < 2; g++) {
+        pre1[g] = make_uint4(0u, 0u, 0u, 0u);
+        pre2[g] = make_uint4(0u, 0u, 0u, 0u);
+        if (NADD > 0) {
+          const long off = out_offset(col + g * 8);
+          if (off >= 0) {
+            pre1[g] = ldg_nc_v4(add1 + off);
+            if (NADD > 1) pre2[g] = ldg_nc_v4(add2 + off);
+          }
+        }
+      }
+    };
+    prefetch(half * 16);   // residuals of the first chunk are fetched while the MMAs still run
+
+    mbar_wait(c.tmem_full + 8u * acc, acc_phase);
+    tc_fence_after();
+    if (row == 0 && half == 0) trace_ev(a, 3, ti, 1);
+    const uint32_t taddr = c.tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * bn + half * 16);
+    for (int c0 = 0; c0 < bn; c0 += 32) {
+      const int col = c0 + half * 16;
+      uint32_t r[16];
+      tmem_ld16(taddr + (uint32_t)c0, r);
+      tmem_ld_wait();
+      const bool last = c0 + 32 >= bn;
+      if (last) {
+        // accumulator fully read by this warp: hand the TMEM buffer back before the store phase
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(c.tmem_empty + 8u * acc);
+        if (row == 0 && half == 0) trace_ev(a, 3, ti, 2);
+      }
+      uint4 cur1[2], cur2[2];
+#pragma unroll
+      for (int g = 0; g < 2; g++) cur1[g] = pre1[g], cur2[g] = pre2[g];
+      if (!last) prefetch(col + 32);
+#pragma unroll
+      for (int g = 0; g < 2; g++) {
+        const int nl = col + g * 8;
+        if (!row_ok || n0 + nl >= n_total) continue;
+        const float4 k0a = lds_f4(coef + 4u * nl), k0b = lds_f4(coef + 4u * (nl + 4));
+        const float4 k1a = lds_f4(coef + 4u * (bn + nl)), k1b = lds_f4(coef + 4u * (bn + nl + 4));
+        const float k0[8] = {k0a.x, k0a.y, k0a.z, k0a.w, k0b.x, k0b.y, k0b.z, k0b.w};
+        const float k1[8] = {k1a.x, k1a.y, k1a.z, k1a.w, k1b.x, k1b.y, k1b.z, k1b.w};
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = __uint_as_float(r[g * 8 + i]);
+        if (F32TM) {
+#pragma unroll
+          for (int i = 0; i < 8; i++) v[i] += k1[i];
+          float4* dst = reinterpret_cast<float4*>(p.out_f32_tm + ((size_t)b * p.rows + j) * n_total + n0 + nl);
+          dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+          dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+          continue;
+        }
+        const long off = out_offset(nl);
+        if (off < 0) continue;
+        if (NADD > 0) {
+          const uint32_t* pa = reinterpret_cast<const uint32_t*>(&cur1[g]);
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            const float2 f = bf2_to_f2(pa[i]);
+            v[2 * i] += f.x, v[2 * i + 1] += f.y;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = fmaf(k0[i], v[i], k1[i]);
+        if (NADD > 1) {
+          const float4 k2a = lds_f4(coef + 4u * (2 * bn + nl)), k2b = lds_f4(coef + 4u * (2 * bn + nl + 4));
+          const float k2[8] = {k2a.x, k2a.y, k2a.z, k2a.w, k2b.x, k2b.y, k2b.z, k2b.w};
+          const uint32_t* pa = reinterpret_cast<const uint32_t*>(&cur2[g]);
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            const float2 f = bf2_to_f2(pa[i]);
+            v[2 * i] = fmaf(k2[2 * i], f.x, v[2 * i]);
+            v[2 * i + 1] = fmaf(k2[2 * i + 1], f.y, v[2 * i + 1]);
+          }
+        }
+        if (NPRELU > 0) {
+#pragma unroll
+          for (int i = 0; i < 8; i++) v[i] = prelu_f(v[i], slope1);
+        }
+        if (NPRELU > 1) {
+#pragma unroll
+          for (int i = 0; i < 8; i++) v[i] = prelu_f(v[i], slope2);
+        }
+        const uint4 o = make_uint4(f2_to_bf2(v[0], v[1]), f2_to_bf2(v[2], v[3]), f2_to_bf2(v[4], v[5]),
+                                   f2_to_bf2(v[6], v[7]));
+        *reinterpret_cast<uint4*>(outp + off) = o;
+      }
+    }
+    if (row == 0 && half == 0) trace_ev(a, 3, ti, 3);
+    acc ^= 1;
+    if (acc == 0) acc_phase ^= 1;
+  }
+}
+
+// ================================================================================ kernel
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv1d_tc_kernel(const TcArgs a, const __grid_constant__ CUtensorMap tm_a,
                  const __grid_constant__ CUtensorMap tm_w) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  extern __shared__ uint8_t smem_raw[];
   const ou_conv_params& p = a.p;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  // shared memory carve-up (stages 1024-byte aligned for the swizzle pattern)
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smA = smem;
-  uint8_t* smB = smA + (size_t)a.a_stages * a.a_stage_bytes;
-  uint8_t* tail = smB + (size_t)a.b_stages * a.b_stage_bytes;
-  uint64_t* full_a = reinterpret_cast<uint64_t*>(tail);   // [MAX_A_STAGES]
-  uint64_t* ready_a = full_a + MAX_A_STAGES;
-  uint64_t* empty_a = ready_a + MAX_A_STAGES;
-  uint64_t* full_b = empty_a + MAX_A_STAGES;               // [MAX_B_STAGES]
-  uint64_t* empty_b = full_b + MAX_B_STAGES;
-  uint64_t* tmem_full = empty_b + MAX_B_STAGES;            // [2]
-  uint64_t* tmem_empty = tmem_full + 2;                    // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  float* bias_s = reinterpret_cast<float*>(tmem_slot + 4); // [bn]
-  float* film_s = bias_s + a.bn;                            // [2 buffers][gamma bn | beta bn]
+  // shared memory carve-up in the 32-bit shared window (stages 1024-byte aligned for the swizzle)
+  Ctx c;
+  const uint32_t raw = smem_u32(smem_raw);
+  c.smA = (raw + 1023u) & ~1023u;
+  c.smB = c.smA + (uint32_t)a.a_stages * a.a_stage_bytes;
+  uint32_t tail = c.smB + (uint32_t)a.b_stages * a.b_stage_bytes;
+  c.full_a = tail;
+  c.ready_a = c.full_a + 8u * MAX_A_STAGES;
+  c.empty_a = c.ready_a + 8u * MAX_A_STAGES;
+  c.full_b = c.empty_a + 8u * MAX_A_STAGES;
+  c.empty_b = c.full_b + 8u * MAX_B_STAGES;
+  c.tmem_full = c.empty_b + 8u * MAX_B_STAGES;
+  c.tmem_empty = c.tmem_full + 16u;
+  const uint32_t tmem_slot = c.tmem_empty + 16u;
+  c.coef = tmem_slot + 16u;
 
   const bool use_xf = p.has_prelu_in != 0;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < a.a_stages; i++) {
-      mbar_init(smem_u32(&full_a[i]), 1);
-      mbar_init(smem_u32(&ready_a[i]), 4);
-      mbar_init(smem_u32(&empty_a[i]), 1);
+      mbar_init(c.full_a + 8u * i, 1);
+      mbar_init(c.ready_a + 8u * i, 4);
+      mbar_init(c.empty_a + 8u * i, 1);
     }
     for (int i = 0; i < a.b_stages; i++) {
-      mbar_init(smem_u32(&full_b[i]), 1);
-      mbar_init(smem_u32(&empty_b[i]), 1);
+      mbar_init(c.full_b + 8u * i, 1);
+      mbar_init(c.empty_b + 8u * i, 1);
     }
     for (int i = 0; i < 2; i++) {
-      mbar_init(smem_u32(&tmem_full[i]), 1);
-      mbar_init(smem_u32(&tmem_empty[i]), 4);
+      mbar_init(c.tmem_full + 8u * i, 1);
+      mbar_init(c.tmem_empty + 8u * i, N_EPI_WARPS);
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), a.tmem_cols);
+  if (warp == 1) tmem_alloc(tmem_slot, a.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(c.tmem_base) : "r"(tmem_slot));
 
   // static tile schedule: this CTA owns N tile `nt` and M tiles mt0, mt0 + stride, ...
-  const int nt = blockIdx.x % a.n_ntiles;
-  const int mt0 = blockIdx.x / a.n_ntiles;
-  const int mt_stride = a.ctas_per_ntile;
-  const int n0 = nt * a.bn;
-  const int taps = p.taps;
-  const int a_loads_per_kb = a.a_per_tap ? taps : 1;
+  c.nt = blockIdx.x % a.n_ntiles;
+  c.mt0 = blockIdx.x / a.n_ntiles;
+  c.mt_stride = a.ctas_per_ntile;
+  c.n0 = c.nt * a.bn;
 
   if (warp == 0) {
-    // ================================ producer ================================
-    if (lane == 0) {
-      Ring ra, rb;
-      bool b_loaded = false;
-      int ti = 0;
-      for (int mt = mt0; mt < a.total_m_tiles; mt += mt_stride, ti++) {
-        const int b = mt / a.m_tiles;
-        const int m0 = (mt - b * a.m_tiles) * BM;
-        for (int kb = 0; kb < a.n_kblocks; kb++) {
-          for (int q = 0; q < taps; q++) {
-            if (q < a_loads_per_kb) {
-              mbar_wait(smem_u32(&empty_a[ra.stage]), ra.phase ^ 1);
-              if (kb == 0 && q == 0) trace_ev(a, 0, ti, 0);
-              const uint32_t bar = smem_u32(&full_a[ra.stage]);
-              mbar_arrive_expect_tx(bar, a.a_tx_bytes);
-              // rows [j0, j0 + arows) of clip b, channel block kb; TMA zero-fills rows outside [0, T)
-              const int j0 = m0 + p.tap_off + (a.a_per_tap ? q : 0);
-              tma_load_4d(smem_u32(smA + (size_t)ra.stage * a.a_stage_bytes), &tm_a, 0, j0, kb, b, bar);
-              ra.advance(a.a_stages);
-            }
-            if (!(a.resident && b_loaded)) {
-              mbar_wait(smem_u32(&empty_b[rb.stage]), rb.phase ^ 1);
-              const uint32_t bar = smem_u32(&full_b[rb.stage]);
-              mbar_arrive_expect_tx(bar, a.b_tx_bytes);
-              tma_load_3d(smem_u32(smB + (size_t)rb.stage * a.b_stage_bytes), &tm_w, 0, n0,
-                          q * a.n_kblocks + kb, bar);
-              rb.advance(a.b_stages);
-            }
-          }
-        }
-        trace_ev(a, 0, ti, 1);
-        b_loaded = true;
-      }
-    }
+    if (lane == 0) producer_role(a, c, &tm_a, &tm_w);
   } else if (warp == 1) {
-    // ================================ MMA issuer ================================
-    Ring ra, rb;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    bool b_waited = false;
-    const int k16_steps = a.cb / 16;
-    int ti = 0;
-    for (int mt = mt0; mt < a.total_m_tiles; mt += mt_stride, ti++) {
-      mbar_wait(smem_u32(&tmem_empty[acc]), acc_phase ^ 1);
-      tc_fence_after();
-      if (lane == 0) trace_ev(a, 1, ti, 0);
-      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * a.bn);
-      for (int kb = 0; kb < a.n_kblocks; kb++) {
-        for (int q = 0; q < taps; q++) {
-          if (q < a_loads_per_kb) {
-            mbar_wait(smem_u32(use_xf ? &ready_a[ra.stage] : &full_a[ra.stage]), ra.phase);
-            if (lane == 0 && kb == 0 && q == 0) trace_ev(a, 1, ti, 1);
-          }
-          int bstage;
-          if (a.resident) {
-            bstage = kb * taps + q;
-            if (!b_waited) mbar_wait(smem_u32(&full_b[bstage]), 0);
-          } else {
-            bstage = rb.stage;
-            mbar_wait(smem_u32(&full_b[bstage]), rb.phase);
-          }
-          tc_fence_after();
-          if (lane == 0) {
-            const uint32_t a_base = smem_u32(smA + (size_t)ra.stage * a.a_stage_bytes) +
-                                    (a.a_per_tap ? 0u : (uint32_t)(q * a.row_bytes));
-            const uint32_t b_base = smem_u32(smB + (size_t)bstage * a.b_stage_bytes);
-            for (int kk = 0; kk < k16_steps; kk++) {
-              const uint64_t ad = make_desc(a_base + kk * 32, a.desc_hi, a.base_off_mode);
-              const uint64_t bd = make_desc(b_base + kk * 32, a.desc_hi, 0);
-              umma_f16(d_tmem, ad, bd, a.idesc, (kb | q | kk) != 0 ? 1u : 0u);
-            }
-            if (!a.resident) umma_commit(smem_u32(&empty_b[bstage]));
-            const bool a_done = a.a_per_tap || q == taps - 1;
-            if (a_done) umma_commit(smem_u32(&empty_a[ra.stage]));
-            if (kb == a.n_kblocks - 1 && q == taps - 1) {
-              umma_commit(smem_u32(&tmem_full[acc]));
-              trace_ev(a, 1, ti, 3);
-            }
-          }
-          __syncwarp();
-          if (!a.resident) rb.advance(a.b_stages);
-          if (a.a_per_tap || q == taps - 1) ra.advance(a.a_stages);
-        }
-      }
-      b_waited = true;
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
+    const int k16 = a.cb / 16;
+    switch (p.taps * 8 + k16) {
+      case 1 * 8 + 1: mma_role<1, 1>(a, c, use_xf, lane); break;
+      case 1 * 8 + 2: mma_role<1, 2>(a, c, use_xf, lane); break;
+      case 1 * 8 + 4: mma_role<1, 4>(a, c, use_xf, lane); break;
+      case 3 * 8 + 1: mma_role<3, 1>(a, c, use_xf, lane); break;
+      case 3 * 8 + 2: mma_role<3, 2>(a, c, use_xf, lane); break;
+      case 3 * 8 + 4: mma_role<3, 4>(a, c, use_xf, lane); break;
+      case 5 * 8 + 1: mma_role<5, 1>(a, c, use_xf, lane); break;
+      case 5 * 8 + 2: mma_role<5, 2>(a, c, use_xf, lane); break;
+      case 5 * 8 + 4: mma_role<5, 4>(a, c, use_xf, lane); break;
+      default: break;   // rejected on the host
     }
   } else if (warp < EPI_WARP0) {
-    // ================================ transform (fused input PReLU) ================================
-    if (use_xf) {
-      const int xt = threadIdx.x - XF_WARP0 * 32;   // 0..127
-      Ring ra;
-      const float slope = p.prelu_in;
-      const int nvec = (int)(a.a_tx_bytes >> 4);
-      int ti = 0;
-      for (int mt = mt0; mt < a.total_m_tiles; mt += mt_stride, ti++) {
-        for (int kb = 0; kb < a.n_kblocks; kb++) {
-          for (int q = 0; q < a_loads_per_kb; q++) {
-            mbar_wait(smem_u32(&full_a[ra.stage]), ra.phase);
-            if (xt == 0 && kb == 0 && q == 0) trace_ev(a, 2, ti, 0);
-            uint4* As = reinterpret_cast<uint4*>(smA + (size_t)ra.stage * a.a_stage_bytes);
-#pragma unroll 4
-            for (int i = xt; i < nvec; i += 128) {
-              uint4 v = As[i];
-              uint32_t* w = reinterpret_cast<uint32_t*>(&v);
-#pragma unroll
-              for (int k = 0; k < 4; k++) {
-                const float2 f = bf2_to_f2(w[k]);
-                w[k] = f2_to_bf2(prelu_f(f.x, slope), prelu_f(f.y, slope));
-              }
-              As[i] = v;
-            }
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&ready_a[ra.stage]));
-            if (xt == 0 && kb == a.n_kblocks - 1) trace_ev(a, 2, ti, 2);
-            ra.advance(a.a_stages);
-          }
-        }
-      }
-    }
+    if (use_xf) transform_role(a, c, threadIdx.x - XF_WARP0 * 32, lane);
   } else {
-    // ================================ epilogue ================================
-    const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
-    const int row = quarter * 32 + lane;
-    const int et = threadIdx.x - EPI_WARP0 * 32;  // 0..127
-    const int cbo = cl_cb(p.cout);
-    const bool blocked_out = p.out_f32_tm == nullptr;
-    const __nv_bfloat16* add1 = (const __nv_bfloat16*)p.add1;
-    const __nv_bfloat16* add2 = (const __nv_bfloat16*)p.add2;
-    for (int i = et; i < a.bn; i += 128) bias_s[i] = (p.bias && n0 + i < p.n) ? p.bias[n0 + i] : 0.f;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    int ti = 0;
-    for (int mt = mt0; mt < a.total_m_tiles; mt += mt_stride, ti++) {
-      const int b = mt / a.m_tiles;
-      const int m0 = (mt - b * a.m_tiles) * BM;
-      const int j = m0 + row;
-      const bool row_ok = j < p.rows;
-      float* film = film_s + acc * 2 * a.bn;
-      if (p.gamma) {
-        for (int i = et; i < a.bn; i += 128) {
-          const int n = n0 + i;
-          const int co = n % p.cout;
-          const bool ok = n < p.n;
-          film[i] = ok ? p.gamma[(size_t)b * p.film_bstride + co] : 0.f;
-          film[a.bn + i] = ok ? p.beta[(size_t)b * p.film_bstride + co] : 0.f;
-        }
+    const int nadd = p.add2 ? 2 : (p.add1 ? 1 : 0);
+    const int nprelu = p.has_prelu_out2 ? 2 : (p.has_prelu_out ? 1 : 0);
+    if (p.out_f32_tm) {
+      epilogue_role<0, 0, true>(a, c, warp, lane);
+    } else {
+      switch (nadd * 3 + nprelu) {
+        case 0: epilogue_role<0, 0, false>(a, c, warp, lane); break;
+        case 1: epilogue_role<0, 1, false>(a, c, warp, lane); break;
+        case 2: epilogue_role<0, 2, false>(a, c, warp, lane); break;
+        case 3: epilogue_role<1, 0, false>(a, c, warp, lane); break;
+        case 4: epilogue_role<1, 1, false>(a, c, warp, lane); break;
+        case 5: epilogue_role<1, 2, false>(a, c, warp, lane); break;
+        case 6: epilogue_role<2, 0, false>(a, c, warp, lane); break;
+        case 7: epilogue_role<2, 1, false>(a, c, warp, lane); break;
+        default: epilogue_role<2, 2, false>(a, c, warp, lane); break;
       }
-      epi_bar_sync();   // bias_s / film_s visible to the four epilogue warps
-      if (row == 0) trace_ev(a, 3, ti, 0);
-
-      // residual vectors of the first 32-column chunk are fetched while the MMAs still run
-      uint4 pre1[4], pre2[4];
-      auto out_offset = [&](int n) -> long {
-        const int ph = n / p.cout;
-        const int co = n - ph * p.cout;
-        const int t = j * p.up + ph;
-        if (!row_ok || n >= p.n || t >= p.t_out) return -1;
-        return (long)cl_off(b, co, t, p.cout, p.t_out, cbo);
-      };
-      auto prefetch = [&](int c0) {
-#pragma unroll
-        for (int g = 0; g < 4; g++) {
-          pre1[g] = make_uint4(0u, 0u, 0u, 0u);
-          pre2[g] = make_uint4(0u, 0u, 0u, 0u);
-          if (blocked_out && (add1 || add2)) {
-            const long off = out_offset(n0 + c0 + g * 8);
-            if (off >= 0) {
-              if (add1) pre1[g] = ldg_nc_v4(add1 + off);
-              if (add2) pre2[g] = ldg_nc_v4(add2 + off);
-            }
-          }
-        }
-      };
-      prefetch(0);
-
-      mbar_wait(smem_u32(&tmem_full[acc]), acc_phase);
-      tc_fence_after();
-      if (row == 0) trace_ev(a, 3, ti, 1);
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * a.bn);
-      for (int c0 = 0; c0 < a.bn; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(taddr + (uint32_t)c0, r);
-        tmem_ld_wait();
-        const bool last = c0 + 32 >= a.bn;
-        if (last) {
-          // accumulator fully read: hand the TMEM buffer back before the store phase
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(&tmem_empty[acc]));
-          if (row == 0) trace_ev(a, 3, ti, 2);
-        }
-        uint4 cur1[4], cur2[4];
-#pragma unroll
-        for (int g = 0; g < 4; g++) cur1[g] = pre1[g], cur2[g] = pre2[g];
-        if (!last) prefetch(c0 + 32);
-#pragma unroll
-        for (int g = 0; g < 4; g++) {
-          const int nl = c0 + g * 8;          // column within the CTA tile
-          const int n = n0 + nl;
-          if (!row_ok || n >= p.n) continue;
-          float v[8];
-#pragma unroll
-          for (int i = 0; i < 8; i++) v[i] = __uint_as_float(r[g * 8 + i]) + bias_s[nl + i];
-          if (!blocked_out) {
-            float4* dst = reinterpret_cast<float4*>(p.out_f32_tm + ((size_t)b * p.rows + j) * p.n + n);
-            dst[0] = make_float4(v[0], v[1], v[2], v[3]);
-            dst[1] = make_float4(v[4], v[5], v[6], v[7]);
-            continue;
-          }
-          const long off = out_offset(n);
-          if (off < 0) continue;
-          if (add1) {
-            const uint32_t* pa = reinterpret_cast<const uint32_t*>(&cur1[g]);
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-              const float2 f = bf2_to_f2(pa[i]);
-              v[2 * i] += f.x, v[2 * i + 1] += f.y;
-            }
-          }
-#pragma unroll
-          for (int i = 0; i < 8; i++) v[i] *= p.scale1;
-          if (add2) {
-            const uint32_t* pa = reinterpret_cast<const uint32_t*>(&cur2[g]);
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-              const float2 f = bf2_to_f2(pa[i]);
-              v[2 * i] += f.x, v[2 * i + 1] += f.y;
-            }
-          }
-#pragma unroll
-          for (int i = 0; i < 8; i++) v[i] *= p.scale2;
-          if (p.gamma) {
-#pragma unroll
-            for (int i = 0; i < 8; i++) v[i] = fmaf(film[nl + i], v[i], film[a.bn + nl + i]);
-          }
-          if (p.has_prelu_out) {
-#pragma unroll
-            for (int i = 0; i < 8; i++) v[i] = prelu_f(v[i], p.prelu_out);
-          }
-          if (p.has_prelu_out2) {
-#pragma unroll
-            for (int i = 0; i < 8; i++) v[i] = prelu_f(v[i], p.prelu_out2);
-          }
-          const uint4 o = make_uint4(f2_to_bf2(v[0], v[1]), f2_to_bf2(v[2], v[3]), f2_to_bf2(v[4], v[5]),
-                                     f2_to_bf2(v[6], v[7]));
-          *reinterpret_cast<uint4*>((__nv_bfloat16*)p.out + off) = o;
-        }
-      }
-      if (row == 0) trace_ev(a, 3, ti, 3);
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, a.tmem_cols);
+  if (warp == 1) tmem_dealloc(c.tmem_base, a.tmem_cols);
 }
 
 // ------------------------------------------------------------------------------------ host side
@@ -532,13 +641,9 @@ static int get_encode() {
   return OU_OK;
 }
 
-static int env_int(const char* name, int dflt) {
-  const char* e = getenv(name);
-  return e ? atoi(e) : dflt;
-}
-
 int plan(const ou_conv_params* p, TcArgs* a) {
   if (p->s != 1 || p->w_tc == nullptr) return OU_ERR_UNSUPPORTED;
+  if (p->taps != 1 && p->taps != 3 && p->taps != 5) return OU_ERR_UNSUPPORTED;
   int bn = 0;
   for (int cand : {256, 128, 64, 32})
     if (p->npad % cand == 0) {
@@ -546,14 +651,13 @@ int plan(const ou_conv_params* p, TcArgs* a) {
       break;
     }
   if (!bn || p->cin % 16 || p->cout % 16) return OU_ERR_UNSUPPORTED;
+  if (p->add2 && !p->add1) return OU_ERR_UNSUPPORTED;
   if (g_num_sms == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (g_num_sms <= 0) g_num_sms = 148;
   }
-  static const int force_per_tap = env_int("OU_TC_PER_TAP", -1);
-  static const int base_off_mode = env_int("OU_TC_BASEOFF", 1);
   a->p = *p;
   a->cb = cl_cb(p->cin);
   a->row_bytes = a->cb * 2;
@@ -562,17 +666,12 @@ int plan(const ou_conv_params* p, TcArgs* a) {
   a->n_ntiles = p->npad / bn;
   a->m_tiles = ceil_div(p->rows, BM);
   a->total_m_tiles = a->m_tiles * p->batch;
-  // One staged A tile serves all taps through row-shifted descriptors when the row is a full
-  // 128-byte swizzle span; narrower rows (C = 32, 48, 80, 96) load one tile per tap instead.
-  a->a_per_tap = (p->taps > 1 && a->row_bytes < 128) ? 1 : 0;
-  if (force_per_tap >= 0 && p->taps > 1) a->a_per_tap = force_per_tap;
-  a->base_off_mode = base_off_mode;
-  a->arows = a->a_per_tap ? BM : BM + p->taps - 1;
+  a->arows = BM + p->taps - 1;
   a->a_tx_bytes = (uint32_t)(a->arows * a->row_bytes);
   a->b_tx_bytes = (uint32_t)(bn * a->row_bytes);
   a->a_stage_bytes = (a->a_tx_bytes + 1023u) & ~1023u;
   a->b_stage_bytes = (a->b_tx_bytes + 1023u) & ~1023u;
-  const int budget = 232448 - 2048 - 5 * bn * 4;   // 227 KB minus alignment slack, barriers, bias / FiLM
+  const int budget = 232448 - 2048 - 6 * bn * 4;   // 227 KB minus alignment slack, barriers, coefficients
   const int nb_all = p->taps * a->n_kblocks;
   if (nb_all <= MAX_B_STAGES && nb_all * (int)a->b_stage_bytes + 3 * (int)a->a_stage_bytes <= budget) {
     a->resident = 1;
@@ -640,7 +739,7 @@ int launch(const ou_conv_params* p, cudaStream_t st) {
   }
   const size_t smem = 1024 + (size_t)a.a_stages * a.a_stage_bytes + (size_t)a.b_stages * a.b_stage_bytes +
                       (3 * MAX_A_STAGES + 2 * MAX_B_STAGES + 4) * sizeof(uint64_t) + 16 +
-                      (size_t)5 * a.bn * sizeof(float);
+                      (size_t)6 * a.bn * sizeof(float);
   static size_t configured = 0;
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(conv1d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
