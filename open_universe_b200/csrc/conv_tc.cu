@@ -201,6 +201,20 @@ __device__ __forceinline__ void epi_bar_sync() {
   asm volatile("bar.sync 1, %0;" ::"n"(N_EPI_WARPS * 32) : "memory");
 }
 
+// One elected lane of a fully converged warp (the compiler keeps warp-uniform operands in uniform
+// registers across this predicate; `if (lane == 0)` would force a per-instruction R2UR shuffle).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P;\n"
+      "elect.sync _|P, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, P;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 struct Ring {
   int stage = 0;
   uint32_t phase = 0;
@@ -262,14 +276,13 @@ __device__ __forceinline__ void mma_role(const TcArgs& a, const Ctx& c, bool use
   const bool resident = a.resident != 0;
   const int n_kblocks = a.n_kblocks, a_stages = a.a_stages, b_stages = a.b_stages;
   const uint32_t a_ready = use_xf ? c.ready_a : c.full_a;
-  const bool issuer = lane == 0;
+  const bool issuer = lane == 0;   // tracing only
   int ti = 0;
   for (int mt = c.mt0; mt < a.total_m_tiles; mt += c.mt_stride, ti++) {
     mbar_wait(c.tmem_empty + 8u * acc, acc_phase ^ 1);
     tc_fence_after();
     if (issuer) trace_ev(a, 1, ti, 0);
     const uint32_t d_tmem = c.tmem_base + (uint32_t)(acc * a.bn);
-    uint32_t accumulate = 0;
     for (int kb = 0; kb < n_kblocks; kb++) {
       mbar_wait(a_ready + 8u * ra.stage, ra.phase);
       tc_fence_after();
@@ -291,25 +304,23 @@ __device__ __forceinline__ void mma_role(const TcArgs& a, const Ctx& c, bool use
         }
         const uint32_t b_lo = (((c.smB + bstage * b_stride) >> 4) & 0x3FFFu) | (1u << 16);
         const uint32_t a_lo = a_lo0 + q * row_units;
-        if (issuer) {
+        if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < K16; kk++) {
             // k16 step inside the swizzled row: +32 bytes = +2 descriptor address units
-            umma_f16(d_tmem, hi64 | (a_lo + 2 * kk), hi64 | (b_lo + 2 * kk), idesc, accumulate);
-            accumulate = 1;
+            umma_f16(d_tmem, hi64 | (a_lo + 2 * kk), hi64 | (b_lo + 2 * kk), idesc,
+                     (kb | q | kk) != 0 ? 1u : 0u);
           }
           if (!resident) umma_commit(c.empty_b + 8u * bstage);
+          if (q == TAPS - 1) umma_commit(c.empty_a + 8u * ra.stage);
+          if (q == TAPS - 1 && kb == n_kblocks - 1) umma_commit(c.tmem_full + 8u * acc);
         }
+        __syncwarp();
         if (!resident) rb.advance(b_stages);
       }
-      if (issuer) umma_commit(c.empty_a + 8u * ra.stage);
       ra.advance(a_stages);
     }
-    if (issuer) {
-      umma_commit(c.tmem_full + 8u * acc);
-      trace_ev(a, 1, ti, 3);
-    }
-    __syncwarp();
+    if (issuer) trace_ev(a, 1, ti, 3);
     b_waited = true;
     acc ^= 1;
     if (acc == 0) acc_phase ^= 1;
