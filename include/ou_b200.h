@@ -69,8 +69,8 @@ typedef struct ou_conv_params {
   const void* w;          /* packed bf16 [taps][kpad/8][npad][8]; element (q, c', n_) = W[n_][q][c'],
                              zero padded; kpad % 32 == 0, npad % 32 == 0 (mma.sync / naive path) */
   const void* w_tc;       /* same weights packed for the tcgen05 path, or NULL: bf16
-                             [taps][cin/CB][npad][CB], CB = channel block of the input layout;
-                             only used when s == 1                                              */
+                             [taps][s*cin/CB][npad][CB], CB = channel block of the input layout
+                             (K index c' = r*cin + ci cut into blocks of CB)                    */
   const float* bias;      /* fp32 [n] or NULL                                                   */
   const void* add1;       /* blocked bf16 (B, cout, t_out) or NULL                         */
   const void* add2;       /* blocked bf16 (B, cout, t_out) or NULL                         */

@@ -47,7 +47,8 @@ struct TcArgs {
   ou_conv_params p;
   int cb;              // channels per K block (= channel block of the input layout: 64 / 32 / 16)
   int row_bytes;       // cb * 2
-  int n_kblocks;       // cin / cb
+  int n_kblocks;       // s * cin / cb  (K block kb <-> input phase r = kb / cin_blocks, channel block kb % cin_blocks)
+  int cin_blocks;      // cin / cb
   int arows;           // rows per A stage: BM + taps - 1
   int bn;              // N per CTA tile
   int n_ntiles;        // npad / bn
@@ -107,12 +108,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2,
-                                            int c3, uint32_t bar) {
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2,
+                                            int c3, int c4, uint32_t bar) {
   asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, "
-      "%4, %5}], [%6];" ::"r"(dst),
-      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, "
+      "%4, %5, %6}], [%7];" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(bar)
       : "memory");
 }
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2,
@@ -241,8 +242,10 @@ __device__ __forceinline__ void producer_role(const TcArgs& a, const Ctx& c, con
       mbar_wait(c.empty_a + 8u * ra.stage, ra.phase ^ 1);
       if (kb == 0) trace_ev(a, 0, ti, 0);
       mbar_arrive_expect_tx(c.full_a + 8u * ra.stage, a.a_tx_bytes);
-      // rows [m0 + tap_off, +arows) of clip b, channel block kb; TMA zero-fills rows outside [0, T)
-      tma_load_4d(c.smA + ra.stage * a.a_stage_bytes, tm_a, 0, m0 + p.tap_off, kb, b,
+      // rows j in [m0 + tap_off, +arows) <-> time steps j*s + r of clip b, channel block kbi;
+      // the TMA unit zero-fills rows outside [0, T/s)
+      const int r = kb / a.cin_blocks, kbi = kb - r * a.cin_blocks;
+      tma_load_5d(c.smA + ra.stage * a.a_stage_bytes, tm_a, 0, r, m0 + p.tap_off, kbi, b,
                   c.full_a + 8u * ra.stage);
       ra.advance(a.a_stages);
       if (!(a.resident && b_loaded)) {
@@ -653,7 +656,9 @@ static int get_encode() {
 }
 
 int plan(const ou_conv_params* p, TcArgs* a) {
-  if (p->s != 1 || p->w_tc == nullptr) return OU_ERR_UNSUPPORTED;
+  // strided input (down convs, st_convs) is read through a (CB, s, T/s, ...) view of the tensor:
+  // needs T divisible by s (always true inside enhance(); odd module-level lengths fall back)
+  if (p->w_tc == nullptr || p->t_in % p->s != 0) return OU_ERR_UNSUPPORTED;
   if (p->taps != 1 && p->taps != 3 && p->taps != 5) return OU_ERR_UNSUPPORTED;
   int bn = 0;
   for (int cand : {256, 128, 64, 32})
@@ -672,7 +677,8 @@ int plan(const ou_conv_params* p, TcArgs* a) {
   a->p = *p;
   a->cb = cl_cb(p->cin);
   a->row_bytes = a->cb * 2;
-  a->n_kblocks = p->cin / a->cb;
+  a->cin_blocks = p->cin / a->cb;
+  a->n_kblocks = p->s * a->cin_blocks;
   a->bn = bn;
   a->n_ntiles = p->npad / bn;
   a->m_tiles = ceil_div(p->rows, BM);
@@ -720,13 +726,14 @@ int launch(const ou_conv_params* p, cudaStream_t st) {
   if (rc) return rc;
   CUtensorMap tm_a, tm_w;
   {
-    // activations: [B][C/CB][T][CB] bf16 -> dims (CB, T, C/CB, B)
-    cuuint64_t dims[4] = {(cuuint64_t)a.cb, (cuuint64_t)p->t_in, (cuuint64_t)a.n_kblocks, (cuuint64_t)p->batch};
-    cuuint64_t strides[3] = {(cuuint64_t)a.row_bytes, (cuuint64_t)p->t_in * a.row_bytes,
-                             (cuuint64_t)p->t_in * a.row_bytes * a.n_kblocks};
-    cuuint32_t box[4] = {(cuuint32_t)a.cb, (cuuint32_t)a.arows, 1, 1};
-    cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = g_encode(&tm_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(p->x), dims, strides,
+    // activations: [B][C/CB][T][CB] bf16 viewed as (CB, s, T/s, C/CB, B): time t = j*s + r
+    const cuuint64_t rowb = (cuuint64_t)a.row_bytes;
+    cuuint64_t dims[5] = {(cuuint64_t)a.cb, (cuuint64_t)p->s, (cuuint64_t)(p->t_in / p->s),
+                          (cuuint64_t)a.cin_blocks, (cuuint64_t)p->batch};
+    cuuint64_t strides[4] = {rowb, rowb * p->s, rowb * p->t_in, rowb * p->t_in * a.cin_blocks};
+    cuuint32_t box[5] = {(cuuint32_t)a.cb, 1, (cuuint32_t)a.arows, 1, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = g_encode(&tm_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(p->x), dims, strides,
                           box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(a.row_bytes),
                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {

@@ -69,7 +69,7 @@ def pack_conv_weights(fc, device):
     w = w.reshape(taps, kpad // 8, 8, npad).permute(0, 1, 3, 2).contiguous()
     out = {"w": w.to(torch.bfloat16), "bias": fc.bias.to(device).contiguous(), "kpad": kpad,
            "npad": npad, "w_tc": None}
-    if fc.s == 1:
+    if True:   # K blocks of the tcgen05 path: c' = r*cin + ci split in channel blocks of the input
         cb = channel_block(fc.cin)
         wt = torch.zeros(taps, k, npad, dtype=torch.float32, device=device)
         wt[:, :, :n] = src
