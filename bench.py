@@ -280,9 +280,14 @@ def run_ours(args):
         execd = sum(op.flops_exec for op, _, _ in prof)
         n = len(prof)
         achieved = algo / (tot_ms * 1e-3) / 1e12
-        roof = {"kernel": "conv1d_mma_kernel (fused implicit-GEMM Conv1d, all launches of the timed region)",
+        traffic = None
+        tp = ROOT / "profiles" / "r1_traffic.json"
+        if tp.exists():
+            traffic = json.loads(tp.read_text()).get("traffic_bytes_per_launch")
+        roof = {"kernel": "ou::tc::conv1d_tc_kernel (tcgen05 fused implicit-GEMM Conv1d; all conv launches of "
+                          "the timed region, CUDA events around each)",
                 "bound": "tensor", "achieved": round(achieved, 2), "peak": tflops_peak,
-                "unit": "TFLOP/s", "frac": round(achieved / tflops_peak, 4), "traffic": None,
+                "unit": "TFLOP/s", "frac": round(achieved / tflops_peak, 4), "traffic": traffic,
                 "peak_source": f"{which} bf16_tflops_sustained (kernel timed inside a long step)",
                 "launches": n, "avg_launch_us": round(tot_ms * 1e3 / n, 2),
                 "algorithmic_gflop_per_launch": round(algo / n / 1e9, 3),

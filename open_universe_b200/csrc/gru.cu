@@ -9,13 +9,16 @@
 // cluster barrier per step.  Everything is fp32 (the recurrence is the precision-critical part).
 #include <cooperative_groups.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace cg = cooperative_groups;
 
 namespace ou {
 
-constexpr int GRU_KPT = 64;  // recurrent-matrix columns held per thread
+// recurrent-matrix columns held per thread: 64 (fewer partial sums) or 32 (twice the threads, half the
+// serial FMA chain per step); OU_GRU_KPT selects at run time, default chosen from measurements
 
 struct GruArgs {
   const float* gx;
@@ -28,12 +31,11 @@ struct GruArgs {
 };
 
 // __expf has ~2 ulp error: |error| of the gates ~1e-7, far below the bf16 output rounding
-__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + __expf(-x)); }
-__device__ __forceinline__ float tanh_f(float x) { return 2.f / (1.f + __expf(-2.f * x)) - 1.f; }
+__device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float tanh_f(float x) { return __fdividef(2.f, 1.f + __expf(-2.f * x)) - 1.f; }
 
-template <int H, int CS, int BG>
-__global__ void __launch_bounds__(3 * (H / CS) * (H / GRU_KPT)) gru_cluster_kernel(const GruArgs a) {
-  constexpr int KPT = GRU_KPT;
+template <int H, int CS, int BG, int KPT>
+__global__ void __launch_bounds__(3 * (H / CS) * (H / KPT)) gru_cluster_kernel(const GruArgs a) {
   constexpr int HS = H / CS;       // hidden units owned by this CTA
   constexpr int ROWS = 3 * HS;     // gate rows owned by this CTA
   constexpr int KS = H / KPT;      // split of the dot product across threads
@@ -150,10 +152,10 @@ __global__ void __launch_bounds__(3 * (H / CS) * (H / GRU_KPT)) gru_cluster_kern
   }
 }
 
-template <int H, int CS, int BG>
-static int launch_gru_bg(const GruArgs& a, cudaStream_t st) {
-  constexpr int NT = 3 * (H / CS) * (H / GRU_KPT);
-  auto kern = gru_cluster_kernel<H, CS, BG>;
+template <int H, int CS, int BG, int KPT>
+static int launch_gru_k(const GruArgs& a, cudaStream_t st) {
+  constexpr int NT = 3 * (H / CS) * (H / KPT);
+  auto kern = gru_cluster_kernel<H, CS, BG, KPT>;
   if (CS > 8) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     if (e != cudaSuccess) {
@@ -187,8 +189,8 @@ template <int H, int CS>
 static int max_clusters() {
   static int cached = 0;
   if (cached) return cached;
-  constexpr int NT = 3 * (H / CS) * (H / GRU_KPT);
-  auto kern = gru_cluster_kernel<H, CS, 4>;
+  constexpr int NT = 3 * (H / CS) * (H / 64);
+  auto kern = gru_cluster_kernel<H, CS, 4, 64>;
   if (CS > 8) cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(CS * 64);
@@ -209,13 +211,26 @@ static int max_clusters() {
   return cached;
 }
 
+template <int H, int CS, int BG>
+static int launch_gru_bg(const GruArgs& a, cudaStream_t st) {
+  static int kpt = 0;
+  if (kpt == 0) {
+    const char* e = getenv("OU_GRU_KPT");
+    kpt = e ? atoi(e) : 64;
+  }
+  if constexpr (H <= 256 && 3 * (H / CS) * (H / 32) <= 1024) {
+    if (kpt == 32) return launch_gru_k<H, CS, BG, 32>(a, st);
+  }
+  return launch_gru_k<H, CS, BG, 64>(a, st);
+}
+
 // Pick the clips-per-cluster so that all clusters run in ONE wave (the recurrence is latency
 // bound: a second wave doubles the time, a wider cluster only adds FMA work).
 template <int H, int CS>
 static int launch_gru(const GruArgs& a, cudaStream_t st) {
   const int groups_max = max_clusters<H, CS>() / 2;
   int bg = ceil_div(a.batch, groups_max > 0 ? groups_max : 1);
-  constexpr int NT = 3 * (H / CS) * (H / GRU_KPT);
+  constexpr int NT = 3 * (H / CS) * (H / 64);
   constexpr int BG_MAX = NT / (H / CS);   // the gate stage needs one thread per (unit, clip)
   if (bg <= 2) return launch_gru_bg<H, CS, 2>(a, st);
   if (bg == 3) return launch_gru_bg<H, CS, 3>(a, st);
