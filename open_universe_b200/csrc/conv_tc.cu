@@ -50,9 +50,12 @@ struct TcArgs {
   int n_kblocks;       // s * cin / cb  (K block kb <-> input phase r = kb / cin_blocks, channel block kb % cin_blocks)
   int cin_blocks;      // cin / cb
   int arows;           // rows per A stage: BM + taps - 1
+  int m_sub;           // 128-row sub-tiles per scheduling unit (2 for narrow layers: halves the
+                       // per-tile synchronisation cost that dominates when a tile is only a few MMAs)
+  uint32_t a_sub_bytes;  // 1024-aligned bytes of one sub-tile inside an A stage
   int bn;              // N per CTA tile
   int n_ntiles;        // npad / bn
-  int m_tiles;         // ceil(rows / BM) per clip
+  int m_tiles;         // scheduling units per clip: ceil(rows / (BM * m_sub))
   int total_m_tiles;   // m_tiles * batch
   int ctas_per_ntile;  // gridDim.x / n_ntiles
   int a_stages, b_stages;
@@ -237,16 +240,17 @@ __device__ __forceinline__ void producer_role(const TcArgs& a, const Ctx& c, con
   int ti = 0;
   for (int mt = c.mt0; mt < a.total_m_tiles; mt += c.mt_stride, ti++) {
     const int b = mt / a.m_tiles;
-    const int m0 = (mt - b * a.m_tiles) * BM;
+    const int m0 = (mt - b * a.m_tiles) * BM * a.m_sub;
     for (int kb = 0; kb < a.n_kblocks; kb++) {
       mbar_wait(c.empty_a + 8u * ra.stage, ra.phase ^ 1);
       if (kb == 0) trace_ev(a, 0, ti, 0);
-      mbar_arrive_expect_tx(c.full_a + 8u * ra.stage, a.a_tx_bytes);
+      mbar_arrive_expect_tx(c.full_a + 8u * ra.stage, a.a_tx_bytes * a.m_sub);
       // rows j in [m0 + tap_off, +arows) <-> time steps j*s + r of clip b, channel block kbi;
       // the TMA unit zero-fills rows outside [0, T/s)
       const int r = kb / a.cin_blocks, kbi = kb - r * a.cin_blocks;
-      tma_load_5d(c.smA + ra.stage * a.a_stage_bytes, tm_a, 0, r, m0 + p.tap_off, kbi, b,
-                  c.full_a + 8u * ra.stage);
+      for (int sub = 0; sub < a.m_sub; sub++)
+        tma_load_5d(c.smA + ra.stage * a.a_stage_bytes + sub * a.a_sub_bytes, tm_a, 0, r,
+                    m0 + sub * BM + p.tap_off, kbi, b, c.full_a + 8u * ra.stage);
       ra.advance(a.a_stages);
       if (!(a.resident && b_loaded)) {
         for (int q = 0; q < taps; q++) {
@@ -285,7 +289,9 @@ __device__ __forceinline__ void mma_role(const TcArgs& a, const Ctx& c, bool use
     mbar_wait(c.tmem_empty + 8u * acc, acc_phase ^ 1);
     tc_fence_after();
     if (issuer) trace_ev(a, 1, ti, 0);
-    const uint32_t d_tmem = c.tmem_base + (uint32_t)(acc * a.bn);
+    const uint32_t d_tmem = c.tmem_base + (uint32_t)(acc * a.bn * a.m_sub);
+    const int m_sub = a.m_sub;
+    const uint32_t sub_units = a.a_sub_bytes >> 4;
     for (int kb = 0; kb < n_kblocks; kb++) {
       mbar_wait(a_ready + 8u * ra.stage, ra.phase);
       tc_fence_after();
@@ -308,11 +314,13 @@ __device__ __forceinline__ void mma_role(const TcArgs& a, const Ctx& c, bool use
         const uint32_t b_lo = (((c.smB + bstage * b_stride) >> 4) & 0x3FFFu) | (1u << 16);
         const uint32_t a_lo = a_lo0 + q * row_units;
         if (elect_one()) {
+          for (int sub = 0; sub < m_sub; sub++) {
 #pragma unroll
-          for (int kk = 0; kk < K16; kk++) {
-            // k16 step inside the swizzled row: +32 bytes = +2 descriptor address units
-            umma_f16(d_tmem, hi64 | (a_lo + 2 * kk), hi64 | (b_lo + 2 * kk), idesc,
-                     (kb | q | kk) != 0 ? 1u : 0u);
+            for (int kk = 0; kk < K16; kk++) {
+              // k16 step inside the swizzled row: +32 bytes = +2 descriptor address units
+              umma_f16(d_tmem + (uint32_t)(sub * a.bn), hi64 | (a_lo + sub * sub_units + 2 * kk),
+                       hi64 | (b_lo + 2 * kk), idesc, (kb | q | kk) != 0 ? 1u : 0u);
+            }
           }
           if (!resident) umma_commit(c.empty_b + 8u * bstage);
           if (q == TAPS - 1) umma_commit(c.empty_a + 8u * ra.stage);
@@ -350,7 +358,8 @@ __device__ __forceinline__ void transform_role(const TcArgs& a, const Ctx& c, in
     for (int kb = 0; kb < a.n_kblocks; kb++) {
       mbar_wait(c.full_a + 8u * ra.stage, ra.phase);
       if (xt == 0 && kb == 0) trace_ev(a, 2, ti, 0);
-      const uint32_t base = c.smA + ra.stage * a.a_stage_bytes;
+      for (int sub = 0; sub < a.m_sub; sub++) {
+      const uint32_t base = c.smA + ra.stage * a.a_stage_bytes + sub * a.a_sub_bytes;
       int i = xt;
       for (; i + 3 * 128 < nvec; i += 4 * 128) {   // 4 independent vectors in flight
         uint4 v0 = lds_u4(base + (uint32_t)i * 16), v1 = lds_u4(base + (uint32_t)(i + 128) * 16);
@@ -361,6 +370,7 @@ __device__ __forceinline__ void transform_role(const TcArgs& a, const Ctx& c, in
         sts_u4(base + (uint32_t)(i + 384) * 16, prelu_vec(v3, slope));
       }
       for (; i < nvec; i += 128) sts_u4(base + (uint32_t)i * 16, prelu_vec(lds_u4(base + (uint32_t)i * 16), slope));
+      }
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(c.ready_a + 8u * ra.stage);
@@ -400,9 +410,7 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& a, const Ctx& c, int
   int ti = 0;
   for (int mt = c.mt0; mt < a.total_m_tiles; mt += c.mt_stride, ti++) {
     const int b = mt / a.m_tiles;
-    const int m0 = (mt - b * a.m_tiles) * BM;
-    const int j = m0 + row;
-    const bool row_ok = j < p.rows;
+    const int m0 = (mt - b * a.m_tiles) * BM * a.m_sub;
     // per-column coefficients: y = c0*(acc + add1) + c2*add2 + c1   (see header comment)
     const uint32_t coef = c.coef + (uint32_t)(acc * 3 * bn) * 4u;
     if (ti < 2 || has_film) {
@@ -427,7 +435,9 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& a, const Ctx& c, int
     if (row == 0 && half == 0) trace_ev(a, 3, ti, 0);
 
     const size_t clip_base = (size_t)b * cout * t_out;
-    const int t_row = j * up;
+    int j = m0 + row;
+    bool row_ok = j < p.rows;
+    int t_row = j * up;
     // element offset of the 8-channel output vector at tile column nl (multiple of 8), or -1
     auto out_offset = [&](int nl) -> long {
       int co = n0_co + nl, ph = n0_ph;
@@ -456,13 +466,22 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& a, const Ctx& c, int
     mbar_wait(c.tmem_full + 8u * acc, acc_phase);
     tc_fence_after();
     if (row == 0 && half == 0) trace_ev(a, 3, ti, 1);
-    const uint32_t taddr = c.tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * bn + half * 16);
+    for (int sub = 0; sub < a.m_sub; sub++) {
+    if (sub > 0) {
+      j = m0 + sub * BM + row;
+      row_ok = j < p.rows;
+      t_row = j * up;
+      prefetch(half * 16);
+    }
+    const uint32_t taddr = c.tmem_base + ((uint32_t)(quarter * 32) << 16) +
+                           (uint32_t)((acc * a.m_sub + sub) * bn + half * 16);
     for (int c0 = 0; c0 < bn; c0 += 32) {
       const int col = c0 + half * 16;
       uint32_t r[16];
       tmem_ld16(taddr + (uint32_t)c0, r);
       tmem_ld_wait();
-      const bool last = c0 + 32 >= bn;
+      const bool last_chunk = c0 + 32 >= bn;
+      const bool last = last_chunk && sub == a.m_sub - 1;
       if (last) {
         // accumulator fully read by this warp: hand the TMEM buffer back before the store phase
         tc_fence_before();
@@ -473,7 +492,7 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& a, const Ctx& c, int
       uint4 cur1[2], cur2[2];
 #pragma unroll
       for (int g = 0; g < 2; g++) cur1[g] = pre1[g], cur2[g] = pre2[g];
-      if (!last) prefetch(col + 32);
+      if (!last_chunk) prefetch(col + 32);
 #pragma unroll
       for (int g = 0; g < 2; g++) {
         const int nl = col + g * 8;
@@ -528,6 +547,7 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& a, const Ctx& c, int
                                    f2_to_bf2(v[6], v[7]));
         *reinterpret_cast<uint4*>(outp + off) = o;
       }
+    }
     }
     if (row == 0 && half == 0) trace_ev(a, 3, ti, 3);
     acc ^= 1;
@@ -681,12 +701,15 @@ int plan(const ou_conv_params* p, TcArgs* a) {
   a->n_kblocks = p->s * a->cin_blocks;
   a->bn = bn;
   a->n_ntiles = p->npad / bn;
-  a->m_tiles = ceil_div(p->rows, BM);
+  static const int pair_env = [] { const char* e = getenv("OU_TC_PAIR"); return e ? atoi(e) : 1; }();
+  a->m_sub = (bn <= 64 && pair_env && p->rows > 2 * BM) ? 2 : 1;
+  a->m_tiles = ceil_div(p->rows, BM * a->m_sub);
   a->total_m_tiles = a->m_tiles * p->batch;
   a->arows = BM + p->taps - 1;
   a->a_tx_bytes = (uint32_t)(a->arows * a->row_bytes);
   a->b_tx_bytes = (uint32_t)(bn * a->row_bytes);
-  a->a_stage_bytes = (a->a_tx_bytes + 1023u) & ~1023u;
+  a->a_sub_bytes = (a->a_tx_bytes + 1023u) & ~1023u;
+  a->a_stage_bytes = a->a_sub_bytes * a->m_sub;
   a->b_stage_bytes = (a->b_tx_bytes + 1023u) & ~1023u;
   const int budget = 232448 - 2048 - 6 * bn * 4;   // 227 KB minus alignment slack, barriers, coefficients
   const int nb_all = p->taps * a->n_kblocks;
@@ -705,7 +728,7 @@ int plan(const ou_conv_params* p, TcArgs* a) {
   // instruction descriptor: D=f32, A=B=bf16, K-major both, N = bn, M = 128
   a->idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
   uint32_t cols = 32;
-  while (cols < (uint32_t)(2 * bn)) cols <<= 1;
+  while (cols < (uint32_t)(2 * bn * a->m_sub)) cols <<= 1;
   a->tmem_cols = cols;
   const uint32_t sbo = 8u * a->row_bytes;                       // 8 rows
   const uint32_t layout = a->row_bytes == 128 ? 2u : (a->row_bytes == 64 ? 4u : 6u);
