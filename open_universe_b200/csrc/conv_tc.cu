@@ -435,25 +435,26 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& a, const Ctx& c, int
     if (row == 0 && half == 0) trace_ev(a, 3, ti, 0);
 
     const size_t clip_base = (size_t)b * cout * t_out;
-    int j = m0 + row;
-    bool row_ok = j < p.rows;
-    int t_row = j * up;
-    // element offset of the 8-channel output vector at tile column nl (multiple of 8), or -1
-    auto out_offset = [&](int nl) -> long {
+    const int m_sub = a.m_sub;
+    // element offset of the 8-channel output vector at (sub-tile, tile column nl), or -1
+    auto out_offset = [&](int sub, int nl) -> long {
+      const int jj = m0 + sub * BM + row;
       int co = n0_co + nl, ph = n0_ph;
       while (co >= cout) co -= cout, ph++;
-      const int t = t_row + ph;
-      if (!row_ok || n0 + nl >= n_total || t >= t_out) return -1;
+      const int t = jj * up + ph;
+      if (jj >= p.rows || n0 + nl >= n_total || t >= t_out) return -1;
       return (long)(clip_base + (size_t)(co >> cbo_shift) * blk_stride + (size_t)t * cbo + (co & (cbo - 1)));
     };
     uint4 pre1[2], pre2[2];
-    auto prefetch = [&](int col) {
+    // residual vectors of work item (sub, chunk) are fetched one item ahead of their use: the first
+    // item while the MMAs of this tile still run
+    auto prefetch = [&](int sub, int col) {
 #pragma unroll
       for (int g = 0; g < 2; g++) {
         pre1[g] = make_uint4(0u, 0u, 0u, 0u);
         pre2[g] = make_uint4(0u, 0u, 0u, 0u);
         if (NADD > 0) {
-          const long off = out_offset(col + g * 8);
+          const long off = out_offset(sub, col + g * 8);
           if (off >= 0) {
             pre1[g] = ldg_nc_v4(add1 + off);
             if (NADD > 1) pre2[g] = ldg_nc_v4(add2 + off);
@@ -461,93 +462,90 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& a, const Ctx& c, int
         }
       }
     };
-    prefetch(half * 16);   // residuals of the first chunk are fetched while the MMAs still run
+    prefetch(0, half * 16);
 
     mbar_wait(c.tmem_full + 8u * acc, acc_phase);
     tc_fence_after();
     if (row == 0 && half == 0) trace_ev(a, 3, ti, 1);
-    for (int sub = 0; sub < a.m_sub; sub++) {
-    if (sub > 0) {
-      j = m0 + sub * BM + row;
-      row_ok = j < p.rows;
-      t_row = j * up;
-      prefetch(half * 16);
-    }
-    const uint32_t taddr = c.tmem_base + ((uint32_t)(quarter * 32) << 16) +
-                           (uint32_t)((acc * a.m_sub + sub) * bn + half * 16);
-    for (int c0 = 0; c0 < bn; c0 += 32) {
-      const int col = c0 + half * 16;
-      uint32_t r[16];
-      tmem_ld16(taddr + (uint32_t)c0, r);
-      tmem_ld_wait();
-      const bool last_chunk = c0 + 32 >= bn;
-      const bool last = last_chunk && sub == a.m_sub - 1;
-      if (last) {
-        // accumulator fully read by this warp: hand the TMEM buffer back before the store phase
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(c.tmem_empty + 8u * acc);
-        if (row == 0 && half == 0) trace_ev(a, 3, ti, 2);
-      }
-      uint4 cur1[2], cur2[2];
-#pragma unroll
-      for (int g = 0; g < 2; g++) cur1[g] = pre1[g], cur2[g] = pre2[g];
-      if (!last_chunk) prefetch(col + 32);
-#pragma unroll
-      for (int g = 0; g < 2; g++) {
-        const int nl = col + g * 8;
-        if (!row_ok || n0 + nl >= n_total) continue;
-        const float4 k0a = lds_f4(coef + 4u * nl), k0b = lds_f4(coef + 4u * (nl + 4));
-        const float4 k1a = lds_f4(coef + 4u * (bn + nl)), k1b = lds_f4(coef + 4u * (bn + nl + 4));
-        const float k0[8] = {k0a.x, k0a.y, k0a.z, k0a.w, k0b.x, k0b.y, k0b.z, k0b.w};
-        const float k1[8] = {k1a.x, k1a.y, k1a.z, k1a.w, k1b.x, k1b.y, k1b.z, k1b.w};
-        float v[8];
-#pragma unroll
-        for (int i = 0; i < 8; i++) v[i] = __uint_as_float(r[g * 8 + i]);
-        if (F32TM) {
-#pragma unroll
-          for (int i = 0; i < 8; i++) v[i] += k1[i];
-          float4* dst = reinterpret_cast<float4*>(p.out_f32_tm + ((size_t)b * p.rows + j) * n_total + n0 + nl);
-          dst[0] = make_float4(v[0], v[1], v[2], v[3]);
-          dst[1] = make_float4(v[4], v[5], v[6], v[7]);
-          continue;
+    for (int sub = 0; sub < m_sub; sub++) {
+      const int j = m0 + sub * BM + row;
+      const bool row_ok = j < p.rows;
+      const uint32_t taddr = c.tmem_base + ((uint32_t)(quarter * 32) << 16) +
+                             (uint32_t)((acc * m_sub + sub) * bn + half * 16);
+      for (int c0 = 0; c0 < bn; c0 += 32) {
+        const int col = c0 + half * 16;
+        uint32_t r[16];
+        tmem_ld16(taddr + (uint32_t)c0, r);
+        tmem_ld_wait();
+        const bool last_chunk = c0 + 32 >= bn;
+        const bool last = last_chunk && sub == m_sub - 1;
+        if (last) {
+          // accumulators fully read by this warp: hand the TMEM buffer back before the store phase
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(c.tmem_empty + 8u * acc);
+          if (row == 0 && half == 0) trace_ev(a, 3, ti, 2);
         }
-        const long off = out_offset(nl);
-        if (off < 0) continue;
-        if (NADD > 0) {
-          const uint32_t* pa = reinterpret_cast<const uint32_t*>(&cur1[g]);
+        uint4 cur1[2], cur2[2];
 #pragma unroll
-          for (int i = 0; i < 4; i++) {
-            const float2 f = bf2_to_f2(pa[i]);
-            v[2 * i] += f.x, v[2 * i + 1] += f.y;
+        for (int g = 0; g < 2; g++) cur1[g] = pre1[g], cur2[g] = pre2[g];
+        if (!last_chunk) prefetch(sub, col + 32);
+        else if (!last) prefetch(sub + 1, half * 16);
+#pragma unroll
+        for (int g = 0; g < 2; g++) {
+          const int nl = col + g * 8;
+          if (!row_ok || n0 + nl >= n_total) continue;
+          const float4 k0a = lds_f4(coef + 4u * nl), k0b = lds_f4(coef + 4u * (nl + 4));
+          const float4 k1a = lds_f4(coef + 4u * (bn + nl)), k1b = lds_f4(coef + 4u * (bn + nl + 4));
+          const float k0[8] = {k0a.x, k0a.y, k0a.z, k0a.w, k0b.x, k0b.y, k0b.z, k0b.w};
+          const float k1[8] = {k1a.x, k1a.y, k1a.z, k1a.w, k1b.x, k1b.y, k1b.z, k1b.w};
+          float v[8];
+#pragma unroll
+          for (int i = 0; i < 8; i++) v[i] = __uint_as_float(r[g * 8 + i]);
+          if (F32TM) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) v[i] += k1[i];
+            float4* dst = reinterpret_cast<float4*>(p.out_f32_tm + ((size_t)b * p.rows + j) * n_total + n0 + nl);
+            dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+            dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+            continue;
           }
-        }
+          const long off = out_offset(sub, nl);
+          if (off < 0) continue;
+          if (NADD > 0) {
+            const uint32_t* pa = reinterpret_cast<const uint32_t*>(&cur1[g]);
 #pragma unroll
-        for (int i = 0; i < 8; i++) v[i] = fmaf(k0[i], v[i], k1[i]);
-        if (NADD > 1) {
-          const float4 k2a = lds_f4(coef + 4u * (2 * bn + nl)), k2b = lds_f4(coef + 4u * (2 * bn + nl + 4));
-          const float k2[8] = {k2a.x, k2a.y, k2a.z, k2a.w, k2b.x, k2b.y, k2b.z, k2b.w};
-          const uint32_t* pa = reinterpret_cast<const uint32_t*>(&cur2[g]);
-#pragma unroll
-          for (int i = 0; i < 4; i++) {
-            const float2 f = bf2_to_f2(pa[i]);
-            v[2 * i] = fmaf(k2[2 * i], f.x, v[2 * i]);
-            v[2 * i + 1] = fmaf(k2[2 * i + 1], f.y, v[2 * i + 1]);
+            for (int i = 0; i < 4; i++) {
+              const float2 f = bf2_to_f2(pa[i]);
+              v[2 * i] += f.x, v[2 * i + 1] += f.y;
+            }
           }
-        }
-        if (NPRELU > 0) {
 #pragma unroll
-          for (int i = 0; i < 8; i++) v[i] = prelu_f(v[i], slope1);
-        }
-        if (NPRELU > 1) {
+          for (int i = 0; i < 8; i++) v[i] = fmaf(k0[i], v[i], k1[i]);
+          if (NADD > 1) {
+            const float4 k2a = lds_f4(coef + 4u * (2 * bn + nl)), k2b = lds_f4(coef + 4u * (2 * bn + nl + 4));
+            const float k2[8] = {k2a.x, k2a.y, k2a.z, k2a.w, k2b.x, k2b.y, k2b.z, k2b.w};
+            const uint32_t* pa = reinterpret_cast<const uint32_t*>(&cur2[g]);
 #pragma unroll
-          for (int i = 0; i < 8; i++) v[i] = prelu_f(v[i], slope2);
+            for (int i = 0; i < 4; i++) {
+              const float2 f = bf2_to_f2(pa[i]);
+              v[2 * i] = fmaf(k2[2 * i], f.x, v[2 * i]);
+              v[2 * i + 1] = fmaf(k2[2 * i + 1], f.y, v[2 * i + 1]);
+            }
+          }
+          if (NPRELU > 0) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) v[i] = prelu_f(v[i], slope1);
+          }
+          if (NPRELU > 1) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) v[i] = prelu_f(v[i], slope2);
+          }
+          const uint4 o = make_uint4(f2_to_bf2(v[0], v[1]), f2_to_bf2(v[2], v[3]), f2_to_bf2(v[4], v[5]),
+                                     f2_to_bf2(v[6], v[7]));
+          *reinterpret_cast<uint4*>(outp + off) = o;
         }
-        const uint4 o = make_uint4(f2_to_bf2(v[0], v[1]), f2_to_bf2(v[2], v[3]), f2_to_bf2(v[4], v[5]),
-                                   f2_to_bf2(v[6], v[7]));
-        *reinterpret_cast<uint4*>(outp + off) = o;
       }
-    }
     }
     if (row == 0 && half == 0) trace_ev(a, 3, ti, 3);
     acc ^= 1;
