@@ -445,41 +445,52 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& a, const Ctx& c, int
       if (jj >= p.rows || n0 + nl >= n_total || t >= t_out) return -1;
       return (long)(clip_base + (size_t)(co >> cbo_shift) * blk_stride + (size_t)t * cbo + (co & (cbo - 1)));
     };
-    uint4 pre1[2], pre2[2];
-    // residual vectors of work item (sub, chunk) are fetched one item ahead of their use: the first
-    // item while the MMAs of this tile still run
-    auto prefetch = [&](int sub, int col) {
+    // Work items of this thread: (sub-tile, 32-column chunk) -> its 16-column half = 2 output vectors.
+    // Residual vectors are prefetched D items ahead (the first D while the MMAs of this tile still
+    // run) so that their HBM latency never sits on the epilogue's critical path.
+    constexpr int D = NADD == 1 ? 4 : (NADD == 2 ? 2 : 1);
+    const int chunk_shift = bn == 256 ? 3 : (bn == 128 ? 2 : (bn == 64 ? 1 : 0));
+    const int nitems = m_sub << chunk_shift;
+    uint4 pre1[D][2], pre2[D][2];
+    auto prefetch = [&](int d, int item) {
+      const int sub = item >> chunk_shift;
+      const int col = ((item - (sub << chunk_shift)) << 5) + half * 16;
 #pragma unroll
       for (int g = 0; g < 2; g++) {
-        pre1[g] = make_uint4(0u, 0u, 0u, 0u);
-        pre2[g] = make_uint4(0u, 0u, 0u, 0u);
-        if (NADD > 0) {
+        pre1[d][g] = make_uint4(0u, 0u, 0u, 0u);
+        pre2[d][g] = make_uint4(0u, 0u, 0u, 0u);
+        if (NADD > 0 && item < nitems) {
           const long off = out_offset(sub, col + g * 8);
           if (off >= 0) {
-            pre1[g] = ldg_nc_v4(add1 + off);
-            if (NADD > 1) pre2[g] = ldg_nc_v4(add2 + off);
+            pre1[d][g] = ldg_nc_v4(add1 + off);
+            if (NADD > 1) pre2[d][g] = ldg_nc_v4(add2 + off);
           }
         }
       }
     };
-    prefetch(0, half * 16);
+    if (NADD > 0) {
+#pragma unroll
+      for (int d = 0; d < D; d++) prefetch(d, d);
+    }
 
     mbar_wait(c.tmem_full + 8u * acc, acc_phase);
     tc_fence_after();
     if (row == 0 && half == 0) trace_ev(a, 3, ti, 1);
-    for (int sub = 0; sub < m_sub; sub++) {
-      const int j = m0 + sub * BM + row;
-      const bool row_ok = j < p.rows;
-      const uint32_t taddr = c.tmem_base + ((uint32_t)(quarter * 32) << 16) +
-                             (uint32_t)((acc * m_sub + sub) * bn + half * 16);
-      for (int c0 = 0; c0 < bn; c0 += 32) {
+    const uint32_t taddr0 = c.tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * m_sub * bn + half * 16);
+    for (int base = 0; base < nitems; base += D) {
+#pragma unroll
+      for (int d = 0; d < D; d++) {
+        const int item = base + d;
+        if (item >= nitems) break;
+        const int sub = item >> chunk_shift;
+        const int c0 = (item - (sub << chunk_shift)) << 5;
         const int col = c0 + half * 16;
+        const int j = m0 + sub * BM + row;
+        const bool row_ok = j < p.rows;
         uint32_t r[16];
-        tmem_ld16(taddr + (uint32_t)c0, r);
+        tmem_ld16(taddr0 + (uint32_t)(sub * bn + c0), r);
         tmem_ld_wait();
-        const bool last_chunk = c0 + 32 >= bn;
-        const bool last = last_chunk && sub == m_sub - 1;
-        if (last) {
+        if (item == nitems - 1) {
           // accumulators fully read by this warp: hand the TMEM buffer back before the store phase
           tc_fence_before();
           __syncwarp();
@@ -488,9 +499,8 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& a, const Ctx& c, int
         }
         uint4 cur1[2], cur2[2];
 #pragma unroll
-        for (int g = 0; g < 2; g++) cur1[g] = pre1[g], cur2[g] = pre2[g];
-        if (!last_chunk) prefetch(sub, col + 32);
-        else if (!last) prefetch(sub + 1, half * 16);
+        for (int g = 0; g < 2; g++) cur1[g] = pre1[d][g], cur2[g] = pre2[d][g];
+        if (NADD > 0) prefetch(d, item + D);
 #pragma unroll
         for (int g = 0; g < 2; g++) {
           const int nl = col + g * 8;
