@@ -710,7 +710,8 @@ int plan(const ou_conv_params* p, TcArgs* a) {
   a->bn = bn;
   a->n_ntiles = p->npad / bn;
   static const int pair_env = [] { const char* e = getenv("OU_TC_PAIR"); return e ? atoi(e) : 1; }();
-  a->m_sub = (bn <= 64 && pair_env && p->rows > 2 * BM) ? 2 : 1;
+  // measured on B200: pairing wins 30-50 % at N = 32 and is neutral-to-negative from N = 64 up
+  a->m_sub = (bn <= 32 && pair_env && p->rows > 2 * BM) ? 2 : 1;
   a->m_tiles = ceil_div(p->rows, BM * a->m_sub);
   a->total_m_tiles = a->m_tiles * p->batch;
   a->arows = BM + p->taps - 1;
