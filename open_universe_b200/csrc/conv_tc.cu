@@ -184,6 +184,23 @@ __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
                : "l"(p));
   return v;
 }
+struct U8 {
+  uint32_t w[8];
+};
+// 256-bit global accesses (sm_100: LDG.E.256 / STG.E.256): one full 32-byte sector per thread
+__device__ __forceinline__ U8 ldg_nc_v8(const void* p) {
+  U8 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v.w[0]), "=r"(v.w[1]), "=r"(v.w[2]), "=r"(v.w[3]), "=r"(v.w[4]), "=r"(v.w[5]),
+                 "=r"(v.w[6]), "=r"(v.w[7])
+               : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void stg_v8(void* p, const U8& v) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v.w[0]), "r"(v.w[1]),
+               "r"(v.w[2]), "r"(v.w[3]), "r"(v.w[4]), "r"(v.w[5]), "r"(v.w[6]), "r"(v.w[7])
+               : "memory");
+}
 __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
@@ -445,26 +462,24 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& a, const Ctx& c, int
       if (jj >= p.rows || n0 + nl >= n_total || t >= t_out) return -1;
       return (long)(clip_base + (size_t)(co >> cbo_shift) * blk_stride + (size_t)t * cbo + (co & (cbo - 1)));
     };
-    // Work items of this thread: (sub-tile, 32-column chunk) -> its 16-column half = 2 output vectors.
-    // Residual vectors are prefetched D items ahead (the first D while the MMAs of this tile still
-    // run) so that their HBM latency never sits on the epilogue's critical path.
+    // Work items of this thread: (sub-tile, 32-column chunk) -> its 16-column half = one 32-byte
+    // output vector (16 consecutive channels of one time step).  Residual vectors are prefetched D
+    // items ahead (the first D while the MMAs of this tile still run) so that their HBM latency
+    // never sits on the epilogue's critical path.
     constexpr int D = NADD == 1 ? 4 : (NADD == 2 ? 2 : 1);
     const int chunk_shift = bn == 256 ? 3 : (bn == 128 ? 2 : (bn == 64 ? 1 : 0));
     const int nitems = m_sub << chunk_shift;
-    uint4 pre1[D][2], pre2[D][2];
+    U8 pre1[D], pre2[D];
     auto prefetch = [&](int d, int item) {
       const int sub = item >> chunk_shift;
       const int col = ((item - (sub << chunk_shift)) << 5) + half * 16;
 #pragma unroll
-      for (int g = 0; g < 2; g++) {
-        pre1[d][g] = make_uint4(0u, 0u, 0u, 0u);
-        pre2[d][g] = make_uint4(0u, 0u, 0u, 0u);
-        if (NADD > 0 && item < nitems) {
-          const long off = out_offset(sub, col + g * 8);
-          if (off >= 0) {
-            pre1[d][g] = ldg_nc_v4(add1 + off);
-            if (NADD > 1) pre2[d][g] = ldg_nc_v4(add2 + off);
-          }
+      for (int i = 0; i < 8; i++) pre1[d].w[i] = 0u, pre2[d].w[i] = 0u;
+      if (NADD > 0 && item < nitems) {
+        const long off = out_offset(sub, col);
+        if (off >= 0) {
+          pre1[d] = ldg_nc_v8(add1 + off);
+          if (NADD > 1) pre2[d] = ldg_nc_v8(add2 + off);
         }
       }
     };
@@ -486,7 +501,6 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& a, const Ctx& c, int
         const int c0 = (item - (sub << chunk_shift)) << 5;
         const int col = c0 + half * 16;
         const int j = m0 + sub * BM + row;
-        const bool row_ok = j < p.rows;
         uint32_t r[16];
         tmem_ld16(taddr0 + (uint32_t)(sub * bn + c0), r);
         tmem_ld_wait();
@@ -497,64 +511,61 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& a, const Ctx& c, int
           if (lane == 0) mbar_arrive(c.tmem_empty + 8u * acc);
           if (row == 0 && half == 0) trace_ev(a, 3, ti, 2);
         }
-        uint4 cur1[2], cur2[2];
-#pragma unroll
-        for (int g = 0; g < 2; g++) cur1[g] = pre1[d][g], cur2[g] = pre2[d][g];
+        const U8 cur1 = pre1[d], cur2 = pre2[d];
         if (NADD > 0) prefetch(d, item + D);
+        if (j >= p.rows || n0 + col >= n_total) continue;
+        float v[16], k0[16], k1[16];
 #pragma unroll
-        for (int g = 0; g < 2; g++) {
-          const int nl = col + g * 8;
-          if (!row_ok || n0 + nl >= n_total) continue;
-          const float4 k0a = lds_f4(coef + 4u * nl), k0b = lds_f4(coef + 4u * (nl + 4));
-          const float4 k1a = lds_f4(coef + 4u * (bn + nl)), k1b = lds_f4(coef + 4u * (bn + nl + 4));
-          const float k0[8] = {k0a.x, k0a.y, k0a.z, k0a.w, k0b.x, k0b.y, k0b.z, k0b.w};
-          const float k1[8] = {k1a.x, k1a.y, k1a.z, k1a.w, k1b.x, k1b.y, k1b.z, k1b.w};
-          float v[8];
-#pragma unroll
-          for (int i = 0; i < 8; i++) v[i] = __uint_as_float(r[g * 8 + i]);
-          if (F32TM) {
-#pragma unroll
-            for (int i = 0; i < 8; i++) v[i] += k1[i];
-            float4* dst = reinterpret_cast<float4*>(p.out_f32_tm + ((size_t)b * p.rows + j) * n_total + n0 + nl);
-            dst[0] = make_float4(v[0], v[1], v[2], v[3]);
-            dst[1] = make_float4(v[4], v[5], v[6], v[7]);
-            continue;
-          }
-          const long off = out_offset(sub, nl);
-          if (off < 0) continue;
-          if (NADD > 0) {
-            const uint32_t* pa = reinterpret_cast<const uint32_t*>(&cur1[g]);
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-              const float2 f = bf2_to_f2(pa[i]);
-              v[2 * i] += f.x, v[2 * i + 1] += f.y;
-            }
-          }
-#pragma unroll
-          for (int i = 0; i < 8; i++) v[i] = fmaf(k0[i], v[i], k1[i]);
-          if (NADD > 1) {
-            const float4 k2a = lds_f4(coef + 4u * (2 * bn + nl)), k2b = lds_f4(coef + 4u * (2 * bn + nl + 4));
-            const float k2[8] = {k2a.x, k2a.y, k2a.z, k2a.w, k2b.x, k2b.y, k2b.z, k2b.w};
-            const uint32_t* pa = reinterpret_cast<const uint32_t*>(&cur2[g]);
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-              const float2 f = bf2_to_f2(pa[i]);
-              v[2 * i] = fmaf(k2[2 * i], f.x, v[2 * i]);
-              v[2 * i + 1] = fmaf(k2[2 * i + 1], f.y, v[2 * i + 1]);
-            }
-          }
-          if (NPRELU > 0) {
-#pragma unroll
-            for (int i = 0; i < 8; i++) v[i] = prelu_f(v[i], slope1);
-          }
-          if (NPRELU > 1) {
-#pragma unroll
-            for (int i = 0; i < 8; i++) v[i] = prelu_f(v[i], slope2);
-          }
-          const uint4 o = make_uint4(f2_to_bf2(v[0], v[1]), f2_to_bf2(v[2], v[3]), f2_to_bf2(v[4], v[5]),
-                                     f2_to_bf2(v[6], v[7]));
-          *reinterpret_cast<uint4*>(outp + off) = o;
+        for (int i = 0; i < 4; i++) {
+          const float4 x0 = lds_f4(coef + 4u * (col + 4 * i));
+          const float4 x1 = lds_f4(coef + 4u * (bn + col + 4 * i));
+          k0[4 * i] = x0.x, k0[4 * i + 1] = x0.y, k0[4 * i + 2] = x0.z, k0[4 * i + 3] = x0.w;
+          k1[4 * i] = x1.x, k1[4 * i + 1] = x1.y, k1[4 * i + 2] = x1.z, k1[4 * i + 3] = x1.w;
         }
+#pragma unroll
+        for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
+        if (F32TM) {
+          float4* dst = reinterpret_cast<float4*>(p.out_f32_tm + ((size_t)b * p.rows + j) * n_total + n0 + col);
+#pragma unroll
+          for (int i = 0; i < 4; i++)
+            dst[i] = make_float4(v[4 * i] + k1[4 * i], v[4 * i + 1] + k1[4 * i + 1], v[4 * i + 2] + k1[4 * i + 2],
+                                 v[4 * i + 3] + k1[4 * i + 3]);
+          continue;
+        }
+        const long off = out_offset(sub, col);
+        if (off < 0) continue;
+        if (NADD > 0) {
+#pragma unroll
+          for (int i = 0; i < 8; i++) {
+            const float2 f = bf2_to_f2(cur1.w[i]);
+            v[2 * i] += f.x, v[2 * i + 1] += f.y;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 16; i++) v[i] = fmaf(k0[i], v[i], k1[i]);
+        if (NADD > 1) {
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            const float4 x2 = lds_f4(coef + 4u * (2 * bn + col + 4 * i));
+            const float2 fa = bf2_to_f2(cur2.w[2 * i]), fb = bf2_to_f2(cur2.w[2 * i + 1]);
+            v[4 * i] = fmaf(x2.x, fa.x, v[4 * i]);
+            v[4 * i + 1] = fmaf(x2.y, fa.y, v[4 * i + 1]);
+            v[4 * i + 2] = fmaf(x2.z, fb.x, v[4 * i + 2]);
+            v[4 * i + 3] = fmaf(x2.w, fb.y, v[4 * i + 3]);
+          }
+        }
+        if (NPRELU > 0) {
+#pragma unroll
+          for (int i = 0; i < 16; i++) v[i] = prelu_f(v[i], slope1);
+        }
+        if (NPRELU > 1) {
+#pragma unroll
+          for (int i = 0; i < 16; i++) v[i] = prelu_f(v[i], slope2);
+        }
+        U8 o;
+#pragma unroll
+        for (int i = 0; i < 8; i++) o.w[i] = f2_to_bf2(v[2 * i], v[2 * i + 1]);
+        stg_v8(outp + off, o);
       }
     }
     if (row == 0 && half == 0) trace_ev(a, 3, ti, 3);
@@ -564,7 +575,7 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& a, const Ctx& c, int
 }
 
 // ================================================================================ kernel
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __maxnreg__(144)
 conv1d_tc_kernel(const TcArgs a, const __grid_constant__ CUtensorMap tm_a,
                  const __grid_constant__ CUtensorMap tm_w) {
   extern __shared__ uint8_t smem_raw[];
