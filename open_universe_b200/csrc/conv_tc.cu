@@ -466,7 +466,7 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& a, const Ctx& c, int
     // output vector (16 consecutive channels of one time step).  Residual vectors are prefetched D
     // items ahead (the first D while the MMAs of this tile still run) so that their HBM latency
     // never sits on the epilogue's critical path.
-    constexpr int D = NADD == 1 ? 4 : (NADD == 2 ? 2 : 1);
+    constexpr int D = NADD == 1 ? 3 : (NADD == 2 ? 2 : 1);
     const int chunk_shift = bn == 256 ? 3 : (bn == 128 ? 2 : (bn == 64 ? 1 : 0));
     const int nitems = m_sub << chunk_shift;
     U8 pre1[D], pre2[D];
@@ -514,53 +514,46 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& a, const Ctx& c, int
         const U8 cur1 = pre1[d], cur2 = pre2[d];
         if (NADD > 0) prefetch(d, item + D);
         if (j >= p.rows || n0 + col >= n_total) continue;
-        float v[16], k0[16], k1[16];
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-          const float4 x0 = lds_f4(coef + 4u * (col + 4 * i));
-          const float4 x1 = lds_f4(coef + 4u * (bn + col + 4 * i));
-          k0[4 * i] = x0.x, k0[4 * i + 1] = x0.y, k0[4 * i + 2] = x0.z, k0[4 * i + 3] = x0.w;
-          k1[4 * i] = x1.x, k1[4 * i + 1] = x1.y, k1[4 * i + 2] = x1.z, k1[4 * i + 3] = x1.w;
-        }
-#pragma unroll
-        for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
         if (F32TM) {
           float4* dst = reinterpret_cast<float4*>(p.out_f32_tm + ((size_t)b * p.rows + j) * n_total + n0 + col);
 #pragma unroll
-          for (int i = 0; i < 4; i++)
-            dst[i] = make_float4(v[4 * i] + k1[4 * i], v[4 * i + 1] + k1[4 * i + 1], v[4 * i + 2] + k1[4 * i + 2],
-                                 v[4 * i + 3] + k1[4 * i + 3]);
+          for (int i = 0; i < 4; i++) {
+            const float4 x1 = lds_f4(coef + 4u * (bn + col + 4 * i));
+            dst[i] = make_float4(__uint_as_float(r[4 * i]) + x1.x, __uint_as_float(r[4 * i + 1]) + x1.y,
+                                 __uint_as_float(r[4 * i + 2]) + x1.z, __uint_as_float(r[4 * i + 3]) + x1.w);
+          }
           continue;
         }
         const long off = out_offset(sub, col);
         if (off < 0) continue;
-        if (NADD > 0) {
+        float v[16];
 #pragma unroll
-          for (int i = 0; i < 8; i++) {
-            const float2 f = bf2_to_f2(cur1.w[i]);
-            v[2 * i] += f.x, v[2 * i + 1] += f.y;
+        for (int i = 0; i < 4; i++) {   // 4 columns at a time: coefficients live only briefly
+          const float4 x0 = lds_f4(coef + 4u * (col + 4 * i));
+          const float4 x1 = lds_f4(coef + 4u * (bn + col + 4 * i));
+          float a0 = __uint_as_float(r[4 * i]), a1 = __uint_as_float(r[4 * i + 1]);
+          float a2 = __uint_as_float(r[4 * i + 2]), a3 = __uint_as_float(r[4 * i + 3]);
+          if (NADD > 0) {
+            const float2 fa = bf2_to_f2(cur1.w[2 * i]), fb = bf2_to_f2(cur1.w[2 * i + 1]);
+            a0 += fa.x, a1 += fa.y, a2 += fb.x, a3 += fb.y;
           }
-        }
-#pragma unroll
-        for (int i = 0; i < 16; i++) v[i] = fmaf(k0[i], v[i], k1[i]);
-        if (NADD > 1) {
-#pragma unroll
-          for (int i = 0; i < 4; i++) {
+          a0 = fmaf(x0.x, a0, x1.x), a1 = fmaf(x0.y, a1, x1.y);
+          a2 = fmaf(x0.z, a2, x1.z), a3 = fmaf(x0.w, a3, x1.w);
+          if (NADD > 1) {
             const float4 x2 = lds_f4(coef + 4u * (2 * bn + col + 4 * i));
             const float2 fa = bf2_to_f2(cur2.w[2 * i]), fb = bf2_to_f2(cur2.w[2 * i + 1]);
-            v[4 * i] = fmaf(x2.x, fa.x, v[4 * i]);
-            v[4 * i + 1] = fmaf(x2.y, fa.y, v[4 * i + 1]);
-            v[4 * i + 2] = fmaf(x2.z, fb.x, v[4 * i + 2]);
-            v[4 * i + 3] = fmaf(x2.w, fb.y, v[4 * i + 3]);
+            a0 = fmaf(x2.x, fa.x, a0), a1 = fmaf(x2.y, fa.y, a1);
+            a2 = fmaf(x2.z, fb.x, a2), a3 = fmaf(x2.w, fb.y, a3);
           }
-        }
-        if (NPRELU > 0) {
-#pragma unroll
-          for (int i = 0; i < 16; i++) v[i] = prelu_f(v[i], slope1);
-        }
-        if (NPRELU > 1) {
-#pragma unroll
-          for (int i = 0; i < 16; i++) v[i] = prelu_f(v[i], slope2);
+          if (NPRELU > 0) {
+            a0 = prelu_f(a0, slope1), a1 = prelu_f(a1, slope1);
+            a2 = prelu_f(a2, slope1), a3 = prelu_f(a3, slope1);
+          }
+          if (NPRELU > 1) {
+            a0 = prelu_f(a0, slope2), a1 = prelu_f(a1, slope2);
+            a2 = prelu_f(a2, slope2), a3 = prelu_f(a3, slope2);
+          }
+          v[4 * i] = a0, v[4 * i + 1] = a1, v[4 * i + 2] = a2, v[4 * i + 3] = a3;
         }
         U8 o;
 #pragma unroll
@@ -575,7 +568,7 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& a, const Ctx& c, int
 }
 
 // ================================================================================ kernel
-__global__ void __maxnreg__(144)
+__global__ void __launch_bounds__(NTHREADS, 1)   // 14 warps: the register file gives 128 per thread
 conv1d_tc_kernel(const TcArgs a, const __grid_constant__ CUtensorMap tm_a,
                  const __grid_constant__ CUtensorMap tm_w) {
   extern __shared__ uint8_t smem_raw[];
