@@ -42,9 +42,12 @@ __global__ void __launch_bounds__(3 * (H / CS) * (H / KPT)) gru_cluster_kernel(c
   constexpr int NT = ROWS * KS;
   static_assert(H % CS == 0 && H % KPT == 0, "bad GRU shape");
   static_assert(HS * BG <= NT, "not enough threads for the gate stage");
+  constexpr int FIN_THREADS = ((HS * BG + 31) / 32) * 32;   // gate-stage warps (whole warps)
+  static_assert(FIN_THREADS <= NT, "gate-stage warps exceed the CTA");
 
   __shared__ __align__(16) float h_buf[2][BG][H];
   __shared__ float part[KS][ROWS][BG];
+  __shared__ __align__(16) float h_stage[BG][HS];   // this CTA's new h slice, pushed as float4 vectors
 
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
@@ -134,9 +137,20 @@ __global__ void __launch_bounds__(3 * (H / CS) * (H / KPT)) gru_cluster_kernel(c
       const float hprev = h_buf[cur][fb][hu];
       const float hnew = fvalid ? (1.f - z) * n + z * hprev : 0.f;
       h_buf_own_new = hnew;
-      float* slot = &h_buf[cur ^ 1][fb][hu];
-#pragma unroll
-      for (int c = 0; c < CS; c++) *cluster.map_shared_rank(slot, c) = hnew;
+      h_stage[fb][fu] = hnew;
+    }
+    // push the slice to every CTA of the cluster as 16-byte DSMEM stores (4x fewer SM-to-SM packets
+    // than per-float stores): BG * HS / 4 vectors per destination
+    if (tid < FIN_THREADS) {   // whole warps: named barrier among the gate-stage warps only
+      asm volatile("bar.sync 2, %0;" ::"n"(FIN_THREADS) : "memory");
+      constexpr int VEC = BG * HS / 4;
+      for (int i = tid; i < VEC * CS; i += FIN_THREADS) {
+        const int c = i / VEC, v = i - c * VEC;
+        const int bb = v / (HS / 4), u4 = v - bb * (HS / 4);
+        const float4 val = *reinterpret_cast<const float4*>(&h_stage[bb][u4 * 4]);
+        float4* dst = reinterpret_cast<float4*>(&h_buf[cur ^ 1][bb][rank * HS + u4 * 4]);
+        *cluster.map_shared_rank(dst, c) = val;
+      }
     }
     // split cluster barrier: release the DSMEM pushes, do the global store, then acquire
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");

@@ -24,22 +24,25 @@ __global__ void input_conv_kernel(const float* __restrict__ x, const float* __re
     xin[i] = (tt >= 0 && tt < t_len) ? x[(size_t)b * t_len + tt] * sc : 0.f;
   }
   const float* sb = sw + cout * k;
-  for (int c8 = 0; c8 < cout / 8; c8++) {
-    uint32_t v[4];
+  const int cb = cl_cb(cout);
+  for (int c16 = 0; c16 < cout / 16; c16++) {   // 16 channels = one 32-byte (256-bit) store
+    uint32_t v[8];
 #pragma unroll
-    for (int h = 0; h < 4; h++) {
+    for (int h = 0; h < 8; h++) {
       float o[2];
 #pragma unroll
       for (int e = 0; e < 2; e++) {
-        const int co = c8 * 8 + h * 2 + e;
+        const int co = c16 * 16 + h * 2 + e;
         float acc = sb[co];
         for (int i = 0; i < k; i++) acc = fmaf(sw[co * k + i], xin[i], acc);
         o[e] = acc;
       }
       v[h] = f2_to_bf2(o[0], o[1]);
     }
-    uint4* dst = reinterpret_cast<uint4*>(out + cl_off(b, c8 * 8, t, cout, t_len, cl_cb(cout)));
-    *dst = make_uint4(v[0], v[1], v[2], v[3]);
+    __nv_bfloat16* dst = out + cl_off(b, c16 * 16, t, cout, t_len, cb);
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "r"(v[0]), "r"(v[1]),
+                 "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
   }
 }
 
@@ -60,17 +63,20 @@ __global__ void output_sde_kernel(const __nv_bfloat16* __restrict__ src, const f
     net = bias;
     const int half = k / 2;
     const int cb = cl_cb(cin);
-    for (int c8 = 0; c8 < cin / 8; c8++) {
+    for (int c16 = 0; c16 < cin / 16; c16++) {
       for (int i = 0; i < k; i++) {
         const int tt = t + i - half;
         if (tt < 0 || tt >= t_src) continue;
-        const uint4 v = *reinterpret_cast<const uint4*>(src + cl_off(b, c8 * 8, tt, cin, t_src, cb));
-        const uint32_t* pv = reinterpret_cast<const uint32_t*>(&v);
+        uint32_t pv[8];   // 16 channels = one 32-byte (256-bit) load
+        asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(pv[0]), "=r"(pv[1]), "=r"(pv[2]), "=r"(pv[3]), "=r"(pv[4]), "=r"(pv[5]),
+                       "=r"(pv[6]), "=r"(pv[7])
+                     : "l"(src + cl_off(b, c16 * 16, tt, cin, t_src, cb)));
 #pragma unroll
-        for (int h = 0; h < 4; h++) {
+        for (int h = 0; h < 8; h++) {
           const float2 f = bf2_to_f2(pv[h]);
-          net = fmaf(sw[(c8 * 8 + h * 2) * k + i], f.x, net);
-          net = fmaf(sw[(c8 * 8 + h * 2 + 1) * k + i], f.y, net);
+          net = fmaf(sw[(c16 * 16 + h * 2) * k + i], f.x, net);
+          net = fmaf(sw[(c16 * 16 + h * 2 + 1) * k + i], f.y, net);
         }
       }
     }
