@@ -258,6 +258,180 @@ static int launch_gru(const GruArgs& a, cudaStream_t st) {
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Tensor-core variant for H = 256 (UNIVERSE / UNIVERSE++ 16 kHz): the per-step mat-vec
+// W_hh[96 x 256] . h[256 x clips] of each CTA runs on mma.sync m16n8k8 TF32 (fp32 accumulate) with
+// the weight fragments register-resident; up to 8 clips per cluster cost the same MMAs, so a batch
+// of 32 needs only 8 clusters.  TF32 is what the reference's own CUDA path (cuDNN, allow_tf32)
+// uses for the recurrent product; the hidden state itself, the gates and the z*h blend stay fp32
+// (each gate-stage thread keeps its h in a register).
+constexpr int GTC_H = 256, GTC_CS = 8, GTC_HS = 32, GTC_ROWS = 96, GTC_NT = 384, GTC_HP = GTC_H + 4;
+
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+      "{%0,%1,%2,%3};\n"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(GTC_NT) gru_cluster_tc_kernel(const GruArgs a, const int bg) {
+  constexpr int H = GTC_H, CS = GTC_CS, HS = GTC_HS, ROWS = GTC_ROWS, HP = GTC_HP;
+  // h (TF32-rounded) of 8 clip slots, row stride H+4 floats: the B-fragment loads (clip = lane/4,
+  // k = lane%4) then hit 32 distinct banks
+  __shared__ __align__(16) float h_buf[2][8][HP];
+  __shared__ float part[2][ROWS][8];
+  __shared__ __align__(16) float h_stage[8][HS];
+
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int cid = blockIdx.x / CS;
+  const int dir = cid & 1;
+  const int b0 = (cid >> 1) * bg;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int T = a.t;
+
+  // warp -> (16-row tile, K half); weight fragments for its 16 k8-steps stay in registers
+  const int mt = warp % 6, khalf = warp / 6;
+  const int gate = mt >> 1, u0 = (mt & 1) * 16;
+  uint32_t wfrag[16][4];
+  {
+    const float* wbase = a.w_hh + ((size_t)dir * 3 * H + (size_t)gate * H + rank * HS + u0) * H;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+      const int k = (khalf * 16 + i) * 8 + t4;
+      wfrag[i][0] = to_tf32(wbase[(size_t)g * H + k]);
+      wfrag[i][1] = to_tf32(wbase[(size_t)(g + 8) * H + k]);
+      wfrag[i][2] = to_tf32(wbase[(size_t)g * H + k + 4]);
+      wfrag[i][3] = to_tf32(wbase[(size_t)(g + 8) * H + k + 4]);
+    }
+  }
+  for (int i = tid; i < 2 * 8 * HP; i += GTC_NT) (&h_buf[0][0][0])[i] = 0.f;
+
+  // gate-stage role: thread <-> (owned unit fu, clip fb)
+  const int fin_threads = ((HS * bg + 31) / 32) * 32;
+  const bool fin = tid < HS * bg;
+  const int fb = tid % bg, fu = tid / bg;
+  const int hu = rank * HS + fu;
+  const bool fvalid = fin && (b0 + fb) < a.batch;
+  float bhr = 0.f, bhz = 0.f, bhn = 0.f, hprev = 0.f;
+  const float* gxp = nullptr;
+  size_t out_base = 0;
+  if (fvalid) {
+    const float* bh = a.b_hh + (size_t)dir * 3 * H;
+    bhr = bh[hu], bhz = bh[H + hu], bhn = bh[2 * H + hu];
+    gxp = a.gx + (size_t)(b0 + fb) * T * 6 * H + (size_t)dir * 3 * H + hu;
+    out_base = cl_off(b0 + fb, dir * H + hu, 0, 2 * H, T, cl_cb(2 * H));
+  }
+  cluster.sync();
+
+  float gxr = 0.f, gxz = 0.f, gxn = 0.f;
+  if (fvalid) {
+    const float* gp = gxp + (size_t)(dir ? T - 1 : 0) * 6 * H;
+    gxr = __ldg(gp), gxz = __ldg(gp + H), gxn = __ldg(gp + 2 * H);
+  }
+  for (int step = 0; step < T; step++) {
+    const int t = dir ? (T - 1 - step) : step;
+    const int cur = step & 1;
+    float nxr = 0.f, nxz = 0.f, nxn = 0.f;
+    if (fvalid && step + 1 < T) {
+      const float* gp = gxp + (size_t)(dir ? t - 1 : t + 1) * 6 * H;
+      nxr = __ldg(gp), nxz = __ldg(gp + H), nxn = __ldg(gp + 2 * H);
+    }
+    // partial products of this warp: 16 rows x 8 clips over its 128 columns, two accumulators to
+    // halve the dependent MMA chain
+    float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
+    const float* hb = &h_buf[cur][g][khalf * 128 + t4];
+#pragma unroll
+    for (int i = 0; i < 16; i += 2) {
+      mma_tf32(acc0, wfrag[i], __float_as_uint(hb[i * 8]), __float_as_uint(hb[i * 8 + 4]));
+      mma_tf32(acc1, wfrag[i + 1], __float_as_uint(hb[(i + 1) * 8]), __float_as_uint(hb[(i + 1) * 8 + 4]));
+    }
+    {
+      const int r0 = mt * 16 + g;
+      part[khalf][r0][2 * t4] = acc0[0] + acc1[0];
+      part[khalf][r0][2 * t4 + 1] = acc0[1] + acc1[1];
+      part[khalf][r0 + 8][2 * t4] = acc0[2] + acc1[2];
+      part[khalf][r0 + 8][2 * t4 + 1] = acc0[3] + acc1[3];
+    }
+    __syncthreads();
+    float hnew_keep = 0.f;
+    if (fin) {
+      const float hr = bhr + part[0][fu][fb] + part[1][fu][fb];
+      const float hz = bhz + part[0][HS + fu][fb] + part[1][HS + fu][fb];
+      const float hn = bhn + part[0][2 * HS + fu][fb] + part[1][2 * HS + fu][fb];
+      const float r = sigmoid_f(gxr + hr);
+      const float z = sigmoid_f(gxz + hz);
+      const float n = tanh_f(gxn + r * hn);
+      const float hnew = fvalid ? (1.f - z) * n + z * hprev : 0.f;
+      hprev = hnew;
+      hnew_keep = hnew;
+      h_stage[fb][fu] = __uint_as_float(to_tf32(hnew));
+    }
+    if (tid < fin_threads) {   // whole warps: named barrier among the gate-stage warps only
+      asm volatile("bar.sync 2, %0;" ::"r"(fin_threads) : "memory");
+      const int vec = bg * HS / 4;
+      for (int i = tid; i < vec * CS; i += fin_threads) {
+        const int c = i / vec, v = i - c * vec;
+        const int bb = v / (HS / 4), u4 = v - bb * (HS / 4);
+        const float4 val = *reinterpret_cast<const float4*>(&h_stage[bb][u4 * 4]);
+        float4* dst = reinterpret_cast<float4*>(&h_buf[cur ^ 1][bb][rank * HS + u4 * 4]);
+        *cluster.map_shared_rank(dst, c) = val;
+      }
+    }
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    if (fvalid) {
+      const size_t off = out_base + (size_t)t * cl_cb(2 * H);
+      float v = hnew_keep;
+      if (a.add) v += __bfloat162float(a.add[off]);
+      a.out[off] = __float2bfloat16(v * a.scale);
+    }
+    gxr = nxr, gxz = nxz, gxn = nxn;
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  }
+}
+
+static int launch_gru_tc(const GruArgs& a, cudaStream_t st) {
+  // clips per cluster: up to 8 cost the same MMAs; use as few clusters as the batch allows
+  int bg = a.batch < 8 ? a.batch : 8;
+  const int clusters = 2 * ceil_div(a.batch, bg);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(clusters * GTC_CS);
+  cfg.blockDim = dim3(GTC_NT);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = GTC_CS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gru_cluster_tc_kernel, a, bg);
+  if (e != cudaSuccess) {
+    set_error("ou_gru_bidir(tc): launch: %s", cudaGetErrorString(e));
+    return OU_ERR_CUDA;
+  }
+  return check_launch("ou_gru_bidir(tc)");
+}
+
+// OU_GRU_IMPL=fma forces the CUDA-core kernel for H = 256 (A/B timing, fp32-exact recurrence)
+static bool gru_use_tc() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = getenv("OU_GRU_IMPL");
+    cached = (e && e[0] == 'f') ? 0 : 1;
+  }
+  return cached == 1;
+}
+
 }  // namespace ou
 
 extern "C" int ou_gru_bidir(const float* gx, const float* w_hh, const float* b_hh, const void* add,
@@ -268,7 +442,7 @@ extern "C" int ou_gru_bidir(const float* gx, const float* w_hh, const float* b_h
   cudaStream_t st = (cudaStream_t)stream;
   switch (hidden) {
     case 128: return ou::launch_gru<128, 4>(a, st);
-    case 256: return ou::launch_gru<256, 8>(a, st);
+    case 256: return ou::gru_use_tc() ? ou::launch_gru_tc(a, st) : ou::launch_gru<256, 8>(a, st);
     case 384: return ou::launch_gru<384, 16>(a, st);
     default:
       ou::set_error("ou_gru_bidir: hidden size %d has no kernel (128, 256, 384)", hidden);
