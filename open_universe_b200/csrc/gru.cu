@@ -16,11 +16,15 @@
 namespace cg = cooperative_groups;
 
 namespace ou {
+namespace tc {
+extern long long* g_trace;
+}
 
 // recurrent-matrix columns held per thread: 64 (fewer partial sums) or 32 (twice the threads, half the
 // serial FMA chain per step); OU_GRU_KPT selects at run time, default chosen from measurements
 
 struct GruArgs {
+  long long* trace;   // debug (ou_debug_set_trace): clock64 stamps of CTA 0 / thread 0, [64 steps][8 events]
   const float* gx;
   const float* w_hh;
   const float* b_hh;
@@ -345,6 +349,9 @@ __global__ void __launch_bounds__(GTC_NT) gru_cluster_tc_kernel(const GruArgs a,
       const float* gp = gxp + (size_t)(dir ? t - 1 : t + 1) * 6 * H;
       nxr = __ldg(gp), nxz = __ldg(gp + H), nxn = __ldg(gp + 2 * H);
     }
+#define GRU_STAMP(ev) \
+  if (a.trace != nullptr && blockIdx.x == 0 && tid == 0 && step >= 100 && step < 164) a.trace[(step - 100) * 8 + (ev)] = clock64();
+    GRU_STAMP(0)
     // partial products of this warp: 16 rows x 8 clips over its 128 columns, two accumulators to
     // halve the dependent MMA chain
     float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
@@ -361,7 +368,9 @@ __global__ void __launch_bounds__(GTC_NT) gru_cluster_tc_kernel(const GruArgs a,
       part[khalf][r0 + 8][2 * t4] = acc0[2] + acc1[2];
       part[khalf][r0 + 8][2 * t4 + 1] = acc0[3] + acc1[3];
     }
+    GRU_STAMP(1)
     __syncthreads();
+    GRU_STAMP(2)
     float hnew_keep = 0.f;
     if (fin) {
       const float hr = bhr + part[0][fu][fb] + part[1][fu][fb];
@@ -375,6 +384,7 @@ __global__ void __launch_bounds__(GTC_NT) gru_cluster_tc_kernel(const GruArgs a,
       hnew_keep = hnew;
       h_stage[fb][fu] = __uint_as_float(to_tf32(hnew));
     }
+    GRU_STAMP(3)
     if (tid < fin_threads) {   // whole warps: named barrier among the gate-stage warps only
       asm volatile("bar.sync 2, %0;" ::"r"(fin_threads) : "memory");
       const int vec = bg * HS / 4;
@@ -386,7 +396,9 @@ __global__ void __launch_bounds__(GTC_NT) gru_cluster_tc_kernel(const GruArgs a,
         *cluster.map_shared_rank(dst, c) = val;
       }
     }
+    GRU_STAMP(4)
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    GRU_STAMP(5)
     if (fvalid) {
       const size_t off = out_base + (size_t)t * cl_cb(2 * H);
       float v = hnew_keep;
@@ -394,7 +406,9 @@ __global__ void __launch_bounds__(GTC_NT) gru_cluster_tc_kernel(const GruArgs a,
       a.out[off] = __float2bfloat16(v * a.scale);
     }
     gxr = nxr, gxz = nxz, gxn = nxn;
+    GRU_STAMP(6)
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    GRU_STAMP(7)
   }
 }
 
@@ -438,7 +452,7 @@ extern "C" int ou_gru_bidir(const float* gx, const float* w_hh, const float* b_h
                             float scale, void* out, int batch, int t, int hidden, void* stream) {
   OU_REQUIRE(gx && w_hh && b_hh && out, "ou_gru_bidir: null pointer");
   OU_REQUIRE(batch > 0 && t > 0, "ou_gru_bidir: empty problem");
-  ou::GruArgs a{gx, w_hh, b_hh, (const __nv_bfloat16*)add, (__nv_bfloat16*)out, scale, batch, t};
+  ou::GruArgs a{ou::tc::g_trace, gx, w_hh, b_hh, (const __nv_bfloat16*)add, (__nv_bfloat16*)out, scale, batch, t};
   cudaStream_t st = (cudaStream_t)stream;
   switch (hidden) {
     case 128: return ou::launch_gru<128, 4>(a, st);

@@ -22,3 +22,19 @@ for B in (4, 8, 16, 24, 28, 32, 48, 64):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 3
     print(f"B={B:3d} clusters={2 * ((B + 3) // 4):3d}  {ms:8.3f} ms  {ms * 1e3 / T:6.2f} us/step")
+
+# per-phase clock64 stamps of the tensor-core kernel (CTA 0, thread 0, steps 100..163)
+B = 32
+gx = torch.randn(B, T, 6 * H, device="cuda")
+out = R.alloc_blocked(B, 2 * H, T, "cuda")
+tr = torch.zeros(64, 8, dtype=torch.int64, device="cuda")
+L.ou_debug_set_trace(R._ptr(tr))
+lib.check(L.ou_gru_bidir(R._ptr(gx), R._ptr(w), R._ptr(b), None, 1.0, R._ptr(out), B, T, H, R._stream()))
+torch.cuda.synchronize()
+L.ou_debug_set_trace(None)
+tr = tr.cpu()
+if int(tr.max()) > 0:
+    d = (tr[:, 1:] - tr[:, :-1]).float().mean(0)
+    step = (tr[1:, 0] - tr[:-1, 0]).float().mean()
+    names = ["mma phase", "syncthreads", "gate math", "bar+push", "cluster arrive", "store+mov", "cluster wait"]
+    print("GRU tc per-step cycles (B=32):", {n: round(float(x)) for n, x in zip(names, d)}, "step", round(float(step)))
