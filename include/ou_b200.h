@@ -91,6 +91,41 @@ typedef struct ou_conv_params {
 
 int ou_conv1d(const ou_conv_params* p, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Fused ConvBlock trunk (conv1 -> FiLM -> conv2 -> conv3 -> residual) for narrow levels: ONE launch
+ * that reads the block input (and the conditioning tensor) once and writes the block output once;
+ * the two intermediate activations stay in shared memory.  Replaces the middle of
+ * ConvBlock.forward, networks/universe/blocks.py:385-399:
+ *   c1 = PReLU(FiLM((conv1_k5(PReLU(x, prelu_in)) + b1 [+ sc]) * scale1), prelu_mid1)   (bf16)
+ *   c2 = PReLU(conv2_k3(c1) + b2, prelu_mid2)                                            (bf16)
+ *   v  = (conv3_k3(c2) + b3 + x) * scale3  -> PReLU(prelu_out) -> PReLU(prelu_out2)  (each if enabled)
+ * All convs are 'same' (zero padded) C -> C channels; FiLM = gamma[b][c] * y + beta[b][c] when gamma
+ * is not NULL.  Rounding points are those of three consecutive ou_conv1d calls.
+ * Supported: channels in {32, 64}, taps (5, 3, 3); anything else returns OU_ERR_UNSUPPORTED (the
+ * caller runs the three ou_conv1d launches instead).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct ou_trunk_params {
+  const void* x;            /* blocked bf16 (B, C, t): raw block input                          */
+  const void* w1;           /* ou_conv_params.w_tc packing of conv1 / conv2 / conv3:            */
+  const void* w2;           /*   bf16 [taps][1][C][C]  (tap, out channel, in channel)            */
+  const void* w3;
+  const float* b1;          /* fp32 [C] each                                                     */
+  const float* b2;
+  const float* b3;
+  const void* sc;           /* blocked bf16 (B, C, t) or NULL                                    */
+  const float* gamma;       /* fp32, element (b, c) at gamma[b*film_bstride + c], or NULL        */
+  const float* beta;
+  void* out;                /* blocked bf16 (B, C, t)                                            */
+  int32_t batch, channels, t;
+  int32_t taps1, taps2, taps3;
+  int32_t film_bstride;
+  int32_t has_prelu_out, has_prelu_out2;
+  float prelu_in, prelu_mid1, prelu_mid2, prelu_out, prelu_out2;
+  float scale1, scale3;
+} ou_trunk_params;
+
+int ou_conv_trunk(const ou_trunk_params* p, void* stream);
+
 /* Reference-quality fp32 CUDA-core version of the same contract (one thread per output): used by
  * the GPU tests to cross-check the tensor-core kernel on device.  Same arguments. */
 int ou_conv1d_naive(const ou_conv_params* p, void* stream);

@@ -31,6 +31,21 @@ class ConvParams(Structure):
     ]
 
 
+class TrunkParams(Structure):
+    _fields_ = [
+        ("x", c_void_p), ("w1", c_void_p), ("w2", c_void_p), ("w3", c_void_p),
+        ("b1", c_void_p), ("b2", c_void_p), ("b3", c_void_p), ("sc", c_void_p),
+        ("gamma", c_void_p), ("beta", c_void_p), ("out", c_void_p),
+        ("batch", c_int32), ("channels", c_int32), ("t", c_int32),
+        ("taps1", c_int32), ("taps2", c_int32), ("taps3", c_int32),
+        ("film_bstride", c_int32),
+        ("has_prelu_out", c_int32), ("has_prelu_out2", c_int32),
+        ("prelu_in", c_float), ("prelu_mid1", c_float), ("prelu_mid2", c_float),
+        ("prelu_out", c_float), ("prelu_out2", c_float),
+        ("scale1", c_float), ("scale3", c_float),
+    ]
+
+
 # name -> (restype, argtypes); every symbol of include/ou_b200.h
 SIGNATURES = {
     "ou_abi_version": (c_int, []),
@@ -38,6 +53,7 @@ SIGNATURES = {
     "ou_launch_count": (c_int64, []),
     "ou_conv1d": (c_int, [POINTER(ConvParams), c_void_p]),
     "ou_conv1d_naive": (c_int, [POINTER(ConvParams), c_void_p]),
+    "ou_conv_trunk": (c_int, [POINTER(TrunkParams), c_void_p]),
     "ou_input_conv": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                               c_int, c_int, c_void_p]),
     "ou_output_sde": (c_int, [c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p,

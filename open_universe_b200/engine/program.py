@@ -65,6 +65,51 @@ class ConvOp:
 
 
 @dataclass
+class TrunkOp:
+    """conv1 -> FiLM -> conv2 -> conv3 -> residual of one narrow ConvBlock in ONE launch
+    (``ou_conv_trunk``, blocks.py:385-399).  ``parts`` are the three ConvOps it stands for: the
+    fused kernel rounds to bf16 at exactly their boundaries, so the emulator (and the runtime,
+    when the fused kernel is switched off or rejects the shape) simply runs the parts."""
+    name: str
+    parts: List[ConvOp]
+    packed: Optional[dict] = None
+
+    @property
+    def flops_exec(self):
+        return sum(p.flops_exec for p in self.parts)
+
+    @property
+    def flops_algo(self):
+        return sum(p.flops_algo for p in self.parts)
+
+
+TRUNK_CHANNELS = (32, 64)
+
+
+def fuse_trunk(prog, name, n_parts=3):
+    """Replace the last three ConvOps of ``prog`` (conv1, conv2, conv3 of one block) by a TrunkOp
+    when the fused kernel covers them (C in {32, 64}, k5-k3-k3, plain blocked outputs)."""
+    c1, c2, c3 = prog.ops[-n_parts:]
+    ok = (all(isinstance(o, ConvOp) for o in (c1, c2, c3))
+          and c1.fc.cin in TRUNK_CHANNELS
+          and all(o.fc.cin == c1.fc.cin and o.fc.cout == c1.fc.cin and o.fc.s == 1 and o.fc.up == 1
+                  and o.dst_kind == "blocked" and o.add2 is None and o.t_in == c1.t_in
+                  and o.t_out == c1.t_in for o in (c1, c2, c3))
+          and (c1.fc.taps, c2.fc.taps, c3.fc.taps) == (5, 3, 3)
+          and (c1.fc.tap_off, c2.fc.tap_off, c3.fc.tap_off) == (-2, -1, -1)
+          and c1.fc.prelu_in is not None and c1.prelu_out is not None and c1.prelu_out2 is None
+          and c2.fc.prelu_in is None and c2.src == c1.dst and c2.add1 is None
+          and c2.film_off is None and c2.prelu_out is not None and c2.prelu_out2 is None
+          and c3.fc.prelu_in is None and c3.src == c2.dst and c3.add1 == c1.src
+          and c3.film_off is None)
+    if not ok:
+        return False
+    del prog.ops[-n_parts:]
+    prog.ops.append(TrunkOp(name, [c1, c2, c3]))
+    return True
+
+
+@dataclass
 class InputConvOp:
     """(B,1,T) fp32 signal -> blocked bf16 (B,C,T): k-tap 'same' conv of a 1-channel input with an
     optional per-clip input scale (EDM c_in, universe.py:197-203).  ``ou_input_conv``."""
@@ -155,6 +200,14 @@ def ceil_div(a, b):
     return -(-a // b)
 
 
+def flat_ops(ops):
+    """Op list with every TrunkOp expanded into its three ConvOps."""
+    out = []
+    for op in ops:
+        out.extend(op.parts if isinstance(op, TrunkOp) else [op])
+    return out
+
+
 def add_conv(prog, name, src, dst, fc, t_in, t_out=None, **kw):
     """Append a ConvOp; derives the output length / GEMM row count from the folded geometry."""
     if t_out is None:
@@ -220,6 +273,8 @@ def lower_conv_block(prog, blk, pfx, src, t_in, *, film_linear=None, input_cond=
     is_down = blk.rate_change_dir == "down"
     v, _ = add_conv(prog, pfx + ".conv3", c2, pfx + ".v", fc3, t, add1=h, scale1=SQRT_HALF,
                     prelu_out=None if is_down else po[0], prelu_out2=None if is_down else po[1])
+    if not raw_cond_out:
+        fuse_trunk(prog, pfx + ".trunk")
     if is_down:
         fcr = fold.fold_prelu_conv(blk.rate_change_conv)
         out, t_out = add_conv(prog, pfx + ".down", v, pfx + ".out", fcr, t)
@@ -375,7 +430,8 @@ def lower_conditioner(net, batch, t, need_signal_tail=True):
     # out = (x_mel + sum(st_convs) + x) / sqrt(n+1)   (condition.py:202-206): the running sum is
     # carried through the st_conv epilogues; the last op producing ``h`` adds it and scales.
     n_sum += 1
-    last = next((op for op in reversed(prog.ops) if isinstance(op, ConvOp) and op.dst == h), None)
+    last = next((op for op in reversed(flat_ops(prog.ops)) if isinstance(op, ConvOp) and op.dst == h),
+                None)
     if last is None or last.add2 is not None:
         raise RuntimeError("unexpected producer of the encoder output")
     if tl != frames:

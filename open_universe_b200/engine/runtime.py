@@ -5,6 +5,7 @@ stream and tiny host-side scalar math only; every FLOP of the networks is issued
 ``csrc/``.  There is NO CPU path: any entry point called with non-CUDA tensors raises.
 """
 import math
+import os
 from ctypes import byref, c_void_p
 
 import torch
@@ -98,7 +99,7 @@ def alloc_buffers(prog, device, skip=()):
 
 def prepare_ops(prog, device):
     """Upload packed weights / small tables for every op of a program."""
-    for op in prog.ops:
+    for op in P.flat_ops(prog.ops):
         if isinstance(op, P.ConvOp):
             op.packed = pack_conv_weights(op.fc, device)
         elif isinstance(op, P.InputConvOp):
@@ -164,6 +165,42 @@ def launch_conv(op, bufs, batch, gamma=None, beta=None, film_bstride=0, naive=Fa
     lib.check(fn(byref(prm), _stream()))
 
 
+# OU_TRUNK=0 runs every fused ConvBlock trunk as its three ou_conv1d launches (A/B measurements)
+USE_TRUNK = os.environ.get("OU_TRUNK", "1") != "0"
+
+
+def launch_trunk(op, bufs, batch, film=None, film_bstride=0):
+    """One ``ou_conv_trunk`` launch for the three ConvOps of a TrunkOp."""
+    c1, c2, c3 = op.parts
+    prm = lib.TrunkParams()
+    prm.x = bufs[c1.src].data_ptr()
+    prm.w1, prm.w2, prm.w3 = (c.packed["w_tc"].data_ptr() for c in op.parts)
+    prm.b1, prm.b2, prm.b3 = (c.packed["bias"].data_ptr() for c in op.parts)
+    prm.sc = bufs[c1.add1].data_ptr() if c1.add1 else None
+    prm.gamma = prm.beta = None
+    if c1.film_off is not None:
+        base = film.data_ptr() + 4 * c1.film_off
+        prm.gamma, prm.beta = base, base + 4 * c1.fc.cout
+    prm.film_bstride = film_bstride
+    prm.out = bufs[c3.dst].data_ptr()
+    prm.batch, prm.channels, prm.t = batch, c1.fc.cin, c1.t_in
+    prm.taps1, prm.taps2, prm.taps3 = c1.fc.taps, c2.fc.taps, c3.fc.taps
+    prm.prelu_in, prm.prelu_mid1, prm.prelu_mid2 = c1.fc.prelu_in, c1.prelu_out, c2.prelu_out
+    prm.has_prelu_out = c3.prelu_out is not None
+    prm.prelu_out = c3.prelu_out or 0.0
+    prm.has_prelu_out2 = c3.prelu_out2 is not None
+    prm.prelu_out2 = c3.prelu_out2 or 0.0
+    prm.scale1, prm.scale3 = c1.scale1, c3.scale1
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        lib.check(lib.load().ou_conv_trunk(byref(prm), _stream()))
+        e1.record()
+        PROFILE.append((op, e0, e1))
+        return
+    lib.check(lib.load().ou_conv_trunk(byref(prm), _stream()))
+
+
 class Executor:
     """A lowered program bound to device buffers."""
 
@@ -179,8 +216,13 @@ class Executor:
             net_out=None):
         L = lib.load()
         bufs, B = self.bufs, self.batch
-        for op in self.prog.ops:
-            if isinstance(op, P.ConvOp):
+        ops = self.prog.ops
+        if self.naive or not USE_TRUNK:
+            ops = P.flat_ops(ops)
+        for op in ops:
+            if isinstance(op, P.TrunkOp):
+                launch_trunk(op, bufs, B, film, film_bstride)
+            elif isinstance(op, P.ConvOp):
                 gamma = beta = None
                 if op.film_off is not None:
                     base = film.data_ptr() + 4 * op.film_off

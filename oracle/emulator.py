@@ -150,7 +150,7 @@ def run_program(prog, inputs, film=None, in_scale=None, coef=None, noise=None, q
     """inputs: {buffer name: (B, C, T) float tensor}.  Returns (bufs, net, x_new)."""
     bufs = dict(inputs)
     net = x_new = None
-    for op in prog.ops:
+    for op in P.flat_ops(prog.ops):      # a TrunkOp rounds exactly where its three ConvOps do
         if isinstance(op, P.ConvOp):
             run_conv(op, bufs, film, quant)
         elif isinstance(op, P.InputConvOp):

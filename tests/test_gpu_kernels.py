@@ -107,6 +107,70 @@ def test_conv1d_vs_emulator(c):
                                  f"bad_per_batch={bad.flatten(1).mean(1).tolist()}")
 
 
+TRUNK_CASES = [
+    dict(C=64, t=1000, B=2, sc=True, film=True, po=(0.3, None)),
+    dict(C=32, t=1000, B=2, sc=True, film=True, po=(0.3, -0.2)),
+    dict(C=64, t=123, B=1, sc=False, film=False, po=(None, None)),      # single partial item
+    dict(C=32, t=251, B=3, sc=False, film=True, po=(None, None)),       # one short of an item
+    dict(C=64, t=124 * 7, B=1, sc=True, film=False, po=(None, None)),   # exact multiple of the item
+    dict(C=32, t=252 * 3 + 1, B=2, sc=True, film=False, po=(0.1, None)),
+    dict(C=64, t=64080, B=3, sc=True, film=True, po=(None, None)),      # many items per CTA, 3 slots
+    dict(C=32, t=128160, B=2, sc=False, film=True, po=(0.25, 0.25)),
+]
+
+
+@pytest.mark.parametrize("c", TRUNK_CASES, ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items()))
+def test_conv_trunk_vs_emulator(c):
+    """ou_conv_trunk against the emulator AND against its own three-launch expansion."""
+    g = torch.Generator().manual_seed(4321)
+    B, C, t = c["B"], c["C"], c["t"]
+    prog = P.Program(B)
+    prog.buf("in", "blocked", C, t)
+    inputs = {"in": bf(torch.randn(B, C, t, generator=g))}
+    if c["sc"]:
+        prog.buf("sc", "blocked", C, t)
+        inputs["sc"] = bf(torch.randn(B, C, t, generator=g))
+    fc1 = rand_fc(g, C, C, taps=5, tap_off=-2, prelu_in=0.2)
+    fc2 = rand_fc(g, C, C, taps=3, tap_off=-1)
+    fc3 = rand_fc(g, C, C, taps=3, tap_off=-1)
+    P.add_conv(prog, "conv1", "in", "c1", fc1, t, add1="sc" if c["sc"] else None,
+               scale1=0.7071 if c["sc"] else 1.0, film_off=0 if c["film"] else None, prelu_out=0.15)
+    P.add_conv(prog, "conv2", "c1", "c2", fc2, t, prelu_out=-0.3)
+    P.add_conv(prog, "conv3", "c2", "v", fc3, t, add1="in", scale1=0.7071, prelu_out=c["po"][0],
+               prelu_out2=c["po"][1])
+    assert P.fuse_trunk(prog, "trunk") and len(prog.ops) == 1
+    film = torch.randn(B, 2 * C, generator=g) if c["film"] else None
+    bufs, _, _ = E.run_program(prog, inputs, film=film, quant=True)
+    want = bufs["v"]
+
+    exe = R.Executor(prog, DEV, external=list(inputs))
+    for k, v in inputs.items():
+        exe.bufs[k] = R.pack_blocked(v.to(DEV))
+    film_d = film.to(DEV).contiguous() if film is not None else None
+    n0 = lib.launch_count()
+    exe.run(film=film_d, film_bstride=2 * C)
+    assert lib.launch_count() - n0 == 1          # the fused kernel ran, not the expansion
+    got = R.unpack_blocked(exe.bufs["v"]).cpu()
+    R.USE_TRUNK = False
+    try:
+        exe.bufs["v"].zero_()
+        n0 = lib.launch_count()
+        exe.run(film=film_d, film_bstride=2 * C)
+        assert lib.launch_count() - n0 == 3
+        split = R.unpack_blocked(exe.bufs["v"]).cpu()
+    finally:
+        R.USE_TRUNK = True
+    assert torch.isfinite(got).all()
+    err, err_split = rel_rms(got, want), rel_rms(got, split)
+    if err >= 3e-3 or err_split >= 3e-3:
+        d = (got - want).abs()
+        idx = [int(i) for i in torch.unravel_index(d.argmax(), d.shape)]
+        bad = (d > 0.05 * want.abs().max()).float()
+        raise AssertionError(f"rel_rms={err:.4f} vs split {err_split:.4f} worst at {idx} got={got[tuple(idx)]:.4f} "
+                             f"want={want[tuple(idx)]:.4f} bad_fraction={bad.mean():.5f} "
+                             f"bad rows (time) {bad.amax(dim=(0, 1)).nonzero().flatten()[:20].tolist()}")
+
+
 @pytest.mark.parametrize("hidden,B,T,add", [(256, 5, 37, True), (128, 2, 20, False),
                                             (384, 3, 25, True), (256, 32, 801, True)])
 def test_gru_vs_explicit(hidden, B, T, add):

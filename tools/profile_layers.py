@@ -85,6 +85,12 @@ def main():
                     byts = 2.0 * B * fc.cin * op.t_in + 4.0 * B * op.rows * fc.n
                 print(f"{op.name:28s} {kind:9s} {fc.cin:5d} {fc.n:5d} {fc.taps:4d} {fc.s:3d} {fc.up:3d} {op.rows:7d} "
                       f"{t:9.1f} {op.flops_exec / t / 1e6:7.1f} {byts / t / 1e3:7.0f} {100 * t / tot:5.1f}")
+            elif isinstance(op, P.TrunkOp):
+                c1 = op.parts[0]
+                c = c1.fc.cin
+                byts = 2.0 * B * c * c1.t_in * (2 + (c1.add1 is not None))
+                print(f"{op.name:28s} {kind:9s} {c:5d} {c:5d} {'533':>4s} {1:3d} {1:3d} {c1.rows:7d} "
+                      f"{t:9.1f} {op.flops_exec / t / 1e6:7.1f} {byts / t / 1e3:7.0f} {100 * t / tot:5.1f}")
             else:
                 print(f"{op.name:28s} {kind:9s} {'':5s} {'':5s} {'':4s} {'':3s} {'':3s} {'':7s} {t:9.1f} {'':7s} {'':7s} {100 * t / tot:5.1f}")
 
