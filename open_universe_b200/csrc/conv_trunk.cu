@@ -27,6 +27,9 @@
 #include "tc_ptx.cuh"
 
 namespace ou {
+namespace tc {
+extern long long* g_trace;
+}
 namespace trunk {
 
 using namespace ou::tc;
@@ -37,6 +40,8 @@ constexpr int TAPS1 = 5, TAPS2 = 3, TAPS3 = 3, NTAPS = TAPS1 + TAPS2 + TAPS3;
 constexpr int SLOT_COLS = 64;                 // TMEM columns per slot (= W * C)
 
 struct TrunkArgs {
+  long long* trace;   // debug (ou_debug_set_trace): CTA 0 stamps clock64(): [0..63][8] slot-0 items, then
+                      // [64..127][8] MMA-warp issue log (event = slot * 3 + stage, round-robin over 64 rows)
   ou_trunk_params p;
   int items_per_clip, total_items;
   int x_box_rows, x_boxes;
@@ -141,6 +146,7 @@ __device__ __forceinline__ void mma_role(const TrunkArgs& a, const Smem& sm, uin
     ph_xp[s] = 0, ph_c[s] = 0;
   }
   int remaining = 3 * n_items;
+  int issued = 0;
   while (remaining > 0) {
     bool any = false;
 #pragma unroll
@@ -167,6 +173,10 @@ __device__ __forceinline__ void mma_role(const TrunkArgs& a, const Smem& sm, uin
         }
         ph_c[s] ^= 1;
       }
+      if (a.trace != nullptr && blockIdx.x == 0 && lane == 0 && issued >= 72 && issued < 72 + 64 * 8) {
+        a.trace[512 + (issued - 72)] = clock64() * 16 + s * 4 + (stage[s] + 2) % 3;
+      }
+      issued++;
       remaining--;
       any = true;
     }
@@ -246,6 +256,9 @@ __device__ __forceinline__ void slot_role(const TrunkArgs& a, const Smem& sm, ui
 
   uint32_t ph_x = 0, ph_sc = 0, ph_acc = 0;
   int last_b = -1;
+#define TRUNK_STAMP(ev)                                                                     \
+  if (a.trace != nullptr && blockIdx.x == 0 && slot == 0 && leader && n / S >= 8 && n / S < 72) \
+    a.trace[(n / S - 8) * 8 + (ev)] = clock64();
   for (int n = slot; n < n_items; n += S) {
     int b, t0;
     item_pos(n, b, t0);
@@ -269,8 +282,10 @@ __device__ __forceinline__ void slot_role(const TrunkArgs& a, const Smem& sm, ui
 
     // ---- stage 0: capture the raw residual rows, PReLU the tile in place
     uint4 res[G::W][G::CH];
+    TRUNK_STAMP(0)
     mbar_wait(bar_x, ph_x);
     ph_x ^= 1;
+    TRUNK_STAMP(1)
 #pragma unroll
     for (int sub = 0; sub < G::W; sub++) {
 #pragma unroll
@@ -291,11 +306,13 @@ __device__ __forceinline__ void slot_role(const TrunkArgs& a, const Smem& sm, ui
     fence_proxy_async();
     __syncwarp();
     if (lane == 0) mbar_arrive(bar_xp);
+    TRUNK_STAMP(2)
 
     // ---- stage 1: c1 = PReLU(FiLM((conv1 + b1 + sc) * s1)) -> Cb (bf16, swizzled)
     mbar_wait(bar_acc, ph_acc);
     ph_acc ^= 1;
     tc_fence_after();
+    TRUNK_STAMP(3)
     if (leader && has_next) load_x(n + S);      // conv1's MMAs are done with X
     if (HAS_SC) {
       mbar_wait(bar_sc, ph_sc);
@@ -343,11 +360,13 @@ __device__ __forceinline__ void slot_role(const TrunkArgs& a, const Smem& sm, ui
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(bar_c);
+    TRUNK_STAMP(4)
 
     // ---- stage 2: c2 = PReLU(conv2 + b2) -> Cb in place
     mbar_wait(bar_acc, ph_acc);
     ph_acc ^= 1;
     tc_fence_after();
+    TRUNK_STAMP(5)
 #pragma unroll
     for (int sub = 0; sub < G::W; sub++) {
       const int i = sub * 128 + row;
@@ -381,11 +400,13 @@ __device__ __forceinline__ void slot_role(const TrunkArgs& a, const Smem& sm, ui
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(bar_c);
+    TRUNK_STAMP(6)
 
     // ---- stage 3: v = (conv3 + b3 + x) * s3 -> PReLUs -> global
     mbar_wait(bar_acc, ph_acc);
     ph_acc ^= 1;
     tc_fence_after();
+    TRUNK_STAMP(7)
     if (HAS_SC && leader && has_next) load_sc(n + S);   // conv3's MMAs are done with Cb
 #pragma unroll
     for (int sub = 0; sub < G::W; sub++) {
@@ -548,6 +569,7 @@ template <int C>
 static int launch_c(const ou_trunk_params* p, cudaStream_t st) {
   using G = Geo<C>;
   TrunkArgs a;
+  a.trace = ou::tc::g_trace;
   a.p = *p;
   a.items_per_clip = ceil_div(p->t, G::VALID);
   a.total_items = a.items_per_clip * p->batch;

@@ -346,6 +346,7 @@ class ScoreRunner:
                     self.proj_exe.bufs[name] = self.exe.bufs[name]
             self._prepare_embedding(net, device)
         self.film = None
+        self._film_tables = {}
         self.cond_lengths = self.prog.meta["lengths"]
         self.cond_channels = self.prog.meta["cond_channels"]
 
@@ -370,7 +371,11 @@ class ScoreRunner:
         Builds the FiLM table for all rows in two launches (embedding + one dense layer)."""
         g = self.sigma_embedding(torch.log10(net_sigma.float()))
         rows = g.shape[0]
-        film = torch.empty(rows, self.film_cols, dtype=torch.float32, device=self.device)
+        # persistent per row count: captured graphs keep pointing at it
+        film = self._film_tables.get(rows)
+        if film is None:
+            film = torch.empty(rows, self.film_cols, dtype=torch.float32, device=self.device)
+            self._film_tables[rows] = film
         lib.check(lib.load().ou_linear_f32(_ptr(g), _ptr(self.film_w), _ptr(self.film_b), _ptr(film),
                                            rows, self.dim, self.film_cols, self.film_cols, 0, 0.0,
                                            _stream()))
@@ -397,6 +402,84 @@ class ScoreRunner:
         film = self.film[film_row:]
         self.exe.run(film=film, film_bstride=self.film_cols if per_clip_film else 0,
                      in_scale=in_scale, coef=coef, noise=noise, xout=xout, net_out=net_out)
+
+
+# OU_GRAPH=0 launches the sampler loop kernel by kernel from Python instead of replaying a CUDA graph
+USE_GRAPH = os.environ.get("OU_GRAPH", "1") != "0"
+GRAPH_NOISE_LIMIT = 8 << 30     # bytes of pre-drawn noise above which the loop runs un-captured
+GRAPH_KERNELS = 0               # kernels of this library executed through graph replays so far
+
+
+def kernel_count():
+    """Kernels of libou_b200.so executed so far: direct launches + kernel nodes of replayed graphs."""
+    return lib.launch_count() + GRAPH_KERNELS
+
+
+class SamplerLoop:
+    """The N-step reverse-SDE loop of ``Universe.enhance`` (universe.py:334-343) for one
+    ScoreRunner, captured ONCE as a CUDA graph (N x 34 kernel nodes) over persistent buffers:
+    x, the per-step noise, FiLM table, input scales and update coefficients are static device
+    tensors whose CONTENTS are refreshed per call, so replaying costs one launch instead of
+    ~2 200 ctypes calls.  Noise is still drawn by ``torch.randn`` in the reference's call order
+    (a5 of SURVEY section 8), just before the replay instead of inside the loop."""
+
+    def __init__(self, sr, n_steps):
+        self.sr, self.n_steps = sr, n_steps
+        dev, B, T = sr.device, sr.batch, sr.t
+        self.x = torch.empty(B, 1, T, dtype=torch.float32, device=dev)
+        self.noise = torch.empty(max(n_steps - 1, 1), B, 1, T, dtype=torch.float32, device=dev)
+        self.in_scale = torch.ones(n_steps, B, dtype=torch.float32, device=dev)
+        self.coef = torch.zeros(n_steps, B, 3, dtype=torch.float32, device=dev)
+        self.graph = None
+
+    def _loop(self):
+        sr, N = self.sr, self.n_steps
+        for n in range(N):
+            sr.step(self.x, n, False, in_scale=self.in_scale[n], coef=self.coef[n],
+                    noise=self.noise[n] if n < N - 1 else None, xout=self.x)
+
+    def capture(self):
+        """Eager warm-up (lazy kernel attributes, tensor-map entry points) on a side stream, then
+        capture.  Runs on whatever is in the static buffers: call before loading real inputs."""
+        self.x.zero_()
+        self.noise.zero_()
+        side = torch.cuda.Stream(device=self.sr.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            self.sr.step(self.x, 0, False, in_scale=self.in_scale[0], coef=self.coef[0],
+                         noise=None, xout=self.x)
+        torch.cuda.current_stream().wait_stream(side)
+        g = torch.cuda.CUDAGraph()
+        n0 = lib.launch_count()
+        with torch.cuda.graph(g):
+            self._loop()
+        self.n_kernels = lib.launch_count() - n0      # kernel nodes of the graph
+        self.graph = g
+
+    def run(self):
+        global GRAPH_KERNELS
+        if self.graph is not None:
+            self.graph.replay()
+            GRAPH_KERNELS += self.n_kernels
+        else:
+            self._loop()
+
+
+def get_sampler_loop(sr, n_steps):
+    """Cached SamplerLoop of a ScoreRunner; captured as a CUDA graph unless disabled, profiled
+    (bench.py's per-launch events) or too large."""
+    loops = sr.__dict__.setdefault("_loops", {})
+    want_graph = (USE_GRAPH and PROFILE is None and
+                  (n_steps - 1) * sr.batch * sr.t * 4 <= GRAPH_NOISE_LIMIT)
+    key = (n_steps, want_graph)
+    if key not in loops:
+        loop = SamplerLoop(sr, n_steps)
+        if want_graph:
+            if sr.film is None or sr.film.shape[0] < n_steps:
+                raise RuntimeError("set_sigmas() must run before the sampler loop is captured")
+            loop.capture()
+        loops[key] = loop
+    return loops[key]
 
 
 def get_score_runner(net, batch, t, device):

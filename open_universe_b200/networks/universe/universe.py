@@ -270,12 +270,16 @@ class Universe(torch.nn.Module):
             sr.set_sigmas(net_sigma)
             sr.set_cond(cond)
 
-            x = randn(mixn, sigma_b[:, 0], rng=rng).contiguous()
+            # the N-step loop (universe.py:334-343) replays a CUDA graph over persistent buffers;
+            # noise is drawn with torch.randn in the reference's order, one call per step
+            loop = runtime.get_sampler_loop(sr, n_steps)
+            loop.in_scale.copy_(in_scale_b)
+            loop.coef.copy_(coef_b)
+            loop.x.copy_(randn(mixn, sigma_b[:, 0], rng=rng))
             for n in range(n_steps - 1):
-                z = randn(x, sigma_b[:, n + 1], rng=rng).contiguous()
-                sr.step(x, n, False, in_scale=in_scale_b[n], coef=coef_b[n], noise=z, xout=x)
-            n = n_steps - 1
-            sr.step(x, n, False, in_scale=in_scale_b[n], coef=coef_b[n], noise=None, xout=x)
+                loop.noise[n].copy_(randn(loop.x, sigma_b[:, n + 1], rng=rng))
+            loop.run()
+            x = loop.x
 
             # unpad, keep_rms, peak limiter (universe.py:346-357)
             out = torch.empty(B, 1, mix_len, dtype=torch.float32, device=dev)

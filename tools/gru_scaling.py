@@ -34,7 +34,8 @@ torch.cuda.synchronize()
 L.ou_debug_set_trace(None)
 tr = tr.cpu()
 if int(tr.max()) > 0:
+    tr = tr[:, :7]
     d = (tr[:, 1:] - tr[:, :-1]).float().mean(0)
     step = (tr[1:, 0] - tr[:-1, 0]).float().mean()
-    names = ["mma phase", "syncthreads", "gate math", "bar+push", "cluster arrive", "store+mov", "cluster wait"]
+    names = ["h_full wait", "mma phase", "syncthreads", "gate math", "shfl+st.async", "store+mov"]
     print("GRU tc per-step cycles (B=32):", {n: round(float(x)) for n, x in zip(names, d)}, "step", round(float(step)))

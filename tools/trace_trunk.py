@@ -1,0 +1,61 @@
+"""Per-stage timeline of the fused trunk kernel (CTA 0: slot-0 warpgroup and the MMA warp) from clock64
+stamps.  GPU box only."""
+import math
+import sys
+from pathlib import Path
+import torch
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+from open_universe_b200.engine import lib, program as P, runtime as R
+from open_universe_b200.engine.fold import FoldedConv
+
+B = 32
+L = lib.load()
+g = torch.Generator().manual_seed(0)
+for name, c, t, sc in (("C64 enc", 64, 64080, False), ("C64 dec", 64, 64080, True), ("C32 enc", 32, 128160, False),
+                       ("C32 dec", 32, 128160, True)):
+    def fc(taps, prelu):
+        return FoldedConv(torch.randn(c, taps, c, generator=g) / math.sqrt(taps * c), torch.zeros(c), c, c, 1, 1,
+                          taps, -(taps // 2), prelu)
+    prog = P.Program(B)
+    prog.buf("in", "blocked", c, t)
+    if sc:
+        prog.buf("sc", "blocked", c, t)
+    P.add_conv(prog, "conv1", "in", "c1", fc(5, 0.25), t, add1="sc" if sc else None, scale1=0.7071,
+               film_off=0, prelu_out=0.25)
+    P.add_conv(prog, "conv2", "c1", "c2", fc(3, None), t, prelu_out=0.25)
+    P.add_conv(prog, "conv3", "c2", "v", fc(3, None), t, add1="in", scale1=0.7071)
+    assert P.fuse_trunk(prog, "trunk")
+    exe = R.Executor(prog, "cuda")
+    exe.bufs["in"].normal_()
+    if sc:
+        exe.bufs["sc"].normal_()
+    film = torch.randn(1, 2 * c, device="cuda")
+    exe.run(film=film, film_bstride=0)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        exe.run(film=film, film_bstride=0)
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) / 5 * 1e3
+    byts = 2.0 * B * c * t * (3 if sc else 2)
+    tr = torch.zeros(1024, dtype=torch.int64, device="cuda")
+    L.ou_debug_set_trace(R._ptr(tr))
+    exe.run(film=film, film_bstride=0)
+    torch.cuda.synchronize()
+    L.ou_debug_set_trace(None)
+    tr = tr.cpu()
+    sl = tr[:512].reshape(64, 8)
+    ok = sl[:, 0] > 0
+    sl = sl[ok].double()
+    names = ["wait x", "T0", "wait acc1", "E1", "wait acc2", "E2", "wait acc3", "E3+coef"]
+    d = torch.cat([sl[:, 1:] - sl[:, :-1], (sl[1:, 0:1] - sl[:-1, 7:8]).mean(0, keepdim=True).expand(sl.shape[0], 1)], 1)
+    per_item = float((sl[1:, 0] - sl[:-1, 0]).float().mean())
+    print(f"== {name}: {us:.1f} us, {byts / us / 1e3:.0f} GB/s; slot-0 item period {per_item:.0f} cycles")
+    print("   " + "  ".join(f"{n}={float(d[:, i].float().mean()):.0f}" for i, n in enumerate(names)))
+    mm = tr[512:]
+    mm = mm[mm > 0]
+    clk, tag = mm // 16, mm % 16
+    gaps = (clk[1:] - clk[:-1]).float()
+    print(f"   MMA warp: mean gap between issues {float(gaps.mean()):.0f} cycles; first 18: "
+          + " ".join(f"s{int(x) // 4}M{int(x) % 4 + 1}+{int(gp)}" for x, gp in zip(tag[1:19], gaps[:18])))
