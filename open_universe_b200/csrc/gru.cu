@@ -8,6 +8,7 @@
 // pushes its slice of h_t into every CTA of the cluster through distributed shared memory; one
 // cluster barrier per step.  Everything is fp32 (the recurrence is the precision-critical part).
 #include <cooperative_groups.h>
+#include <cuda_fp16.h>
 
 #include <cstdlib>
 
@@ -465,7 +466,6 @@ __global__ void __launch_bounds__(GTC_NT) gru_cluster_tc_kernel(const GruArgs a)
       }
     }
     gxr = nxr, gxz = nxz, gxn = nxn, addv = nadd;
-    GRU_STAMP(6)
   }
   // no CTA may exit while a peer's stores to it could still be in flight
   cluster.sync();
@@ -494,14 +494,336 @@ static int launch_gru_tc(const GruArgs& a, cudaStream_t st) {
   return check_launch("ou_gru_bidir(tc)");
 }
 
-// OU_GRU_IMPL=fma forces the CUDA-core kernel for H = 256 (A/B timing, fp32-exact recurrence)
-static bool gru_use_tc() {
+// ------------------------------------------------------------------------------------------------
+// fp16 tensor-core variant (all hidden sizes; the default).  Same significand as the TF32 kernel
+// above (11 bits) for W_hh and for the exchanged hidden state, fp32 accumulation, fp32 gates and an
+// fp32 copy of h in the owning thread.  What bounds a step of the recurrence is the all-to-all
+// exchange of h_t over the SM-to-SM network, which moves roughly one st.async packet per clock per
+// SM whatever its size (measured: 512 packets of 16 B and 512 of 8 B both cost ~600 clk), so the
+// design minimises PACKETS: fp16 state, 16-byte packets (one clip x 8 units), and as few clip slots
+// per cluster as co-residency allows.  There is NO intra-CTA barrier: a warp owns 8 hidden units and
+// computes their three gate rows over the FULL K itself as two m16n8k16 tiles, [r(8) | z(8)] and
+// [n(8) | 8 zero rows], so every lane ends up with r, z, n of unit g for clips 2*t4 and 2*t4+1
+// without any shuffle, applies the gates, and after an 8-shuffle all-gather lane g pushes the two
+// (clip, 8 units) vectors into CTA g.  K is visited in a permuted order (lane t4 owns 8 consecutive
+// columns of every 32) so that one 16-byte shared load feeds two k16 steps; W_hh fragments use the
+// same permutation.  h_buf holds 16-byte (octet, clip) cells at index octet * 10 + clip: the
+// B-fragment loads of a quarter warp then hit 32 distinct banks.
+template <int H>
+struct G16 {
+  static constexpr int CS = 8;
+  static constexpr int HS = H / CS;      // hidden units per CTA
+  static constexpr int NW = HS / 8;      // warps (8 units each)
+  static constexpr int NT = NW * 32;
+  static constexpr int KS = H / 16;      // k16 steps
+  static constexpr int CELLS = (H / 8) * 10;   // 16-byte cells per h buffer
+  static_assert(H % 64 == 0 && HS % 8 == 0 && KS % 2 == 0, "bad GRU shape");
+};
+
+// 1 / (1 + 2^x): ex2.approx.ftz + rcp.approx.ftz, ~2 ulp; the argument never leaves [-126, 126] in any
+// regime that matters (2^x underflows to 0 -> 1, overflows to inf -> 0: both the correct limits)
+__device__ __forceinline__ float rcp1p_ex2(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+  return r;
+}
+
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ void mma_f16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                        uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+      "{%0,%1,%2,%3};\n"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void st_async_u4(uint32_t remote_addr, uint4 v, uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+               ::"r"(remote_addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(remote_bar)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t r;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+  return r;
+}
+
+// BG: clip slots per cluster (4 or 8; the MMA n dimension is always 8); NCH: accumulator chains per
+// tile (measured: 4 chains are no faster than 2 -- the k loop is bound by HMMA issue, ~10 clk each);
+// LEAN: branch-free gate math on bare ex2 / rcp (halves the gate phase)
+template <int H, int BG, int NCH, bool LEAN>
+__global__ void __launch_bounds__(G16<H>::NT) gru_cluster_f16_kernel(const GruArgs a) {
+  using G = G16<H>;
+  constexpr int CS = G::CS, HS = G::HS, KS = G::KS;
+  __shared__ __align__(16) uint4 h_buf[2][G::CELLS];
+  __shared__ __align__(8) unsigned long long h_full[2];
+
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int cid = blockIdx.x / CS;
+  const int dir = cid & 1;
+  const int b0 = (cid >> 1) * BG;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int T = a.t;
+
+  // gate stage of this lane: unit hu, clip slots 2*t4 and 2*t4 + 1
+  const int hu = rank * HS + 8 * warp + g;
+  const int octet = rank * (HS / 8) + warp;
+
+  // register-resident fp16 A fragments.  tile 1: row g = r(unit g), row g + 8 = z(unit g);
+  // tile 2: row g = n(unit g), rows 8..15 zero
+  uint32_t wr[KS][2], wz[KS][2], wn[KS][2];
+  {
+    const float* w_r = a.w_hh + ((size_t)dir * 3 * H + hu) * H;
+    const float* w_z = w_r + (size_t)H * H;
+    const float* w_n = w_z + (size_t)H * H;
+#pragma unroll
+    for (int i = 0; i < KS; i++) {
+      const int p = 32 * (i >> 1) + 8 * t4 + 4 * (i & 1);
+      const float4 vr = *reinterpret_cast<const float4*>(w_r + p);
+      const float4 vz = *reinterpret_cast<const float4*>(w_z + p);
+      const float4 vn = *reinterpret_cast<const float4*>(w_n + p);
+      wr[i][0] = pack_h2(vr.x, vr.y), wr[i][1] = pack_h2(vr.z, vr.w);
+      wz[i][0] = pack_h2(vz.x, vz.y), wz[i][1] = pack_h2(vz.z, vz.w);
+      wn[i][0] = pack_h2(vn.x, vn.y), wn[i][1] = pack_h2(vn.z, vn.w);
+    }
+  }
+  for (int i = tid; i < 2 * G::CELLS; i += G::NT) (&h_buf[0][0])[i] = make_uint4(0, 0, 0, 0);
+  const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(&h_full[0]);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // h_{-1} = 0 is already in h_buf[0]: complete phase 0 of its barrier by hand
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar0) : "memory");
+  }
+
+  const bool slot_ok = 2 * t4 < BG;               // lanes whose clip slots exist in this cluster
+  bool valid[2];
+  float bhr = 0.f, bhz = 0.f, bhn = 0.f;
+  float hprev[2] = {0.f, 0.f};
+  const float* gxp[2] = {nullptr, nullptr};
+  size_t out_base[2] = {0, 0};
+  {
+    const float* bh = a.b_hh + (size_t)dir * 3 * H;
+    bhr = bh[hu], bhz = bh[H + hu], bhn = bh[2 * H + hu];
+  }
+#pragma unroll
+  for (int e = 0; e < 2; e++) {
+    const int clip = b0 + 2 * t4 + e;
+    valid[e] = slot_ok && clip < a.batch;
+    if (valid[e]) {
+      gxp[e] = a.gx + (size_t)clip * T * 6 * H + (size_t)dir * 3 * H + hu;
+      out_base[e] = cl_off(clip, dir * H + hu, 0, 2 * H, T, cl_cb(2 * H));
+    }
+  }
+  const bool has_add = a.add != nullptr;
+  const unsigned short* addp = reinterpret_cast<const unsigned short*>(a.add);
+  const int ocb = cl_cb(2 * H);
+  // push target of this lane: CTA g; cells (octet, clip 2*t4) and (octet, clip 2*t4 + 1) of its h_buf[0]
+  const uint32_t dst_h = mapa_u32((uint32_t)__cvta_generic_to_shared(&h_buf[0][octet * 10 + 2 * t4]), (uint32_t)g);
+  const uint32_t dst_bar = mapa_u32(bar0, (uint32_t)g);
+  cluster.sync();
+
+  // input pre-activations (and the residual) come from HBM / L2: fetched two steps ahead and kept as
+  // raw bits until used, so that no dependent instruction stalls the in-order warp on a load.  The
+  // loop is deliberately NOT unrolled (rotating register sets instead of the moves at its end): the
+  // 3x larger body measured 12 % slower -- the recurrence is a serial chain and pays for every
+  // instruction-cache line it touches.
+  float x0[2][3], x1[2][3];
+  unsigned short ad0[2], ad1[2];
+#pragma unroll
+  for (int e = 0; e < 2; e++) {
+    x0[e][0] = x0[e][1] = x0[e][2] = x1[e][0] = x1[e][1] = x1[e][2] = 0.f;
+    ad0[e] = ad1[e] = 0;
+    if (valid[e]) {
+      const int ta = dir ? T - 1 : 0;
+      const float* gp = gxp[e] + (size_t)ta * 6 * H;
+      x0[e][0] = __ldg(gp), x0[e][1] = __ldg(gp + H), x0[e][2] = __ldg(gp + 2 * H);
+      if (has_add) ad0[e] = __ldg(addp + out_base[e] + (size_t)ta * ocb);
+      if (T > 1) {
+        const int tb = dir ? T - 2 : 1;
+        gp = gxp[e] + (size_t)tb * 6 * H;
+        x1[e][0] = __ldg(gp), x1[e][1] = __ldg(gp + H), x1[e][2] = __ldg(gp + 2 * H);
+        if (has_add) ad1[e] = __ldg(addp + out_base[e] + (size_t)tb * ocb);
+      }
+    }
+  }
+  for (int step = 0; step < T; step++) {
+    const int t = dir ? (T - 1 - step) : step;
+    const int cur = step & 1;
+    float x2[2][3];
+    unsigned short ad2[2];
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      x2[e][0] = x2[e][1] = x2[e][2] = 0.f;
+      ad2[e] = 0;
+      if (valid[e] && step + 2 < T) {
+        const int tn = dir ? t - 2 : t + 2;
+        const float* gp = gxp[e] + (size_t)tn * 6 * H;
+        x2[e][0] = __ldg(gp), x2[e][1] = __ldg(gp + H), x2[e][2] = __ldg(gp + 2 * H);
+        if (has_add) ad2[e] = __ldg(addp + out_base[e] + (size_t)tn * ocb);
+      }
+    }
+    // arm the barrier that collects h_t (H units x BG clips x 2 B), then wait for h_{t-1}
+    if (tid == 0 && step + 1 < T)
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8u * (cur ^ 1)),
+                   "r"((uint32_t)(H * BG * 2))
+                   : "memory");
+    GRU_STAMP(0)
+    gru_mbar_wait(bar0 + 8u * cur, (uint32_t)((step >> 1) & 1));
+    GRU_STAMP(1)
+    // NCH independent accumulator chains per tile: the k loop is bound by the HMMA accumulate latency
+    float a1[NCH][4], a2[NCH][4];
+#pragma unroll
+    for (int c = 0; c < NCH; c++)
+      a1[c][0] = a1[c][1] = a1[c][2] = a1[c][3] = a2[c][0] = a2[c][1] = a2[c][2] = a2[c][3] = 0.f;
+    const uint4* hb = &h_buf[cur][t4 * 10 + g];
+#pragma unroll
+    for (int i = 0; i < KS; i += 2) {
+      const uint4 v = hb[(i >> 1) * 40];   // octet 4 * (i / 2) + t4
+      const int c = NCH == 4 ? (i & 2) : 0;
+      mma_f16(a1[c], wr[i][0], wz[i][0], wr[i][1], wz[i][1], v.x, v.y);
+      mma_f16(a2[c], wn[i][0], 0u, wn[i][1], 0u, v.x, v.y);
+      mma_f16(a1[c + 1], wr[i + 1][0], wz[i + 1][0], wr[i + 1][1], wz[i + 1][1], v.z, v.w);
+      mma_f16(a2[c + 1], wn[i + 1][0], 0u, wn[i + 1][1], 0u, v.z, v.w);
+    }
+    GRU_STAMP(2)
+    float hnew[2];
+    if (LEAN) {
+      // gates of both (unit, clip) elements, branch-free so that their MUFU chains interleave
+      constexpr float L2E = 1.4426950408889634f;
+      float rr[2], zz[2], hn[2];
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        float hr = a1[0][e] + a1[1][e], hz = a1[0][2 + e] + a1[1][2 + e];
+        hn[e] = a2[0][e] + a2[1][e];
+        if (NCH == 4) {
+          hr += a1[2][e] + a1[3][e], hz += a1[2][2 + e] + a1[3][2 + e];
+          hn[e] += a2[2][e] + a2[3][e];
+        }
+        hn[e] += bhn;
+        rr[e] = rcp1p_ex2(-L2E * (x0[e][0] + (bhr + hr)));
+        zz[e] = rcp1p_ex2(-L2E * (x0[e][1] + (bhz + hz)));
+      }
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const float n = fmaf(2.f, rcp1p_ex2(-2.f * L2E * fmaf(rr[e], hn[e], x0[e][2])), -1.f);
+        const float hv = fmaf(zz[e], hprev[e] - n, n);   // (1 - z) n + z h
+        hnew[e] = valid[e] ? hv : 0.f;
+        hprev[e] = hnew[e];
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        float hr = a1[0][e] + a1[1][e], hz = a1[0][2 + e] + a1[1][2 + e], hn = a2[0][e] + a2[1][e];
+        if (NCH == 4) {
+          hr += a1[2][e] + a1[3][e], hz += a1[2][2 + e] + a1[3][2 + e];
+          hn += a2[2][e] + a2[3][e];
+        }
+        const float r = sigmoid_f(x0[e][0] + bhr + hr);
+        const float z = sigmoid_f(x0[e][1] + bhz + hz);
+        const float n = tanh_f(x0[e][2] + r * (bhn + hn));
+        hnew[e] = valid[e] ? (1.f - z) * n + z * hprev[e] : 0.f;
+        hprev[e] = hnew[e];
+      }
+    }
+    GRU_STAMP(3)
+    if (step + 1 < T) {
+      // all-gather the 8 units of the warp: w[j] = (h(unit j, clip 2*t4), h(unit j, clip 2*t4+1)) as f16x2
+      const uint32_t hq = pack_h2(hnew[0], hnew[1]);
+      uint32_t w[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) w[j] = __shfl_sync(0xffffffffu, hq, t4 + 4 * j);
+      if (slot_ok) {
+        const uint32_t boff = (uint32_t)((cur ^ 1) * G::CELLS * 16);
+        const uint4 lo4 = make_uint4(prmt(w[0], w[1], 0x5410), prmt(w[2], w[3], 0x5410),
+                                     prmt(w[4], w[5], 0x5410), prmt(w[6], w[7], 0x5410));
+        const uint4 hi4 = make_uint4(prmt(w[0], w[1], 0x7632), prmt(w[2], w[3], 0x7632),
+                                     prmt(w[4], w[5], 0x7632), prmt(w[6], w[7], 0x7632));
+        st_async_u4(dst_h + boff, lo4, dst_bar + 8u * (cur ^ 1));
+        st_async_u4(dst_h + boff + 16u, hi4, dst_bar + 8u * (cur ^ 1));
+      }
+    }
+    GRU_STAMP(4)
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      if (valid[e]) {
+        const float addv = __uint_as_float((uint32_t)ad0[e] << 16);
+        a.out[out_base[e] + (size_t)t * ocb] = __float2bfloat16((hnew[e] + addv) * a.scale);
+      }
+#pragma unroll
+      for (int q = 0; q < 3; q++) x0[e][q] = x1[e][q], x1[e][q] = x2[e][q];
+      ad0[e] = ad1[e], ad1[e] = ad2[e];
+    }
+    GRU_STAMP(5)
+  }
+  // no CTA may exit while a peer's stores to it could still be in flight
+  cluster.sync();
+}
+
+template <int H, int BG, int NCH = 2, bool LEAN = true>
+static int launch_gru_f16_bg(const GruArgs& a, cudaStream_t st, int* max_clusters) {
+  using G = G16<H>;
+  auto kern = gru_cluster_f16_kernel<H, BG, NCH, LEAN>;
+  const int clusters = 2 * ceil_div(a.batch, BG);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(clusters * G::CS);
+  cfg.blockDim = dim3(G::NT);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = G::CS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (max_clusters) {   // query only
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) {
+      cudaGetLastError();
+      n = 0;
+    }
+    *max_clusters = n;
+    return OU_OK;
+  }
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a);
+  if (e != cudaSuccess) {
+    set_error("ou_gru_bidir(f16): launch H=%d BG=%d: %s", H, BG, cudaGetErrorString(e));
+    return OU_ERR_CUDA;
+  }
+  return check_launch("ou_gru_bidir(f16)");
+}
+
+// 8 clip slots per cluster.  Measured on B200: 4 slots (half the exchange packets, twice the clusters)
+// is no faster while every cluster has its SMs to itself and slower once two CTAs share an SM;
+// OU_GRU_BG=4 keeps the variant reachable for A/B runs.
+template <int H>
+static int launch_gru_f16(const GruArgs& a, cudaStream_t st) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("OU_GRU_BG");
+    forced = e ? atoi(e) : 0;
+  }
+  const bool use4 = forced == 4;
+  return use4 ? launch_gru_f16_bg<H, 4>(a, st, nullptr) : launch_gru_f16_bg<H, 8>(a, st, nullptr);
+}
+
+// OU_GRU_IMPL = f16 (default) | tf32 (H = 256 only) | fma (CUDA cores, fp32-exact recurrence)
+static int gru_impl() {
   static int cached = -1;
   if (cached < 0) {
     const char* e = getenv("OU_GRU_IMPL");
-    cached = (e && e[0] == 'f') ? 0 : 1;
+    cached = (e && e[0] == 'f' && e[1] == 'm') ? 0 : ((e && e[0] == 't') ? 1 : 2);
   }
-  return cached == 1;
+  return cached;
 }
 
 }  // namespace ou
@@ -512,10 +834,13 @@ extern "C" int ou_gru_bidir(const float* gx, const float* w_hh, const float* b_h
   OU_REQUIRE(batch > 0 && t > 0, "ou_gru_bidir: empty problem");
   ou::GruArgs a{ou::tc::g_trace, gx, w_hh, b_hh, (const __nv_bfloat16*)add, (__nv_bfloat16*)out, scale, batch, t};
   cudaStream_t st = (cudaStream_t)stream;
+  const int impl = ou::gru_impl();
   switch (hidden) {
-    case 128: return ou::launch_gru<128, 4>(a, st);
-    case 256: return ou::gru_use_tc() ? ou::launch_gru_tc(a, st) : ou::launch_gru<256, 8>(a, st);
-    case 384: return ou::launch_gru<384, 16>(a, st);
+    case 128: return impl == 2 ? ou::launch_gru_f16<128>(a, st) : ou::launch_gru<128, 4>(a, st);
+    case 256:
+      return impl == 2 ? ou::launch_gru_f16<256>(a, st)
+                       : (impl == 1 ? ou::launch_gru_tc(a, st) : ou::launch_gru<256, 8>(a, st));
+    case 384: return impl == 2 ? ou::launch_gru_f16<384>(a, st) : ou::launch_gru<384, 16>(a, st);
     default:
       ou::set_error("ou_gru_bidir: hidden size %d has no kernel (128, 256, 384)", hidden);
       return OU_ERR_UNSUPPORTED;

@@ -34,8 +34,17 @@ torch.cuda.synchronize()
 L.ou_debug_set_trace(None)
 tr = tr.cpu()
 if int(tr.max()) > 0:
-    tr = tr[:, :7]
+    import os
+    impl = os.environ.get("OU_GRU_IMPL", "f16")
+    if impl.startswith("f1"):
+                order = [0, 1, 2, 3, 4, 5]
+        names = ["h_full wait", "lds+mma", "gate math", "gather+st.async", "store+mov"]
+    else:
+        order = [0, 1, 2, 3, 4, 5, 6]
+        names = ["h_full wait", "mma phase", "syncthreads", "gate math", "shfl+st.async", "store+mov"]
+    tr = tr[:, order]
     d = (tr[:, 1:] - tr[:, :-1]).float().mean(0)
     step = (tr[1:, 0] - tr[:-1, 0]).float().mean()
-    names = ["h_full wait", "mma phase", "syncthreads", "gate math", "shfl+st.async", "store+mov"]
-    print("GRU tc per-step cycles (B=32):", {n: round(float(x)) for n, x in zip(names, d)}, "step", round(float(step)))
+    back = (tr[1:, 0] - tr[:-1, -1]).float().mean()
+    print("GRU per-step cycles (B=32):", {n: round(float(x)) for n, x in zip(names, d)},
+          "loop back-edge", round(float(back)), "step", round(float(step)))
