@@ -198,19 +198,10 @@ __device__ __forceinline__ void mma_role(const TcArgs& a, const Ctx& c, bool use
 }
 
 // ================================================================================ transform
-__device__ __forceinline__ uint4 prelu_vec(uint4 v, float slope) {
-  uint32_t* w = reinterpret_cast<uint32_t*>(&v);
-#pragma unroll
-  for (int k = 0; k < 4; k++) {
-    const float2 f = bf2_to_f2(w[k]);
-    w[k] = f2_to_bf2(prelu_f(f.x, slope), prelu_f(f.y, slope));
-  }
-  return v;
-}
-
 __device__ __forceinline__ void transform_role(const TcArgs& a, const Ctx& c, int xt, int lane) {
   Ring ra;
-  const float slope = a.p.prelu_in;
+  uint32_t slope, slope_lo;   // packed bf16x2 (hi, lo) halves of the slope
+  split_slope(a.p.prelu_in, slope, slope_lo);
   const int nvec = (int)(a.a_tx_bytes >> 4);
   int ti = 0;
   for (int mt = c.mt0; mt < a.total_m_tiles; mt += c.mt_stride, ti++) {
@@ -223,12 +214,12 @@ __device__ __forceinline__ void transform_role(const TcArgs& a, const Ctx& c, in
       for (; i + 3 * 128 < nvec; i += 4 * 128) {   // 4 independent vectors in flight
         uint4 v0 = lds_u4(base + (uint32_t)i * 16), v1 = lds_u4(base + (uint32_t)(i + 128) * 16);
         uint4 v2 = lds_u4(base + (uint32_t)(i + 256) * 16), v3 = lds_u4(base + (uint32_t)(i + 384) * 16);
-        sts_u4(base + (uint32_t)i * 16, prelu_vec(v0, slope));
-        sts_u4(base + (uint32_t)(i + 128) * 16, prelu_vec(v1, slope));
-        sts_u4(base + (uint32_t)(i + 256) * 16, prelu_vec(v2, slope));
-        sts_u4(base + (uint32_t)(i + 384) * 16, prelu_vec(v3, slope));
+        sts_u4(base + (uint32_t)i * 16, prelu_bf16x8(v0, slope, slope_lo));
+        sts_u4(base + (uint32_t)(i + 128) * 16, prelu_bf16x8(v1, slope, slope_lo));
+        sts_u4(base + (uint32_t)(i + 256) * 16, prelu_bf16x8(v2, slope, slope_lo));
+        sts_u4(base + (uint32_t)(i + 384) * 16, prelu_bf16x8(v3, slope, slope_lo));
       }
-      for (; i < nvec; i += 128) sts_u4(base + (uint32_t)i * 16, prelu_vec(lds_u4(base + (uint32_t)i * 16), slope));
+      for (; i < nvec; i += 128) sts_u4(base + (uint32_t)i * 16, prelu_bf16x8(lds_u4(base + (uint32_t)i * 16), slope, slope_lo));
       }
       fence_proxy_async();
       __syncwarp();

@@ -35,7 +35,13 @@ namespace trunk {
 using namespace ou::tc;
 
 constexpr int S = 3;                          // item slots per CTA
-constexpr int NTHREADS = (1 + 4 * S) * 32;    // 416
+// Warps per slot: 4 (one per TMEM lane quarter, a thread owns a whole accumulator row) or 8 (two column
+// halves per quarter).  Measured on B200: 8 is 25 % SLOWER -- the kernel is bound by shared-memory
+// bandwidth (the N = 32 / 64 MMAs re-read their 4 KB A tile for every 16-wide k step: ~260 KB of
+// operand reads per item against ~115 KB of tile traffic), not by thread-level parallelism, and 25
+// warps leave only 72 registers per thread.
+constexpr int WPS = 4;
+constexpr int NTHREADS = (1 + WPS * S) * 32;  // 416
 constexpr int TAPS1 = 5, TAPS2 = 3, TAPS3 = 3, NTAPS = TAPS1 + TAPS2 + TAPS3;
 constexpr int SLOT_COLS = 64;                 // TMEM columns per slot (= W * C)
 
@@ -185,16 +191,6 @@ __device__ __forceinline__ void mma_role(const TrunkArgs& a, const Smem& sm, uin
 }
 
 // ---------------------------------------------------------------------------------- slot warpgroup
-__device__ __forceinline__ uint4 prelu_u4(uint4 v, float slope) {
-  uint32_t* w = reinterpret_cast<uint32_t*>(&v);
-#pragma unroll
-  for (int k = 0; k < 4; k++) {
-    const float2 f = bf2_to_f2(w[k]);
-    w[k] = f2_to_bf2(prelu_f(f.x, slope), prelu_f(f.y, slope));
-  }
-  return v;
-}
-
 template <int NPRELU>
 __device__ __forceinline__ float out_act(float y, float s1, float s2) {
   if (NPRELU > 0) y = prelu_f(y, s1);
@@ -209,9 +205,13 @@ __device__ __forceinline__ void slot_role(const TrunkArgs& a, const Smem& sm, ui
   using G = Geo<C>;
   const ou_trunk_params& p = a.p;
   const int quarter = warp & 3;                 // TMEM lane quarter this warp may read
+  const int half = ((warp - 1) % WPS) >> 2;     // which part of the channels this thread handles
   const int row = quarter * 32 + lane;          // accumulator row inside a 128-row sub-tile
-  const int wg_tid = (int)threadIdx.x - 32 - slot * 128;
-  const bool leader = row == 0;
+  const int wg_tid = (int)threadIdx.x - 32 - slot * (WPS * 32);
+  const bool leader = row == 0 && half == 0;
+  constexpr int HC = C / (WPS / 4);             // channels per thread
+  constexpr int CHH = G::CH / (WPS / 4);        // 16-byte chunks per thread and row
+  const int col0 = half * HC, ch0 = half * CHH;
   const int T = p.t;
   // per-slot addresses resolved once (the struct is indexed dynamically only here)
   const uint32_t X = sm.x[slot], Cb = sm.cb[slot];
@@ -221,6 +221,8 @@ __device__ __forceinline__ void slot_role(const TrunkArgs& a, const Smem& sm, ui
   const uint32_t bias2 = sm.bias2, coef3 = sm.coef3;
   const float slope_in = p.prelu_in, slope_m1 = p.prelu_mid1, slope_m2 = p.prelu_mid2;
   const float s3 = p.scale3;
+  uint32_t a_in_hi, a_in_lo;
+  split_slope(slope_in, a_in_hi, a_in_lo);
   const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(slot * SLOT_COLS);
   __nv_bfloat16* outp = (__nv_bfloat16*)p.out;
 
@@ -276,31 +278,40 @@ __device__ __forceinline__ void slot_role(const TrunkArgs& a, const Smem& sm, ui
         sts_f1(coef1 + 4u * wg_tid, c0);
         sts_f1(coef1 + 4u * (C + wg_tid), fmaf(c0, p.b1[wg_tid], be));
       }
-      asm volatile("bar.sync %0, 128;" ::"r"(1 + slot) : "memory");
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + slot), "n"(WPS * 32) : "memory");
     }
     last_b = b;
 
-    // ---- stage 0: capture the raw residual rows, PReLU the tile in place
-    uint4 res[G::W][G::CH];
+    // ---- stage 0: capture the raw residual rows, PReLU the tile in place.  All loads of a phase are
+    // issued before the first dependent instruction (the accessors are volatile asm and keep their
+    // order): a slot's warpgroup is a serial chain, every exposed shared-memory / TMEM latency
+    // is paid in full.
+    uint4 res[G::W][CHH];
     TRUNK_STAMP(0)
     mbar_wait(bar_x, ph_x);
     ph_x ^= 1;
     TRUNK_STAMP(1)
+    {
+      uint4 halo[CHH];
 #pragma unroll
-    for (int sub = 0; sub < G::W; sub++) {
+      for (int sub = 0; sub < G::W; sub++)
 #pragma unroll
-      for (int c = 0; c < G::CH; c++) {
-        const uint32_t addr = swz<C>(X, (uint32_t)((sub * 128 + row + 4) * G::ROWB + c * 16));
-        const uint4 v = lds_u4(addr);
-        res[sub][c] = v;
-        sts_u4(addr, prelu_u4(v, slope_in));
+        for (int c = 0; c < CHH; c++)
+          res[sub][c] = lds_u4(swz<C>(X, (uint32_t)((sub * 128 + row + 4) * G::ROWB + (ch0 + c) * 16)));
+      if (row < 4) {
+#pragma unroll
+        for (int c = 0; c < CHH; c++) halo[c] = lds_u4(swz<C>(X, (uint32_t)(row * G::ROWB + (ch0 + c) * 16)));
       }
-    }
-    if (row < 4) {
 #pragma unroll
-      for (int c = 0; c < G::CH; c++) {
-        const uint32_t addr = swz<C>(X, (uint32_t)(row * G::ROWB + c * 16));
-        sts_u4(addr, prelu_u4(lds_u4(addr), slope_in));
+      for (int sub = 0; sub < G::W; sub++)
+#pragma unroll
+        for (int c = 0; c < CHH; c++)
+          sts_u4(swz<C>(X, (uint32_t)((sub * 128 + row + 4) * G::ROWB + (ch0 + c) * 16)),
+                 prelu_bf16x8(res[sub][c], a_in_hi, a_in_lo));
+      if (row < 4) {
+#pragma unroll
+        for (int c = 0; c < CHH; c++)
+          sts_u4(swz<C>(X, (uint32_t)(row * G::ROWB + (ch0 + c) * 16)), prelu_bf16x8(halo[c], a_in_hi, a_in_lo));
       }
     }
     fence_proxy_async();
@@ -318,42 +329,54 @@ __device__ __forceinline__ void slot_role(const TrunkArgs& a, const Smem& sm, ui
       mbar_wait(bar_sc, ph_sc);
       ph_sc ^= 1;
     }
+    // The accumulator is read in NQ chunks of 16 columns, chunk q + 1 in flight (tcgen05.ld) while chunk
+    // q is processed; with the per-chunk shared loads issued before the wait.
+    constexpr int QS = HC / 16;   // chunks per sub-tile and thread
+    constexpr int NQ = G::W * QS;
+    auto q_taddr = [&](int q) { return taddr + (uint32_t)((q / QS) * C + col0 + (q % QS) * 16); };
+    uint32_t rbuf[2][16];
+    tmem_ld16(q_taddr(0), rbuf[0]);
 #pragma unroll
-    for (int sub = 0; sub < G::W; sub++) {
+    for (int q = 0; q < NQ; q++) {
+      const int sub = q / QS, cc = q % QS;
       const int i = sub * 128 + row;
       const int t = t0 - 2 + i;
       const bool inside = t >= 0 && t < T;
+      float4 k0[4], k1[4];
+      uint4 scv[2];
 #pragma unroll
-      for (int cc = 0; cc < C / 16; cc++) {
-        uint32_t r[16];
-        tmem_ld16(taddr + (uint32_t)(sub * C + cc * 16), r);
-        tmem_ld_wait();
+      for (int j = 0; j < 4; j++) {
+        k0[j] = lds_f4(coef1 + 4u * (col0 + cc * 16 + j * 4));
+        k1[j] = lds_f4(coef1 + 4u * (C + col0 + cc * 16 + j * 4));
+      }
+      if (HAS_SC) {
+        scv[0] = lds_u4(swz<C>(Cb, (uint32_t)(i * G::ROWB + (ch0 + 2 * cc) * 16)));
+        scv[1] = lds_u4(swz<C>(Cb, (uint32_t)(i * G::ROWB + (ch0 + 2 * cc + 1) * 16)));
+      }
+      tmem_ld_wait();
+      if (q + 1 < NQ) tmem_ld16(q_taddr(q + 1), rbuf[(q + 1) & 1]);
+      const uint32_t(&r)[16] = rbuf[q & 1];
 #pragma unroll
-        for (int h = 0; h < 2; h++) {
-          const uint32_t addr = swz<C>(Cb, (uint32_t)(i * G::ROWB + (2 * cc + h) * 16));
-          uint4 scv = make_uint4(0, 0, 0, 0);
-          if (HAS_SC) scv = lds_u4(addr);
-          const uint32_t* sw = reinterpret_cast<const uint32_t*>(&scv);
-          uint4 o;
-          uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+      for (int h = 0; h < 2; h++) {
+        const uint32_t* sw = reinterpret_cast<const uint32_t*>(&scv[h]);
+        uint4 o;
+        uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
 #pragma unroll
-          for (int k = 0; k < 2; k++) {
-            const int col = cc * 16 + h * 8 + k * 4;
-            const float4 c0 = lds_f4(coef1 + 4u * col);
-            const float4 c1 = lds_f4(coef1 + 4u * (C + col));
-            float a0 = __uint_as_float(r[h * 8 + k * 4]), a1 = __uint_as_float(r[h * 8 + k * 4 + 1]);
-            float a2 = __uint_as_float(r[h * 8 + k * 4 + 2]), a3 = __uint_as_float(r[h * 8 + k * 4 + 3]);
-            if (HAS_SC) {
-              const float2 fa = bf2_to_f2(sw[2 * k]), fb = bf2_to_f2(sw[2 * k + 1]);
-              a0 += fa.x, a1 += fa.y, a2 += fb.x, a3 += fb.y;
-            }
-            a0 = prelu_f(fmaf(c0.x, a0, c1.x), slope_m1), a1 = prelu_f(fmaf(c0.y, a1, c1.y), slope_m1);
-            a2 = prelu_f(fmaf(c0.z, a2, c1.z), slope_m1), a3 = prelu_f(fmaf(c0.w, a3, c1.w), slope_m1);
-            ow[2 * k] = inside ? f2_to_bf2(a0, a1) : 0u;
-            ow[2 * k + 1] = inside ? f2_to_bf2(a2, a3) : 0u;
+        for (int k = 0; k < 2; k++) {
+          const float4 c0 = k0[h * 2 + k], c1 = k1[h * 2 + k];
+          const int e = h * 8 + k * 4;
+          float a0 = __uint_as_float(r[e]), a1 = __uint_as_float(r[e + 1]);
+          float a2 = __uint_as_float(r[e + 2]), a3 = __uint_as_float(r[e + 3]);
+          if (HAS_SC) {
+            const float2 fa = bf2_to_f2(sw[2 * k]), fb = bf2_to_f2(sw[2 * k + 1]);
+            a0 += fa.x, a1 += fa.y, a2 += fb.x, a3 += fb.y;
           }
-          sts_u4(addr, o);
+          a0 = prelu_f(fmaf(c0.x, a0, c1.x), slope_m1), a1 = prelu_f(fmaf(c0.y, a1, c1.y), slope_m1);
+          a2 = prelu_f(fmaf(c0.z, a2, c1.z), slope_m1), a3 = prelu_f(fmaf(c0.w, a3, c1.w), slope_m1);
+          ow[2 * k] = inside ? f2_to_bf2(a0, a1) : 0u;
+          ow[2 * k + 1] = inside ? f2_to_bf2(a2, a3) : 0u;
         }
+        sts_u4(swz<C>(Cb, (uint32_t)(i * G::ROWB + (ch0 + 2 * cc + h) * 16)), o);
       }
     }
     fence_proxy_async();
@@ -367,33 +390,35 @@ __device__ __forceinline__ void slot_role(const TrunkArgs& a, const Smem& sm, ui
     ph_acc ^= 1;
     tc_fence_after();
     TRUNK_STAMP(5)
+    tmem_ld16(q_taddr(0), rbuf[0]);
 #pragma unroll
-    for (int sub = 0; sub < G::W; sub++) {
+    for (int q = 0; q < NQ; q++) {
+      const int sub = q / QS, cc = q % QS;
       const int i = sub * 128 + row;
       const int t = t0 - 1 + i;
       const bool inside = t >= 0 && t < T && i < 128 * G::W - 2;
+      float4 bb[4];
 #pragma unroll
-      for (int cc = 0; cc < C / 16; cc++) {
-        uint32_t r[16];
-        tmem_ld16(taddr + (uint32_t)(sub * C + cc * 16), r);
-        tmem_ld_wait();
+      for (int j = 0; j < 4; j++) bb[j] = lds_f4(bias2 + 4u * (col0 + cc * 16 + j * 4));
+      tmem_ld_wait();
+      if (q + 1 < NQ) tmem_ld16(q_taddr(q + 1), rbuf[(q + 1) & 1]);
+      const uint32_t(&r)[16] = rbuf[q & 1];
 #pragma unroll
-        for (int h = 0; h < 2; h++) {
-          const uint32_t addr = swz<C>(Cb, (uint32_t)(i * G::ROWB + (2 * cc + h) * 16));
-          uint4 o;
-          uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+      for (int h = 0; h < 2; h++) {
+        uint4 o;
+        uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
 #pragma unroll
-          for (int k = 0; k < 2; k++) {
-            const float4 bb = lds_f4(bias2 + 4u * (cc * 16 + h * 8 + k * 4));
-            const float a0 = prelu_f(__uint_as_float(r[h * 8 + k * 4]) + bb.x, slope_m2);
-            const float a1 = prelu_f(__uint_as_float(r[h * 8 + k * 4 + 1]) + bb.y, slope_m2);
-            const float a2 = prelu_f(__uint_as_float(r[h * 8 + k * 4 + 2]) + bb.z, slope_m2);
-            const float a3 = prelu_f(__uint_as_float(r[h * 8 + k * 4 + 3]) + bb.w, slope_m2);
-            ow[2 * k] = inside ? f2_to_bf2(a0, a1) : 0u;
-            ow[2 * k + 1] = inside ? f2_to_bf2(a2, a3) : 0u;
-          }
-          sts_u4(addr, o);
+        for (int k = 0; k < 2; k++) {
+          const float4 b4 = bb[h * 2 + k];
+          const int e = h * 8 + k * 4;
+          const float a0 = prelu_f(__uint_as_float(r[e]) + b4.x, slope_m2);
+          const float a1 = prelu_f(__uint_as_float(r[e + 1]) + b4.y, slope_m2);
+          const float a2 = prelu_f(__uint_as_float(r[e + 2]) + b4.z, slope_m2);
+          const float a3 = prelu_f(__uint_as_float(r[e + 3]) + b4.w, slope_m2);
+          ow[2 * k] = inside ? f2_to_bf2(a0, a1) : 0u;
+          ow[2 * k + 1] = inside ? f2_to_bf2(a2, a3) : 0u;
         }
+        sts_u4(swz<C>(Cb, (uint32_t)(i * G::ROWB + (ch0 + 2 * cc + h) * 16)), o);
       }
     }
     fence_proxy_async();
@@ -408,37 +433,40 @@ __device__ __forceinline__ void slot_role(const TrunkArgs& a, const Smem& sm, ui
     tc_fence_after();
     TRUNK_STAMP(7)
     if (HAS_SC && leader && has_next) load_sc(n + S);   // conv3's MMAs are done with Cb
+    tmem_ld16(q_taddr(0), rbuf[0]);
 #pragma unroll
-    for (int sub = 0; sub < G::W; sub++) {
+    for (int q = 0; q < NQ; q++) {
+      const int sub = q / QS, cc = q % QS;
       const int i = sub * 128 + row;
       const int t = t0 + i;
       const bool valid = i < G::VALID && t < T;
       __nv_bfloat16* dst = outp + ((size_t)b * T + t) * C;
+      float4 kk[4];
 #pragma unroll
-      for (int cc = 0; cc < C / 16; cc++) {
-        uint32_t r[16];
-        tmem_ld16(taddr + (uint32_t)(sub * C + cc * 16), r);
-        tmem_ld_wait();
-        U8 o;
+      for (int j = 0; j < 4; j++) kk[j] = lds_f4(coef3 + 4u * (col0 + cc * 16 + j * 4));
+      tmem_ld_wait();
+      if (q + 1 < NQ) tmem_ld16(q_taddr(q + 1), rbuf[(q + 1) & 1]);
+      const uint32_t(&r)[16] = rbuf[q & 1];
+      U8 o;
 #pragma unroll
-        for (int h = 0; h < 2; h++) {
-          const uint32_t* rw = reinterpret_cast<const uint32_t*>(&res[sub][2 * cc + h]);
+      for (int h = 0; h < 2; h++) {
+        const uint32_t* rw = reinterpret_cast<const uint32_t*>(&res[sub][2 * cc + h]);
 #pragma unroll
-          for (int k = 0; k < 2; k++) {
-            const float4 c1 = lds_f4(coef3 + 4u * (cc * 16 + h * 8 + k * 4));
-            const float2 fa = bf2_to_f2(rw[2 * k]), fb = bf2_to_f2(rw[2 * k + 1]);
-            const float a0 = fmaf(s3, __uint_as_float(r[h * 8 + k * 4]) + fa.x, c1.x);
-            const float a1 = fmaf(s3, __uint_as_float(r[h * 8 + k * 4 + 1]) + fa.y, c1.y);
-            const float a2 = fmaf(s3, __uint_as_float(r[h * 8 + k * 4 + 2]) + fb.x, c1.z);
-            const float a3 = fmaf(s3, __uint_as_float(r[h * 8 + k * 4 + 3]) + fb.y, c1.w);
-            o.w[h * 4 + 2 * k] = f2_to_bf2(out_act<NPRELU>(a0, p.prelu_out, p.prelu_out2),
-                                           out_act<NPRELU>(a1, p.prelu_out, p.prelu_out2));
-            o.w[h * 4 + 2 * k + 1] = f2_to_bf2(out_act<NPRELU>(a2, p.prelu_out, p.prelu_out2),
-                                               out_act<NPRELU>(a3, p.prelu_out, p.prelu_out2));
-          }
+        for (int k = 0; k < 2; k++) {
+          const float4 c1 = kk[h * 2 + k];
+          const int e = h * 8 + k * 4;
+          const float2 fa = bf2_to_f2(rw[2 * k]), fb = bf2_to_f2(rw[2 * k + 1]);
+          const float a0 = fmaf(s3, __uint_as_float(r[e]) + fa.x, c1.x);
+          const float a1 = fmaf(s3, __uint_as_float(r[e + 1]) + fa.y, c1.y);
+          const float a2 = fmaf(s3, __uint_as_float(r[e + 2]) + fb.x, c1.z);
+          const float a3 = fmaf(s3, __uint_as_float(r[e + 3]) + fb.y, c1.w);
+          o.w[h * 4 + 2 * k] = f2_to_bf2(out_act<NPRELU>(a0, p.prelu_out, p.prelu_out2),
+                                         out_act<NPRELU>(a1, p.prelu_out, p.prelu_out2));
+          o.w[h * 4 + 2 * k + 1] = f2_to_bf2(out_act<NPRELU>(a2, p.prelu_out, p.prelu_out2),
+                                             out_act<NPRELU>(a3, p.prelu_out, p.prelu_out2));
         }
-        if (valid) stg_v8(dst + cc * 16, o);
       }
+      if (valid) stg_v8(dst + col0 + cc * 16, o);
     }
     tc_fence_before();   // TMEM reads ordered before the next item's MMAs (via xp_ready)
   }
@@ -481,8 +509,8 @@ trunk_kernel(const TrunkArgs a, const __grid_constant__ CUtensorMap tm_x,
     for (int s = 0; s < S; s++) {
       mbar_init(sm.x_full[s], 1);
       mbar_init(sm.sc_full[s], 1);
-      mbar_init(sm.xp_ready[s], 4);
-      mbar_init(sm.c_ready[s], 4);
+      mbar_init(sm.xp_ready[s], WPS);
+      mbar_init(sm.c_ready[s], WPS);
       mbar_init(sm.acc_full[s], 1);
     }
     fence_barrier_init();
@@ -504,7 +532,7 @@ trunk_kernel(const TrunkArgs a, const __grid_constant__ CUtensorMap tm_x,
   if (warp == 0) {
     mma_role<C>(a, sm, tmem_base, n_items, &tm_w1, &tm_w2, &tm_w3, lane);
   } else {
-    const int slot = (warp - 1) >> 2;
+    const int slot = (warp - 1) / WPS;
     const int nprelu = p.has_prelu_out2 ? 2 : (p.has_prelu_out ? 1 : 0);
     if (nprelu == 0)
       slot_role<C, HAS_SC, 0>(a, sm, tmem_base, slot, n_items, &tm_x, &tm_sc, warp, lane);
