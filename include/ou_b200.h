@@ -227,6 +227,25 @@ int ou_unpack_blocked(const void* src, float* dst, int batch, int channels, int 
 int ou_film_f32(const float* x, const float* y, float* out, int batch, int channels, int t,
                 void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * AliasFreeSnake (networks/bigvgan/snake.py:127-157, alias_free_act.py:8-30) and, fused behind it,
+ * the k-tap 'same' convolution to ONE channel of UniverseGAN.signal_decoupling_layer
+ * (universe_gan.py:117-126; PReLU_Conv.forward with act_type snake / snakebeta, blocks.py:205-227):
+ * the `aux_to_wav` step of enhance(use_aux_signal=True / warm_start=n) (universe.py:317-331).
+ *   x            activations, bf16 blocked [B][C/CB][T][CB] (x_blocked != 0) or fp32 [B][C][T]
+ *   alpha, beta  fp32 [C] Snake parameters (beta NULL = Snake, else SnakeBeta); exp() applied when
+ *                logscale != 0 (snake.py:52-62, 116-124)
+ *   up_kernel    fp32 [2][up_len]   torchaudio Resample(1 -> 2) `kernel` buffer (up_len odd)
+ *   down_kernel  fp32 [down_len]    torchaudio Resample(2 -> 1) `kernel` buffer (down_len even)
+ *   w, bias, k   fp32 [C][k] conv weights (weight norm already folded), scalar bias, odd k; w NULL =
+ *                activation only
+ *   out          fp32 [B][T] (w != NULL) or fp32 [B][C][T] (w == NULL)
+ * ------------------------------------------------------------------------------------------ */
+int ou_alias_free_snake(const void* x, int x_blocked, const float* alpha, const float* beta,
+                        int logscale, const float* up_kernel, int up_len, const float* down_kernel,
+                        int down_len, const float* w, float bias, int k, float* out, int batch,
+                        int channels, int t, void* stream);
+
 /* Debug hook: when set to a device buffer of 4*64*4 int64, CTA 0 of the tcgen05 conv kernel stamps
  * clock64() per warp role / tile / event into it (tools/trace_conv.py).  NULL disables. */
 int ou_debug_set_trace(void* device_buffer);

@@ -13,7 +13,7 @@ from pathlib import Path
 
 CSRC = Path(__file__).resolve().parent / "csrc"
 LIB = CSRC / "libou_b200.so"
-SOURCES = ["api.cu", "conv.cu", "conv_tc.cu", "conv_trunk.cu", "gru.cu", "signal.cu", "mel.cu"]
+SOURCES = ["api.cu", "conv.cu", "conv_tc.cu", "conv_trunk.cu", "gru.cu", "signal.cu", "mel.cu", "snake.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 

@@ -75,6 +75,9 @@ SIGNATURES = {
     "ou_pack_blocked": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "ou_unpack_blocked": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "ou_film_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "ou_alias_free_snake": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int,
+                                    c_void_p, c_int, c_void_p, c_float, c_int, c_void_p, c_int,
+                                    c_int, c_int, c_void_p]),
     "ou_debug_set_trace": (c_int, [c_void_p]),
 }
 

@@ -423,8 +423,8 @@ class SamplerLoop:
     ~2 200 ctypes calls.  Noise is still drawn by ``torch.randn`` in the reference's call order
     (a5 of SURVEY section 8), just before the replay instead of inside the loop."""
 
-    def __init__(self, sr, n_steps):
-        self.sr, self.n_steps = sr, n_steps
+    def __init__(self, sr, n_steps, n_start=0):
+        self.sr, self.n_steps, self.n_start = sr, n_steps, n_start
         dev, B, T = sr.device, sr.batch, sr.t
         self.x = torch.empty(B, 1, T, dtype=torch.float32, device=dev)
         self.noise = torch.empty(max(n_steps - 1, 1), B, 1, T, dtype=torch.float32, device=dev)
@@ -434,7 +434,7 @@ class SamplerLoop:
 
     def _loop(self):
         sr, N = self.sr, self.n_steps
-        for n in range(N):
+        for n in range(self.n_start, N):   # warm start skips the first steps (universe.py:326-334)
             sr.step(self.x, n, False, in_scale=self.in_scale[n], coef=self.coef[n],
                     noise=self.noise[n] if n < N - 1 else None, xout=self.x)
 
@@ -465,15 +465,15 @@ class SamplerLoop:
             self._loop()
 
 
-def get_sampler_loop(sr, n_steps):
+def get_sampler_loop(sr, n_steps, n_start=0):
     """Cached SamplerLoop of a ScoreRunner; captured as a CUDA graph unless disabled, profiled
     (bench.py's per-launch events) or too large."""
     loops = sr.__dict__.setdefault("_loops", {})
     want_graph = (USE_GRAPH and PROFILE is None and
                   (n_steps - 1) * sr.batch * sr.t * 4 <= GRAPH_NOISE_LIMIT)
-    key = (n_steps, want_graph)
+    key = (n_steps, n_start, want_graph)
     if key not in loops:
-        loop = SamplerLoop(sr, n_steps)
+        loop = SamplerLoop(sr, n_steps, n_start)
         if want_graph:
             if sr.film is None or sr.film.shape[0] < n_steps:
                 raise RuntimeError("set_sigmas() must run before the sampler loop is captured")
@@ -615,9 +615,61 @@ class _FilmPassthrough:
         self.c = c
 
 
-def prelu_conv_forward(pc, x):
+def alias_free_snake(mod, x, conv=None, blocked=False, t=None):
+    """AliasFreeSnake.forward (bigvgan/snake.py:127-157), optionally fused with the k-tap conv to one
+    channel behind it (``conv``: a Conv1d with out_channels == 1, 'same' padding).
+    x: (B, C, T) fp32, or a blocked bf16 activation buffer when ``blocked``.
+    Returns (B, C, T) fp32 without ``conv``, (B, 1, T) fp32 with it."""
+    require_cuda(x)
+    act = mod.act
+    if act.up_ratio != 2 or act.down_ratio != 2:
+        raise NotImplementedError("AliasFreeSnake kernel covers the x2 / :2 configuration upstream uses")
+    snake = act.act
+    if blocked:
+        b, nblk, tt, cb = x.shape
+        c = nblk * cb
+    else:
+        b, c, tt = x.shape
+        x = x.contiguous().float()
+    if t is not None and t != tt:
+        raise ValueError(f"expected length {t}, got {tt}")
+    dev = x.device
+    alpha = snake.alpha.detach().float().to(dev).contiguous()
+    beta = snake.beta.detach().float().to(dev).contiguous() if hasattr(snake, "beta") else None
+    ku = act.upsample.kernel.detach().float().to(dev).contiguous()      # (2, 1, up_len)
+    kd = act.downsample.kernel.detach().float().to(dev).contiguous()    # (1, 1, down_len)
+    if ku.shape[0] != 2 or kd.shape[0] != 1:
+        raise ValueError("unexpected resampling kernel shapes")
+    w = bias = None
+    k = 1
+    if conv is not None:
+        if conv.out_channels != 1 or conv.in_channels != c:
+            raise ValueError("the fused conv must map all channels to one")
+        w = fold.effective_weight(conv)[0].float().to(dev).contiguous()   # (C, k)
+        k = w.shape[1]
+        bias = float(conv.bias.detach()[0].item()) if conv.bias is not None else 0.0
+        out = torch.empty(b, 1, tt, dtype=torch.float32, device=dev)
+    else:
+        out = torch.empty(b, c, tt, dtype=torch.float32, device=dev)
+    lib.check(lib.load().ou_alias_free_snake(
+        _ptr(x), 1 if blocked else 0, _ptr(alpha), _ptr(beta), 1 if snake.alpha_logscale else 0,
+        _ptr(ku), ku.shape[-1], _ptr(kd), kd.shape[-1], _ptr(w), bias or 0.0, k, _ptr(out), b, c, tt,
+        _stream()))
+    return out
+
+
+def prelu_conv_forward(pc, x, blocked=False):
     """PReLU_Conv.forward on a (B, C, T) fp32 tensor (blocks.py:205-227)."""
     require_cuda(x)
+    if pc.act_type in ("snake", "snakebeta"):
+        # only instance upstream: UniverseGAN.signal_decoupling_layer (universe_gan.py:117-126)
+        if (pc.out_channels != 1 or pc.stride != 1 or pc.padding != "same" or pc.use_transpose
+                or pc.antialiasing):
+            raise NotImplementedError("snake-activated PReLU_Conv is only built as the signal "
+                                      "decoupling layer (C -> 1, 'same')")
+        return alias_free_snake(pc.prelu, x, conv=pc.conv, blocked=blocked)
+    if blocked:
+        raise NotImplementedError("blocked input is only accepted by the signal decoupling layer")
     if pc.act_type != "prelu":
         raise NotImplementedError("only act_type='prelu' has a kernel")
     b, c, t = x.shape

@@ -3,10 +3,10 @@
 Upstream this package holds the BigVGAN discriminators / GAN losses (training only, out of
 scope -- SURVEY.md section 2 #10) and the Snake activations.  Only ``AliasFreeSnake`` can be
 reached from ``enhance()``, through ``UniverseGAN.signal_decoupling_layer`` when
-``use_aux_signal`` / ``warm_start`` is requested (universe.py:317-331).  It is kept here as a
-parameter container with the reference's ``state_dict`` keys (``act.act.alpha``,
-``act.upsample.kernel``, ``act.downsample.kernel``) so that checkpoints load strictly; its
-device kernel is a SURVEY section 8(f) "next" row and not built yet.
+``use_aux_signal`` / ``warm_start`` is requested (universe.py:317-331).  The modules keep the
+reference's ``state_dict`` keys (``act.act.alpha``, ``act.upsample.kernel``,
+``act.downsample.kernel``); the arithmetic is one CUDA kernel (``csrc/snake.cu``,
+``ou_alias_free_snake``) which reads the resampling taps from those buffers.
 """
 import torch
 import torchaudio
@@ -48,6 +48,5 @@ class AliasFreeSnake(torch.nn.Module):
                                     alpha_logscale=alpha_logscale))
 
     def forward(self, x):
-        raise NotImplementedError(
-            "AliasFreeSnake (warm_start / use_aux_signal path) has no CUDA kernel yet -- "
-            "SURVEY.md section 8(f) item 3")
+        from ...engine import runtime
+        return runtime.alias_free_snake(self, x)

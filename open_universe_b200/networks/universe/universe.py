@@ -121,6 +121,10 @@ class Universe(torch.nn.Module):
     def aux_to_wav(self, y_aux):
         return y_aux
 
+    def _aux_to_wav_blocked(self, y_blocked):
+        """The conditioner's signal estimate (blocked bf16) -> (B, C, T) fp32 waveform(s)."""
+        return self.aux_to_wav(runtime.unpack_blocked(y_blocked))
+
     def get_std_dev(self, time):
         if self.diff_kwargs.schedule == "geometric":
             s_min = self.diff_kwargs.sigma_min
@@ -220,11 +224,12 @@ class Universe(torch.nn.Module):
         if target is not None or fake_score_snr is not None:
             raise NotImplementedError("oracle-score debugging (target / fake_score_snr, "
                                       "universe.py:276-296) is not part of the accelerated path")
-        if use_aux_signal or warm_start is not None:
-            raise NotImplementedError("warm_start / use_aux_signal need the AliasFreeSnake kernel "
-                                      "(SURVEY.md section 8(f) item 3)")
         if n_steps < 2:
             raise ValueError("n_steps must be at least 2")
+        if warm_start is not None and not 0 <= warm_start < n_steps:
+            raise ValueError("warm_start must be a step index in [0, n_steps)")
+        if ensemble is not None and ensemble_stat not in ("mean", "median", "signal_median"):
+            raise NotImplementedError()
 
         x_ndim = mix.ndim
         if x_ndim == 1:
@@ -264,22 +269,38 @@ class Universe(torch.nn.Module):
             coef_b = coef[:, None, :].expand(n_steps, B, 3).contiguous()
 
             # conditioning: once per call (universe.py:314-316)
-            cr = runtime.get_conditioner_runner(self.condition_model, B, t_pad, dev, False)
-            cond, _, _ = cr.run(mixn, mixn)
-            sr = runtime.get_score_runner(self.get_score_model(), B, t_pad, dev)
-            sr.set_sigmas(net_sigma)
-            sr.set_cond(cond)
-
-            # the N-step loop (universe.py:334-343) replays a CUDA graph over persistent buffers;
-            # noise is drawn with torch.randn in the reference's order, one call per step
-            loop = runtime.get_sampler_loop(sr, n_steps)
-            loop.in_scale.copy_(in_scale_b)
-            loop.coef.copy_(coef_b)
-            loop.x.copy_(randn(mixn, sigma_b[:, 0], rng=rng))
-            for n in range(n_steps - 1):
-                loop.noise[n].copy_(randn(loop.x, sigma_b[:, n + 1], rng=rng))
-            loop.run()
-            x = loop.x
+            need_aux = bool(use_aux_signal) or warm_start is not None
+            cr = runtime.get_conditioner_runner(self.condition_model, B, t_pad, dev, need_aux)
+            cond, aux_signal, _ = cr.run(mixn, mixn)
+            sig = None
+            if need_aux:
+                # the conditioner's signal estimate -> waveform (universe.py:317-319, 328)
+                sig = self._aux_to_wav_blocked(aux_signal)
+                if sig.shape != (B, 1, t_pad):
+                    raise ValueError("aux_to_wav must return one waveform per clip, got "
+                                     f"{tuple(sig.shape)}")
+            if use_aux_signal:
+                x = sig
+            else:
+                sr = runtime.get_score_runner(self.get_score_model(), B, t_pad, dev)
+                sr.set_sigmas(net_sigma)
+                sr.set_cond(cond)
+                # the N-step loop (universe.py:334-343) replays a CUDA graph over persistent
+                # buffers; noise is drawn with torch.randn in the reference's order, one call per
+                # step.  warm_start = n0 starts from the signal estimate at noise level sigma[n0]
+                # (universe.py:326-331)
+                n_start = 0 if warm_start is None else int(warm_start)
+                loop = runtime.get_sampler_loop(sr, n_steps, n_start)
+                loop.in_scale.copy_(in_scale_b)
+                loop.coef.copy_(coef_b)
+                if warm_start is None:
+                    loop.x.copy_(randn(mixn, sigma_b[:, 0], rng=rng))
+                else:
+                    loop.x.copy_(sig + randn(sig, sigma_b[:, n_start], rng=rng))
+                for n in range(n_start, n_steps - 1):
+                    loop.noise[n].copy_(randn(loop.x, sigma_b[:, n + 1], rng=rng))
+                loop.run()
+                x = loop.x
 
             # unpad, keep_rms, peak limiter (universe.py:346-357)
             out = torch.empty(B, 1, mix_len, dtype=torch.float32, device=dev)
@@ -293,6 +314,8 @@ class Universe(torch.nn.Module):
                 x = x.mean(dim=0)
             elif ensemble_stat == "median":
                 x = x.median(dim=0).values
+            elif ensemble_stat == "signal_median":
+                x = utils.signal_median(x)
             else:
                 raise NotImplementedError()
         if x_ndim == 1:

@@ -44,3 +44,10 @@ class UniverseGAN(Universe):
         if self.signal_decoupling_layer is not None:
             return self.signal_decoupling_layer(y_aux)
         return y_aux
+
+    def _aux_to_wav_blocked(self, y_blocked):
+        """enhance()-internal: the conditioner's signal output still in the blocked bf16 layout."""
+        from ...engine import runtime
+        if self.signal_decoupling_layer is not None:
+            return runtime.prelu_conv_forward(self.signal_decoupling_layer, y_blocked, blocked=True)
+        return super()._aux_to_wav_blocked(y_blocked)

@@ -325,6 +325,65 @@ def conditioner_network(cfg_cond, sd, p, x, x_wav=None):
     return conditions, y, h
 
 
+# ----------------------------------------------------------------------------- aux signal path
+def sinc_resample(x, kernel, orig, new):
+    """torchaudio.functional._apply_sinc_resample_kernel (torchaudio 2.x, third-party: not under
+    /root/reference; call sites networks/bigvgan/alias_free_act.py:21-22,26-28) with the kernel
+    taken from the module's ``kernel`` buffer, shape (new, 1, 2*width + orig):
+    pad (width, width + orig) -> conv1d stride ``orig`` -> interleave the ``new`` phases ->
+    crop to ceil(new * L / orig)."""
+    b, c, length = x.shape
+    width = (kernel.shape[-1] - orig) // 2
+    y = F.pad(x.reshape(b * c, 1, length), (width, width + orig))
+    y = F.conv1d(y, kernel.to(x), stride=orig)                # (b*c, new, frames)
+    y = y.transpose(1, 2).reshape(b * c, -1)
+    target = -(-new * length // orig)
+    return y[:, :target].reshape(b, c, target)
+
+
+def alias_free_snake(sd, p, x, beta=False):
+    """networks/bigvgan/snake.py:127-157 + alias_free_act.py:25-30: x2 sinc up-sampling ->
+    Snake with log-scale alpha (snake.py:52-62; SnakeBeta :116-124) -> /2 down-sampling."""
+    x = sinc_resample(x, sd[p + ".act.upsample.kernel"], 1, 2)
+    alpha = torch.exp(sd[p + ".act.act.alpha"])[None, :, None]
+    mag = torch.exp(sd[p + ".act.act.beta"])[None, :, None] if beta else alpha
+    x = x + (1.0 / (mag + 0.000000001)) * torch.sin(x * alpha) ** 2
+    return sinc_resample(x, sd[p + ".act.downsample.kernel"], 2, 1)
+
+
+def aux_to_wav(cfg, sd, y_aux):
+    """universe_gan.py:117-126,145-149: PReLU_Conv(n_channels -> 1, k=3, 'same') whose activation
+    is ``losses.signal_decoupling_act`` (snake in every shipped UNIVERSE++ config); identity for
+    the original UNIVERSE class (universe.py has no decoupling layer)."""
+    p = "signal_decoupling_layer"
+    if (p + ".conv.weight") not in sd and (p + ".conv.weight_v") not in sd:
+        return y_aux
+    act = (cfg.get("losses") or {}).get("signal_decoupling_act", None)
+    if act in ("snake", "snakebeta"):
+        y_aux = alias_free_snake(sd, p + ".prelu", y_aux, beta=act == "snakebeta")
+    elif act == "prelu":
+        y_aux = F.prelu(y_aux, sd[p + ".prelu.weight"])
+    elif act != "none":
+        raise ValueError("'act_type' should be one of [prelu | snake]")
+    return F.conv1d(y_aux, eff_weight(sd, p + ".conv"), sd.get(p + ".conv.bias"), padding="same")
+
+
+def signal_median(signal):
+    """utils/stats.py:22-66: pick, per batch row, the ensemble member that is the sample-wise
+    median most often.  signal: (ensemble, batch, ...) -> (batch, ...)."""
+    shape = signal.shape
+    flat = signal.flatten(start_dim=2)
+    n = flat.shape[0]
+    _, order = flat.sort(dim=0)
+    # rank position closest to n/2 holds the member that is "the median" of that sample; torch's
+    # min() returns the first minimum, as upstream
+    _, pos = (order - n / 2).abs().min(dim=0)                  # (batch, samples)
+    counts = torch.stack([(pos == i).sum(dim=1) for i in range(n)], dim=1)
+    select = counts.argmax(dim=1)
+    out = torch.stack([flat[select[i], i] for i in range(flat.shape[1])], dim=0)
+    return out.reshape(shape[1:])
+
+
 # ----------------------------------------------------------------------------- enhance()
 class UniverseOracle:
     """Functional stand-in for ``Universe`` / ``UniverseGAN`` inference (universe.py:231-375)."""
@@ -390,10 +449,14 @@ class UniverseOracle:
         time = torch.linspace(0, 1, n_steps).type_as(like).flip(dims=[0])
         return float(d["sigma_min"]) * (float(d["sigma_max"]) / float(d["sigma_min"])) ** time
 
-    def enhance(self, mix, n_steps=None, epsilon=None, noise=None, rng=None, keep_rms=False):
-        """universe.py:231-375, default path (target=None, no ensemble, no warm start).
-        ``noise``: optional list of N unit-variance (B,1,T_pad) tensors used in draw order
-        instead of torch.randn (universe.py:39-41)."""
+    def aux_to_wav(self, y_aux):
+        return aux_to_wav(self.cfg, self.sd, y_aux)
+
+    def enhance(self, mix, n_steps=None, epsilon=None, noise=None, rng=None, keep_rms=False,
+                use_aux_signal=False, ensemble=None, ensemble_stat="median", warm_start=None):
+        """universe.py:231-375 with target=None (the oracle-score debugging hooks :276-296 are not
+        restated).  ``noise``: optional list of unit-variance (B,1,T_pad) tensors used in draw
+        order instead of torch.randn (universe.py:39-41)."""
         d = self.cfg["diffusion"]
         epsilon = d["epsilon"] if epsilon is None else epsilon
         n_steps = d["n_steps"] if n_steps is None else n_steps
@@ -405,6 +468,9 @@ class UniverseOracle:
         elif x_ndim > 3:
             raise ValueError("The input should have at most 3 dimensions")
         mix_rms = mix.square().mean(dim=(-2, -1), keepdim=True).sqrt()
+        if ensemble is not None:
+            mix_shape = mix.shape
+            mix = torch.stack([mix] * ensemble, dim=0).view((-1,) + mix_shape[1:])
         mix_len = mix.shape[-1]
         mix, pad = self.pad(mix)
         mix = self.normalize(mix)
@@ -423,15 +489,23 @@ class UniverseOracle:
         beta = math.sqrt(1 - gamma ** (2 * (epsilon - 1.0)))
         sigma = self.sigmas(n_steps, mix)
         sigma = sigma[None, :].expand(mix.shape[0], -1)
-        cond, _, _ = self.condition(mix, x_wav=mix)
-        x = randn(sigma[:, 0])
-        for n in range(n_steps - 1):
-            s_now, s_next = sigma[:, n], sigma[:, n + 1]
-            score = self.score(x, s_now, cond)
-            z = randn(s_next)
-            x = x + s_now[:, None, None] ** 2 * eta * score + beta * z
-        score = self.score(x, sigma[:, -1], cond)
-        x = x + sigma[:, -1, None, None] ** 2 * score
+        cond, aux_signal, _ = self.condition(mix, x_wav=mix)
+        if use_aux_signal:
+            x = self.aux_to_wav(aux_signal)
+        else:
+            if warm_start is None:
+                x = randn(sigma[:, 0])
+                n_start = 0
+            else:
+                x = self.aux_to_wav(aux_signal) + randn(sigma[:, warm_start])
+                n_start = warm_start
+            for n in range(n_start, n_steps - 1):
+                s_now, s_next = sigma[:, n], sigma[:, n + 1]
+                score = self.score(x, s_now, cond)
+                z = randn(s_next)
+                x = x + s_now[:, None, None] ** 2 * eta * score + beta * z
+            score = self.score(x, sigma[:, -1], cond)
+            x = x + sigma[:, -1, None, None] ** 2 * score
         x = self.unpad(x, pad)
         x = F.pad(x, (0, mix_len - x.shape[-1]))
         if keep_rms:
@@ -439,6 +513,16 @@ class UniverseOracle:
             x = x * (mix_rms / x_rms)
         scale = abs(x).max(dim=-1, keepdim=True).values
         x = torch.where(scale > 1.0, x / scale, x)
+        if ensemble is not None:
+            x = x.view((-1,) + mix_shape)
+            if ensemble_stat == "mean":
+                x = x.mean(dim=0)
+            elif ensemble_stat == "median":
+                x = x.median(dim=0).values
+            elif ensemble_stat == "signal_median":
+                x = signal_median(x)
+            else:
+                raise NotImplementedError()
         if x_ndim == 1:
             x = x[0, 0]
         elif x_ndim == 2:

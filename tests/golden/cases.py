@@ -21,6 +21,18 @@ ENHANCE_CASES = [
          kwargs={"keep_rms": True}),
     dict(name="upp16k_eps", model="upp16k", shape=(1, 4000), n_steps=5, seed=16,
          kwargs={"epsilon": 2.0}),
+    # aux-signal / warm-start path (universe.py:317-331, universe_gan.py:117-126,145-149: AliasFreeSnake)
+    dict(name="upp16k_aux", model="upp16k", shape=(2, 3000), n_steps=2, seed=17,
+         kwargs={"use_aux_signal": True}),
+    dict(name="upp16k_warm", model="upp16k", shape=(1, 4000), n_steps=5, seed=18,
+         kwargs={"warm_start": 2}),
+    # ensembles (universe.py:261-264, 359-368; utils/stats.py:22-66)
+    dict(name="upp16k_ens_median", model="upp16k", shape=(2, 2000), n_steps=2, seed=19,
+         kwargs={"ensemble": 3, "ensemble_stat": "median"}),
+    dict(name="upp16k_ens_sigmed", model="upp16k", shape=(2, 2000), n_steps=2, seed=19,
+         kwargs={"ensemble": 3, "ensemble_stat": "signal_median"}),
+    dict(name="upp16k_ens_mean", model="upp16k", shape=(1, 2000), n_steps=2, seed=20,
+         kwargs={"ensemble": 2, "ensemble_stat": "mean"}),
     dict(name="orig16k_short", model="orig16k", shape=(1, 6000), n_steps=3, seed=21, kwargs={}),
     dict(name="upp24k_short", model="upp24k", shape=(1, 7000), n_steps=3, seed=31, kwargs={}),
 ]
@@ -33,3 +45,10 @@ NET_CASES = [
     dict(name="orig16k_net_odd", model="orig16k", B=1, T=3001, seed=43, sigmas=[1.1]),
     dict(name="upp24k_net_odd", model="upp24k", B=1, T=4001, seed=44, sigmas=[0.5]),
 ]
+
+
+def noise_rows(case):
+    """Rows of the diffusion-noise tensors of an enhance case: batch x ensemble."""
+    shape = tuple(case["shape"])
+    b = 1 if len(shape) == 1 else shape[0]
+    return b * (case["kwargs"].get("ensemble") or 1)

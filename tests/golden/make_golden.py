@@ -21,7 +21,7 @@ HERE = Path(__file__).resolve().parent
 sys.path.insert(0, str(HERE))
 
 import ref_shim  # noqa: E402
-from cases import ENHANCE_CASES, MODELS, NET_CASES, WEIGHT_SEED  # noqa: E402
+from cases import ENHANCE_CASES, MODELS, NET_CASES, WEIGHT_SEED, noise_rows  # noqa: E402
 from detweights import (det_audio, det_noise, det_state_dict,  # noqa: E402
                         is_constructor_buffer, subsample)
 
@@ -73,7 +73,7 @@ def run_enhance_case(case):
     model, _ = get_model(case["model"])
     shape = tuple(case["shape"])
     mix = det_audio(shape, case["seed"])
-    b = 1 if len(shape) == 1 else shape[0]
+    b = noise_rows(case)
     t = shape[-1]
     t_pad = t + (model.tot_ds - t % model.tot_ds)
     noise = det_noise(case["n_steps"], (b, 1, t_pad), case["seed"])

@@ -307,3 +307,34 @@ def test_cpu_tensors_raise():
     from open_universe_b200.config import builtin_config, instantiate
     with pytest.raises(R.NoCudaPathError):
         R.pack_blocked(torch.zeros(1, 8, 4))
+
+
+@pytest.mark.parametrize("C,B,T,beta", [(32, 2, 1000, False), (48, 1, 333, True), (16, 3, 64, False),
+                                        (32, 1, 7, False)])
+def test_alias_free_snake_and_decoupling_conv(C, B, T, beta):
+    """ou_alias_free_snake against the oracle restatement of bigvgan.AliasFreeSnake and of
+    UniverseGAN.signal_decoupling_layer (fp32 in, fp32 out: tight tolerance), plus the blocked
+    bf16 input flavour enhance() uses."""
+    from open_universe_b200.networks.universe.blocks import PReLU_Conv
+    torch.manual_seed(5)
+    pc = PReLU_Conv(C, 1, kernel_size=3, padding="same", act_type="snakebeta" if beta else "snake")
+    with torch.no_grad():
+        pc.prelu.act.act.alpha.copy_(0.3 * torch.randn(C))
+        if beta:
+            pc.prelu.act.act.beta.copy_(0.3 * torch.randn(C))
+    sd = {"p." + k: v.detach() for k, v in pc.state_dict().items()}
+    x = torch.randn(B, C, T)
+    want_act = O.alias_free_snake(sd, "p.prelu", x, beta=beta)
+    cfg = {"losses": {"signal_decoupling_act": "snakebeta" if beta else "snake"}}
+    sd2 = {k.replace("p.", "signal_decoupling_layer."): v for k, v in sd.items()}
+    want_wav = O.aux_to_wav(cfg, sd2, x)
+    pc = pc.to(DEV)
+    got_act = pc.prelu(x.to(DEV)).cpu()
+    got_wav = pc(x.to(DEV)).cpu()
+    assert got_act.shape == want_act.shape and got_wav.shape == want_wav.shape == (B, 1, T)
+    assert rel_rms(got_act, want_act) < 2e-5
+    assert rel_rms(got_wav, want_wav) < 2e-5
+    xb = bf(x)
+    want_b = O.aux_to_wav(cfg, sd2, xb)
+    got_b = R.prelu_conv_forward(pc, R.pack_blocked(xb.to(DEV)), blocked=True).cpu()
+    assert rel_rms(got_b, want_b) < 2e-5

@@ -14,7 +14,7 @@ fp32 FiLM / GRU state / EDM + SDE update.  Two weight sets:
 import pytest
 import torch
 
-from cases import ENHANCE_CASES, NET_CASES
+from cases import ENHANCE_CASES, NET_CASES, noise_rows
 from common import (OUR_CONFIG, abs_rms, det_audio, det_noise, full_state_dict, load_golden,
                     make_oracle, rel_rms, sub)
 
@@ -94,8 +94,7 @@ def test_enhance_vs_reference_golden(case, monkeypatch):
     m = our_model(case["model"])
     shape = tuple(case["shape"])
     mix = det_audio(shape, case["seed"])
-    b = 1 if len(shape) == 1 else shape[0]
-    noise = det_noise(case["n_steps"], (b, 1, int(g["t_pad"])), case["seed"])
+    noise = det_noise(case["n_steps"], (noise_rows(case), 1, int(g["t_pad"])), case["seed"])
     inject_noise(monkeypatch, noise)
     y = m.enhance(mix.to(DEV), n_steps=case["n_steps"], **case["kwargs"]).cpu()
     assert y.shape == mix.shape == g["y"].shape

@@ -162,8 +162,23 @@ def test_no_cpu_fallback():
         m.get_score_model()(x, torch.ones(1), [x])
     with pytest.raises(ValueError):
         m.enhance(torch.zeros(1, 1, 1, 320))
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(runtime.NoCudaPathError):
         m.enhance(torch.zeros(1, 320), warm_start=2)
+    with pytest.raises(ValueError):
+        m.enhance(torch.zeros(1, 320), n_steps=4, warm_start=4)
+    with pytest.raises(NotImplementedError):      # oracle-score debugging hooks are not accelerated
+        m.enhance(torch.zeros(1, 320), target=torch.zeros(1, 320))
+    with pytest.raises(NotImplementedError):      # universe.py:368
+        m.enhance(torch.zeros(1, 320), ensemble=2, ensemble_stat="mode")
+
+
+def test_signal_median_matches_oracle():
+    from open_universe_b200.utils import signal_median
+    from oracle.universe_oracle import signal_median as want
+    g = torch.Generator().manual_seed(3)
+    for e, b, s in [(3, 2, 50), (4, 3, 101), (5, 1, 7), (2, 2, 9)]:
+        x = torch.randn(e, b, 1, s, generator=g)
+        assert torch.equal(signal_median(x), want(x))
 
 
 def test_film_channel_check():

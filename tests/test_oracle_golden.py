@@ -3,7 +3,7 @@
 import pytest
 import torch
 
-from cases import ENHANCE_CASES, NET_CASES
+from cases import ENHANCE_CASES, NET_CASES, noise_rows
 from common import (abs_rms, det_audio, det_noise, golden_buffers, load_golden, make_oracle,
                     model_cfg, rel_rms, sub)
 
@@ -40,8 +40,7 @@ def test_enhance_matches_reference(case):
     o = make_oracle(case["model"])
     shape = tuple(case["shape"])
     mix = det_audio(shape, case["seed"])
-    b = 1 if len(shape) == 1 else shape[0]
-    noise = det_noise(case["n_steps"], (b, 1, int(g["t_pad"])), case["seed"])
+    noise = det_noise(case["n_steps"], (noise_rows(case), 1, int(g["t_pad"])), case["seed"])
     with torch.no_grad():
         y = o.enhance(mix, n_steps=case["n_steps"], noise=noise, **case["kwargs"])
     assert y.shape == mix.shape == g["y"].shape
