@@ -5,67 +5,75 @@
 namespace ou {
 
 // ------------------------------------------------------------------------------ input conv
-// One thread per time step: reads k input samples, writes cout channels as 16-byte vectors.
-__global__ void input_conv_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                  const float* __restrict__ bias, const float* __restrict__ in_scale,
-                                  __nv_bfloat16* __restrict__ out, int t_len, int cout, int k) {
-  extern __shared__ float sw[];  // [cout][k] weights then [cout] bias
-  for (int i = threadIdx.x; i < cout * k; i += blockDim.x) sw[i] = w[i];
-  for (int i = threadIdx.x; i < cout; i += blockDim.x) sw[cout * k + i] = bias ? bias[i] : 0.f;
+// One thread per time step: reads k input samples, writes cout channels as 32-byte vectors.  The
+// weights sit in shared memory tap-major ([k][cout], then the bias) so that a 16-byte broadcast load
+// feeds four FMAs: with one 4-byte load per FMA the kernel was bound by shared-memory instruction
+// issue (96 loads per thread at C = 32), not by its 262 MB of output.
+template <int K>
+__global__ void __launch_bounds__(256) input_conv_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                         const float* __restrict__ bias,
+                                                         const float* __restrict__ in_scale,
+                                                         __nv_bfloat16* __restrict__ out, int t_len, int cout) {
+  extern __shared__ __align__(16) float sw[];  // [K][cout] weights then [cout] bias
+  for (int i = threadIdx.x; i < cout * K; i += blockDim.x) sw[(i % K) * cout + i / K] = w[i];
+  for (int i = threadIdx.x; i < cout; i += blockDim.x) sw[cout * K + i] = bias ? bias[i] : 0.f;
   __syncthreads();
   const int b = blockIdx.y;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= t_len) return;
   const float sc = in_scale ? in_scale[b] : 1.f;
-  float xin[8];
-  const int half = k / 2;
-  for (int i = 0; i < k; i++) {
-    const int tt = t + i - half;
-    xin[i] = (tt >= 0 && tt < t_len) ? x[(size_t)b * t_len + tt] * sc : 0.f;
+  float xin[K];
+#pragma unroll
+  for (int i = 0; i < K; i++) {
+    const int tt = t + i - K / 2;
+    xin[i] = (tt >= 0 && tt < t_len) ? __ldg(x + (size_t)b * t_len + tt) * sc : 0.f;
   }
-  const float* sb = sw + cout * k;
   const int cb = cl_cb(cout);
   for (int c16 = 0; c16 < cout / 16; c16++) {   // 16 channels = one 32-byte (256-bit) store
-    uint32_t v[8];
+    float4 acc[4];
 #pragma unroll
-    for (int h = 0; h < 8; h++) {
-      float o[2];
+    for (int q = 0; q < 4; q++) acc[q] = *reinterpret_cast<const float4*>(sw + cout * K + c16 * 16 + q * 4);
 #pragma unroll
-      for (int e = 0; e < 2; e++) {
-        const int co = c16 * 16 + h * 2 + e;
-        float acc = sb[co];
-        for (int i = 0; i < k; i++) acc = fmaf(sw[co * k + i], xin[i], acc);
-        o[e] = acc;
+    for (int i = 0; i < K; i++) {
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const float4 wv = *reinterpret_cast<const float4*>(sw + i * cout + c16 * 16 + q * 4);
+        acc[q].x = fmaf(wv.x, xin[i], acc[q].x), acc[q].y = fmaf(wv.y, xin[i], acc[q].y);
+        acc[q].z = fmaf(wv.z, xin[i], acc[q].z), acc[q].w = fmaf(wv.w, xin[i], acc[q].w);
       }
-      v[h] = f2_to_bf2(o[0], o[1]);
     }
     __nv_bfloat16* dst = out + cl_off(b, c16 * 16, t, cout, t_len, cb);
-    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "r"(v[0]), "r"(v[1]),
-                 "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "r"(f2_to_bf2(acc[0].x, acc[0].y)),
+                 "r"(f2_to_bf2(acc[0].z, acc[0].w)), "r"(f2_to_bf2(acc[1].x, acc[1].y)),
+                 "r"(f2_to_bf2(acc[1].z, acc[1].w)), "r"(f2_to_bf2(acc[2].x, acc[2].y)),
+                 "r"(f2_to_bf2(acc[2].z, acc[2].w)), "r"(f2_to_bf2(acc[3].x, acc[3].y)),
+                 "r"(f2_to_bf2(acc[3].z, acc[3].w))
                  : "memory");
   }
 }
 
 // ------------------------------------------------------------------------------ output conv + SDE
-__global__ void output_sde_kernel(const __nv_bfloat16* __restrict__ src, const float* __restrict__ w,
-                                  float bias, const float* __restrict__ coef,
-                                  const float* __restrict__ x, const float* __restrict__ noise,
-                                  float* __restrict__ xout, float* __restrict__ net_out, int cin,
-                                  int k, int t_src, int t_sig) {
-  extern __shared__ float sw[];  // [cin][k]
-  for (int i = threadIdx.x; i < cin * k; i += blockDim.x) sw[i] = w[i];
+template <int K>
+__global__ void __launch_bounds__(256) output_sde_kernel(const __nv_bfloat16* __restrict__ src,
+                                                         const float* __restrict__ w, float bias,
+                                                         const float* __restrict__ coef,
+                                                         const float* __restrict__ x,
+                                                         const float* __restrict__ noise, float* __restrict__ xout,
+                                                         float* __restrict__ net_out, int cin, int t_src, int t_sig) {
+  extern __shared__ __align__(16) float sw[];  // [K][cin], tap-major (see input_conv_kernel)
+  for (int i = threadIdx.x; i < cin * K; i += blockDim.x) sw[(i % K) * cin + i / K] = w[i];
   __syncthreads();
   const int b = blockIdx.y;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= t_sig) return;
   float net = 0.f;
   if (t < t_src) {
-    net = bias;
-    const int half = k / 2;
     const int cb = cl_cb(cin);
+    float4 acc = make_float4(bias, 0.f, 0.f, 0.f);   // four partial sums, added at the end
     for (int c16 = 0; c16 < cin / 16; c16++) {
-      for (int i = 0; i < k; i++) {
-        const int tt = t + i - half;
+#pragma unroll
+      for (int i = 0; i < K; i++) {
+        const int tt = t + i - K / 2;
         if (tt < 0 || tt >= t_src) continue;
         uint32_t pv[8];   // 16 channels = one 32-byte (256-bit) load
         asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -73,13 +81,15 @@ __global__ void output_sde_kernel(const __nv_bfloat16* __restrict__ src, const f
                        "=r"(pv[6]), "=r"(pv[7])
                      : "l"(src + cl_off(b, c16 * 16, tt, cin, t_src, cb)));
 #pragma unroll
-        for (int h = 0; h < 8; h++) {
-          const float2 f = bf2_to_f2(pv[h]);
-          net = fmaf(sw[(c16 * 16 + h * 2) * k + i], f.x, net);
-          net = fmaf(sw[(c16 * 16 + h * 2 + 1) * k + i], f.y, net);
+        for (int q = 0; q < 4; q++) {
+          const float4 wv = *reinterpret_cast<const float4*>(sw + i * cin + c16 * 16 + q * 4);
+          const float2 f0 = bf2_to_f2(pv[2 * q]), f1 = bf2_to_f2(pv[2 * q + 1]);
+          acc.x = fmaf(wv.x, f0.x, acc.x), acc.y = fmaf(wv.y, f0.y, acc.y);
+          acc.z = fmaf(wv.z, f1.x, acc.z), acc.w = fmaf(wv.w, f1.y, acc.w);
         }
       }
     }
+    net = (acc.x + acc.y) + (acc.z + acc.w);
   }
   const size_t o = (size_t)b * t_sig + t;
   if (net_out) net_out[o] = net;
@@ -225,8 +235,14 @@ extern "C" int ou_input_conv(const float* x, const float* w, const float* bias, 
   OU_REQUIRE(k >= 1 && k <= 7 && (k & 1), "ou_input_conv: kernel size must be odd and <= 7");
   dim3 grid(ou::ceil_div(t, 256), batch);
   const size_t smem = (size_t)(cout * k + cout) * sizeof(float);
-  ou::input_conv_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(
-      x, w, bias, in_scale, (__nv_bfloat16*)out, t, cout, k);
+  cudaStream_t st = (cudaStream_t)stream;
+  __nv_bfloat16* o = (__nv_bfloat16*)out;
+  switch (k) {
+    case 1: ou::input_conv_kernel<1><<<grid, 256, smem, st>>>(x, w, bias, in_scale, o, t, cout); break;
+    case 3: ou::input_conv_kernel<3><<<grid, 256, smem, st>>>(x, w, bias, in_scale, o, t, cout); break;
+    case 5: ou::input_conv_kernel<5><<<grid, 256, smem, st>>>(x, w, bias, in_scale, o, t, cout); break;
+    default: ou::input_conv_kernel<7><<<grid, 256, smem, st>>>(x, w, bias, in_scale, o, t, cout); break;
+  }
   return ou::check_launch("ou_input_conv");
 }
 
@@ -235,12 +251,19 @@ extern "C" int ou_output_sde(const void* src, const float* w, float bias, const 
                              int batch, int cin, int k, int t_src, int t_sig, void* stream) {
   OU_REQUIRE(src && w, "ou_output_sde: null pointer");
   OU_REQUIRE(batch > 0 && t_src > 0 && t_sig >= t_src && cin % 16 == 0, "ou_output_sde: bad shape");
-  OU_REQUIRE(k >= 1 && (k & 1), "ou_output_sde: kernel size must be odd");
+  OU_REQUIRE(k >= 1 && (k & 1) && k <= 7, "ou_output_sde: kernel size must be odd and <= 7");
   OU_REQUIRE(coef == nullptr || (x && xout), "ou_output_sde: coef needs x and xout");
   OU_REQUIRE(coef || net_out, "ou_output_sde: nothing to write");
   dim3 grid(ou::ceil_div(t_sig, 256), batch);
-  ou::output_sde_kernel<<<grid, 256, (size_t)cin * k * sizeof(float), (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)src, w, bias, coef, x, noise, xout, net_out, cin, k, t_src, t_sig);
+  const size_t smem = (size_t)cin * k * sizeof(float);
+  cudaStream_t st = (cudaStream_t)stream;
+  const __nv_bfloat16* s = (const __nv_bfloat16*)src;
+  switch (k) {
+    case 1: ou::output_sde_kernel<1><<<grid, 256, smem, st>>>(s, w, bias, coef, x, noise, xout, net_out, cin, t_src, t_sig); break;
+    case 3: ou::output_sde_kernel<3><<<grid, 256, smem, st>>>(s, w, bias, coef, x, noise, xout, net_out, cin, t_src, t_sig); break;
+    case 5: ou::output_sde_kernel<5><<<grid, 256, smem, st>>>(s, w, bias, coef, x, noise, xout, net_out, cin, t_src, t_sig); break;
+    default: ou::output_sde_kernel<7><<<grid, 256, smem, st>>>(s, w, bias, coef, x, noise, xout, net_out, cin, t_src, t_sig); break;
+  }
   return ou::check_launch("ou_output_sde");
 }
 

@@ -221,9 +221,6 @@ class Universe(torch.nn.Module):
             epsilon = self.diff_kwargs.epsilon
         if n_steps is None:
             n_steps = self.diff_kwargs.n_steps
-        if target is not None or fake_score_snr is not None:
-            raise NotImplementedError("oracle-score debugging (target / fake_score_snr, "
-                                      "universe.py:276-296) is not part of the accelerated path")
         if n_steps < 2:
             raise ValueError("n_steps must be at least 2")
         if warm_start is not None and not 0 <= warm_start < n_steps:
@@ -251,6 +248,11 @@ class Universe(torch.nn.Module):
             mix = torch.stack([mix] * ensemble, dim=0).view((-1,) + mix_shape[1:]).contiguous()
             if mix_rms is not None:
                 mix_rms = mix_rms.repeat(ensemble).contiguous()
+        if target is not None:
+            if ensemble is not None:
+                raise NotImplementedError("target (oracle score) and ensemble do not combine upstream")
+            runtime.require_cuda(target)
+            target = target.reshape(mix.shape).contiguous().float()
         B, _, mix_len = mix.shape
         pad = self.tot_ds - mix_len % self.tot_ds
         t_pad = mix_len + pad
@@ -261,8 +263,18 @@ class Universe(torch.nn.Module):
         with torch.no_grad():
             # pad + normalize_batch fused (universe.py:267-272)
             mixn = torch.empty(B, 1, t_pad, dtype=torch.float32, device=dev)
-            lib.check(L.ou_pad_normalize(runtime._ptr(mix), runtime._ptr(mixn), None, B, mix_len,
-                                         t_pad, pad // 2, level, runtime._stream()))
+            stats = torch.empty(B, 2, dtype=torch.float32, device=dev)
+            lib.check(L.ou_pad_normalize(runtime._ptr(mix), runtime._ptr(mixn), runtime._ptr(stats), B,
+                                         mix_len, t_pad, pad // 2, level, runtime._stream()))
+            if target is not None:
+                # utils/norm.py:72-86: own statistics with ref='both', the mixture's otherwise
+                tgt = torch.empty_like(mixn)
+                if self.normalization_kwargs.get("ref", "noisy") == "both":
+                    lib.check(L.ou_pad_normalize(runtime._ptr(target), runtime._ptr(tgt), None, B,
+                                                 mix_len, t_pad, pad // 2, level, runtime._stream()))
+                else:
+                    tp = torch.nn.functional.pad(target, (pad // 2, pad - pad // 2))
+                    tgt = (tp - stats[:, 0, None, None]) / stats[:, 1, None, None]
             sigma, net_sigma, in_scale, coef, _ = self._sampler_tables(n_steps, epsilon, mixn)
             sigma_b = torch.broadcast_to(sigma[None, :], (B, n_steps))
             in_scale_b = in_scale[:, None].expand(n_steps, B).contiguous()
@@ -281,6 +293,9 @@ class Universe(torch.nn.Module):
                                      f"{tuple(sig.shape)}")
             if use_aux_signal:
                 x = sig
+            elif target is not None:
+                x = self._oracle_score_sampler(mixn, tgt, sig, sigma_b, n_steps, epsilon, warm_start,
+                                               fake_score_snr, rng)
             else:
                 sr = runtime.get_score_runner(self.get_score_model(), B, t_pad, dev)
                 sr.set_sigmas(net_sigma)
@@ -323,6 +338,36 @@ class Universe(torch.nn.Module):
         elif x_ndim == 2:
             x = x[:, 0, :]
         return x
+
+    def _oracle_score_sampler(self, mixn, target, sig, sigma, n_steps, epsilon, warm_start,
+                              fake_score_snr, rng):
+        """The sampler driven by a "perfect" score computed from a known target plus white noise at
+        ``fake_score_snr`` dB (universe.py:276-300, 322-343).  A debugging aid for the sampler
+        itself: the score network is never evaluated, so this is a dozen element-wise torch ops on
+        (B, 1, T) signals per step, not a kernel path."""
+        d = self.diff_kwargs
+        delta_t = 1.0 / (n_steps - 1)
+        gamma = (d.sigma_max / d.sigma_min) ** -delta_t
+        eta = 1 - gamma**epsilon
+        beta = math.sqrt(1 - gamma ** (2 * (epsilon - 1.0)))
+        score_snr = 5.0 if fake_score_snr is None else fake_score_snr
+
+        def score(x, s):
+            true_score = -(x - target) / s[:, None, None] ** 2
+            noise_rms = (true_score**2).mean().sqrt() * 10 ** (-score_snr / 20.0)
+            nz = torch.randn(true_score.shape, dtype=true_score.dtype, device=true_score.device,
+                             generator=rng)
+            return true_score + nz * noise_rms
+
+        if warm_start is None:
+            x, n_start = randn(mixn, sigma[:, 0], rng=rng), 0
+        else:
+            x, n_start = sig + randn(sig, sigma[:, warm_start], rng=rng), int(warm_start)
+        for n in range(n_start, n_steps - 1):
+            sc = score(x, sigma[:, n])
+            z = randn(x, sigma[:, n + 1], rng=rng)
+            x = x + sigma[:, n, None, None] ** 2 * eta * sc + beta * z
+        return x + sigma[:, -1, None, None] ** 2 * score(x, sigma[:, -1])
 
     # ------------------------------------------------------------------ EMA weight swap
     def train(self, mode=True, no_ema=False):

@@ -452,11 +452,24 @@ class UniverseOracle:
     def aux_to_wav(self, y_aux):
         return aux_to_wav(self.cfg, self.sd, y_aux)
 
+    def normalize_target(self, mix_padded, target_padded):
+        """utils/norm.py:72-86: ref='both' normalises the target on its own statistics, ref='noisy'
+        with the mixture's mean and gain."""
+        kw = self.cfg.get("normalization_kwargs", {})
+        level = 10.0 ** (kw.get("level_db", 0.0) / 20.0)
+        if kw.get("ref", "noisy") == "both":
+            t = target_padded - target_padded.mean(dim=(1, 2), keepdim=True)
+            return t * (level / t.std(dim=(1, 2), keepdim=True).clamp(min=1e-5))
+        mean = mix_padded.mean(dim=(1, 2), keepdim=True)
+        gain = level / (mix_padded - mean).std(dim=(1, 2), keepdim=True).clamp(min=1e-5)
+        return (target_padded - mean) * gain
+
     def enhance(self, mix, n_steps=None, epsilon=None, noise=None, rng=None, keep_rms=False,
-                use_aux_signal=False, ensemble=None, ensemble_stat="median", warm_start=None):
-        """universe.py:231-375 with target=None (the oracle-score debugging hooks :276-296 are not
-        restated).  ``noise``: optional list of unit-variance (B,1,T_pad) tensors used in draw
-        order instead of torch.randn (universe.py:39-41)."""
+                use_aux_signal=False, ensemble=None, ensemble_stat="median", warm_start=None,
+                target=None, fake_score_snr=None):
+        """universe.py:231-375.  ``noise``: optional list of unit-variance (B,1,T_pad) tensors used
+        in draw order instead of the module-level ``randn`` (universe.py:39-41); the oracle-score
+        debugging noise of ``score_wrapper`` (:293-300) always comes from torch.randn, as upstream."""
         d = self.cfg["diffusion"]
         epsilon = d["epsilon"] if epsilon is None else epsilon
         n_steps = d["n_steps"] if n_steps is None else n_steps
@@ -473,8 +486,22 @@ class UniverseOracle:
             mix = torch.stack([mix] * ensemble, dim=0).view((-1,) + mix_shape[1:])
         mix_len = mix.shape[-1]
         mix, pad = self.pad(mix)
+        if target is not None:
+            target, _ = self.pad(target, pad=pad)
+            target = self.normalize_target(mix, target)
         mix = self.normalize(mix)
+        score_snr = 5.0 if fake_score_snr is None else fake_score_snr
         it = iter(noise) if noise is not None else None
+
+        def score_wrapper(x, s, cond):
+            # universe.py:284-300
+            if target is None:
+                return self.score(x, s, cond)
+            true_score = -(x - target) / s[:, None, None] ** 2
+            noise_rms = (true_score**2).mean().sqrt() * 10 ** (-score_snr / 20.0)
+            nz = torch.randn(true_score.shape, dtype=true_score.dtype, device=true_score.device,
+                             generator=rng)
+            return true_score + nz * noise_rms
 
         def randn(sig):
             if it is not None:
@@ -501,10 +528,10 @@ class UniverseOracle:
                 n_start = warm_start
             for n in range(n_start, n_steps - 1):
                 s_now, s_next = sigma[:, n], sigma[:, n + 1]
-                score = self.score(x, s_now, cond)
+                score = score_wrapper(x, s_now, cond)
                 z = randn(s_next)
                 x = x + s_now[:, None, None] ** 2 * eta * score + beta * z
-            score = self.score(x, sigma[:, -1], cond)
+            score = score_wrapper(x, sigma[:, -1], cond)
             x = x + sigma[:, -1, None, None] ** 2 * score
         x = self.unpad(x, pad)
         x = F.pad(x, (0, mix_len - x.shape[-1]))

@@ -33,6 +33,10 @@ ENHANCE_CASES = [
          kwargs={"ensemble": 3, "ensemble_stat": "signal_median"}),
     dict(name="upp16k_ens_mean", model="upp16k", shape=(1, 2000), n_steps=2, seed=20,
          kwargs={"ensemble": 2, "ensemble_stat": "mean"}),
+    # sampler debugging with an oracle score (universe.py:276-300): the network is never called;
+    # at +200 dB "score SNR" the torch.randn perturbation of the score is below fp32 resolution
+    dict(name="upp16k_target", model="upp16k", shape=(2, 1, 2500), n_steps=6, seed=22,
+         target_seed=23, kwargs={"fake_score_snr": 200.0}),
     dict(name="orig16k_short", model="orig16k", shape=(1, 6000), n_steps=3, seed=21, kwargs={}),
     dict(name="upp24k_short", model="upp24k", shape=(1, 7000), n_steps=3, seed=31, kwargs={}),
 ]
@@ -52,3 +56,12 @@ def noise_rows(case):
     shape = tuple(case["shape"])
     b = 1 if len(shape) == 1 else shape[0]
     return b * (case["kwargs"].get("ensemble") or 1)
+
+
+def case_kwargs(case):
+    """enhance() keyword arguments of a case, with the synthetic ``target`` tensor materialised."""
+    from detweights import det_audio
+    kw = dict(case["kwargs"])
+    if case.get("target_seed") is not None:
+        kw["target"] = det_audio(tuple(case["shape"]), case["target_seed"])
+    return kw

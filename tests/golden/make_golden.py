@@ -21,7 +21,7 @@ HERE = Path(__file__).resolve().parent
 sys.path.insert(0, str(HERE))
 
 import ref_shim  # noqa: E402
-from cases import ENHANCE_CASES, MODELS, NET_CASES, WEIGHT_SEED, noise_rows  # noqa: E402
+from cases import ENHANCE_CASES, MODELS, NET_CASES, WEIGHT_SEED, case_kwargs, noise_rows  # noqa: E402
 from detweights import (det_audio, det_noise, det_state_dict,  # noqa: E402
                         is_constructor_buffer, subsample)
 
@@ -79,7 +79,7 @@ def run_enhance_case(case):
     noise = det_noise(case["n_steps"], (b, 1, t_pad), case["seed"])
     ref_shim.set_injected_noise(noise)
     with torch.no_grad():
-        y = model.enhance(mix, n_steps=case["n_steps"], **case["kwargs"])
+        y = model.enhance(mix, n_steps=case["n_steps"], **case_kwargs(case))
     assert y.shape == mix.shape
     np.savez(HERE / f"{case['name']}.npz", y=y.numpy(), t_pad=np.int64(t_pad))
     print(case["name"], "rms", float(y.square().mean().sqrt()))

@@ -14,7 +14,7 @@ fp32 FiLM / GRU state / EDM + SDE update.  Two weight sets:
 import pytest
 import torch
 
-from cases import ENHANCE_CASES, NET_CASES, noise_rows
+from cases import ENHANCE_CASES, NET_CASES, case_kwargs, noise_rows
 from common import (OUR_CONFIG, abs_rms, det_audio, det_noise, full_state_dict, load_golden,
                     make_oracle, rel_rms, sub)
 
@@ -96,7 +96,8 @@ def test_enhance_vs_reference_golden(case, monkeypatch):
     mix = det_audio(shape, case["seed"])
     noise = det_noise(case["n_steps"], (noise_rows(case), 1, int(g["t_pad"])), case["seed"])
     inject_noise(monkeypatch, noise)
-    y = m.enhance(mix.to(DEV), n_steps=case["n_steps"], **case["kwargs"]).cpu()
+    kw = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in case_kwargs(case).items()}
+    y = m.enhance(mix.to(DEV), n_steps=case["n_steps"], **kw).cpu()
     assert y.shape == mix.shape == g["y"].shape
     assert torch.isfinite(y).all()
     err = rel_rms(y, g["y"])

@@ -166,7 +166,7 @@ def test_no_cpu_fallback():
         m.enhance(torch.zeros(1, 320), warm_start=2)
     with pytest.raises(ValueError):
         m.enhance(torch.zeros(1, 320), n_steps=4, warm_start=4)
-    with pytest.raises(NotImplementedError):      # oracle-score debugging hooks are not accelerated
+    with pytest.raises(runtime.NoCudaPathError):
         m.enhance(torch.zeros(1, 320), target=torch.zeros(1, 320))
     with pytest.raises(NotImplementedError):      # universe.py:368
         m.enhance(torch.zeros(1, 320), ensemble=2, ensemble_stat="mode")

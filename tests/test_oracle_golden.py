@@ -3,7 +3,7 @@
 import pytest
 import torch
 
-from cases import ENHANCE_CASES, NET_CASES, noise_rows
+from cases import ENHANCE_CASES, NET_CASES, case_kwargs, noise_rows
 from common import (abs_rms, det_audio, det_noise, golden_buffers, load_golden, make_oracle,
                     model_cfg, rel_rms, sub)
 
@@ -42,7 +42,7 @@ def test_enhance_matches_reference(case):
     mix = det_audio(shape, case["seed"])
     noise = det_noise(case["n_steps"], (noise_rows(case), 1, int(g["t_pad"])), case["seed"])
     with torch.no_grad():
-        y = o.enhance(mix, n_steps=case["n_steps"], noise=noise, **case["kwargs"])
+        y = o.enhance(mix, n_steps=case["n_steps"], noise=noise, **case_kwargs(case))
     assert y.shape == mix.shape == g["y"].shape
     assert rel_rms(y, g["y"]) < 10 * TOL, (rel_rms(y, g["y"]), abs_rms(y, g["y"]))
 
