@@ -76,6 +76,7 @@ struct Ctx {
   uint32_t full_b, empty_b;
   uint32_t tmem_full, tmem_empty;            // [2]
   uint32_t coef;                             // fp32 [2 buffers][c0 | c1 | c2][bn]
+  const float* coef_ptr;                     // the same array as a generic pointer (plain C++ loads)
   uint32_t tmem_base;
   int nt, n0, mt0, mt_stride;
 };
@@ -197,6 +198,66 @@ __device__ __forceinline__ void mma_role(const TcArgs& a, const Ctx& c, bool use
   }
 }
 
+// Weights resident in shared memory (C <= 128: the layers whose MMAs are only 32-64 clocks long, so that
+// the ISSUE rate of this warp is what bounds the kernel): one wait for the whole weight slice before the
+// first tile, then per K block a single elected straight-line burst of TAPS x MSUB x K16 MMAs whose
+// descriptors differ by compile-time multiples of loop-invariant strides -- one barrier wait, one
+// elect and two commits per K block instead of per tap.
+template <int TAPS, int K16, int MSUB>
+__device__ __forceinline__ void mma_role_resident(const TcArgs& a, const Ctx& c, bool use_xf, int lane) {
+  Ring ra;
+  int acc = 0;
+  uint32_t acc_phase = 0;
+  const uint32_t a_stride16 = a.a_stage_bytes >> 4, b_stride16 = a.b_stage_bytes >> 4;
+  const uint32_t row_units = (uint32_t)a.row_bytes >> 4;   // tap shift in 16-byte descriptor units
+  const uint32_t sub_units = a.a_sub_bytes >> 4;
+  const uint32_t hi = a.desc_hi, idesc = a.idesc;
+  const uint32_t a_lo_base = ((c.smA >> 4) & 0x3FFFu) | (1u << 16);
+  const uint32_t b_lo_base = ((c.smB >> 4) & 0x3FFFu) | (1u << 16);
+  const uint32_t bn = (uint32_t)a.bn;
+  const int n_kblocks = a.n_kblocks, a_stages = a.a_stages;
+  const uint32_t a_ready = use_xf ? c.ready_a : c.full_a;
+  const bool issuer = lane == 0;   // tracing only
+  for (int i = 0; i < TAPS * n_kblocks; i++) mbar_wait(c.full_b + 8u * i, 0);
+  tc_fence_after();
+  int ti = 0;
+  for (int mt = c.mt0; mt < a.total_m_tiles; mt += c.mt_stride, ti++) {
+    mbar_wait(c.tmem_empty + 8u * acc, acc_phase ^ 1);
+    tc_fence_after();
+    if (issuer) trace_ev(a, 1, ti, 0);
+    const uint32_t d_tmem = c.tmem_base + (uint32_t)acc * bn * MSUB;
+    for (int kb = 0; kb < n_kblocks; kb++) {
+      mbar_wait(a_ready + 8u * ra.stage, ra.phase);
+      tc_fence_after();
+      if (issuer && kb == 0) trace_ev(a, 1, ti, 1);
+      const uint32_t a_lo0 = a_lo_base + (uint32_t)ra.stage * a_stride16;
+      const uint32_t b_lo0 = b_lo_base + (uint32_t)(kb * TAPS) * b_stride16;
+      const uint32_t first = kb != 0 ? 1u : 0u;
+      if (elect_one()) {
+#pragma unroll
+        for (int q = 0; q < TAPS; q++) {
+#pragma unroll
+          for (int sub = 0; sub < MSUB; sub++) {
+#pragma unroll
+            for (int kk = 0; kk < K16; kk++) {
+              // k16 step inside the swizzled row: +32 bytes = +2 descriptor address units
+              umma_f16_lohi(d_tmem + (uint32_t)sub * bn, a_lo0 + q * row_units + sub * sub_units + 2 * kk,
+                            b_lo0 + q * b_stride16 + 2 * kk, hi, idesc, (q | kk) != 0 ? 1u : first);
+            }
+          }
+        }
+        umma_commit(c.empty_a + 8u * ra.stage);
+        if (kb == n_kblocks - 1) umma_commit(c.tmem_full + 8u * acc);
+      }
+      __syncwarp();
+      ra.advance(a_stages);
+    }
+    if (issuer) trace_ev(a, 1, ti, 3);
+    acc ^= 1;
+    if (acc == 0) acc_phase ^= 1;
+  }
+}
+
 // ================================================================================ transform
 __device__ __forceinline__ void transform_role(const TcArgs& a, const Ctx& c, int xt, int lane) {
   Ring ra;
@@ -234,7 +295,9 @@ __device__ __forceinline__ void transform_role(const TcArgs& a, const Ctx& c, in
 // NADD: number of residual inputs (0, 1: add1, 2: add1 + add2); NPRELU: output PReLUs (0, 1, 2).
 // Eight warps: warp pair (w, w+4) shares TMEM lane quarter w%4 and splits every 32-column chunk
 // into two 16-column halves.
-template <int NADD, int NPRELU, bool F32TM>
+// FILM: per-clip gamma / beta present; without it the scale factors are per-launch scalars and only the
+// folded bias vector c1 is read per column.
+template <int NADD, int NPRELU, bool F32TM, bool FILM>
 __device__ __forceinline__ void epilogue_role(const TcArgs& a, const Ctx& c, int warp, int lane) {
   const ou_conv_params& p = a.p;
   const int quarter = warp & 3;
@@ -253,7 +316,8 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& a, const Ctx& c, int
   __nv_bfloat16* outp = (__nv_bfloat16*)p.out;
   const float s1 = p.scale1, s2 = p.scale2;
   const float slope1 = p.prelu_out, slope2 = p.prelu_out2;
-  const bool has_film = p.gamma != nullptr;
+  const bool has_film = FILM;
+  const float c0s = s1 * s2;     // column scale without FiLM
 
   int acc = 0;
   uint32_t acc_phase = 0;
@@ -263,6 +327,7 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& a, const Ctx& c, int
     const int m0 = (mt - b * a.m_tiles) * BM * a.m_sub;
     // per-column coefficients: y = c0*(acc + add1) + c2*add2 + c1   (see header comment)
     const uint32_t coef = c.coef + (uint32_t)(acc * 3 * bn) * 4u;
+    const float* coefp = c.coef_ptr + acc * 3 * bn;
     if (ti < 2 || has_film) {
       for (int i = et; i < bn; i += N_EPI_WARPS * 32) {
         const int n = n0 + i;
@@ -335,8 +400,13 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& a, const Ctx& c, int
         const int col = c0 + half * 16;
         const int j = m0 + sub * BM + row;
         uint32_t r[16];
+#define EPI_DETAIL(ev)                                                                                  \
+  if (a.trace != nullptr && blockIdx.x == 0 && ti == 8 && row == 0 && half == 0 && item < 8)           \
+    a.trace[1024 + item * 4 + (ev)] = clock64();
+        EPI_DETAIL(0)
         tmem_ld16(taddr0 + (uint32_t)(sub * bn + c0), r);
         tmem_ld_wait();
+        EPI_DETAIL(1)
         if (item == nitems - 1) {
           // accumulators fully read by this warp: hand the TMEM buffer back before the store phase
           tc_fence_before();
@@ -346,6 +416,7 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& a, const Ctx& c, int
         }
         const U8 cur1 = pre1[d], cur2 = pre2[d];
         if (NADD > 0) prefetch(d, item + D);
+        EPI_DETAIL(2)
         if (j >= p.rows || n0 + col >= n_total) continue;
         if (F32TM) {
           float4* dst = reinterpret_cast<float4*>(p.out_f32_tm + ((size_t)b * p.rows + j) * n_total + n0 + col);
@@ -360,10 +431,16 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& a, const Ctx& c, int
         const long off = out_offset(sub, col);
         if (off < 0) continue;
         float v[16];
+        // coefficient vectors as plain shared-memory loads: the compiler is free to hoist them over the
+        // arithmetic of the previous group (volatile asm accessors would serialise every load)
+        const float4* k0 = reinterpret_cast<const float4*>(coefp + col);
+        const float4* k1 = reinterpret_cast<const float4*>(coefp + bn + col);
+        const float4* k2 = reinterpret_cast<const float4*>(coefp + 2 * bn + col);
 #pragma unroll
-        for (int i = 0; i < 4; i++) {   // 4 columns at a time: coefficients live only briefly
-          const float4 x0 = lds_f4(coef + 4u * (col + 4 * i));
-          const float4 x1 = lds_f4(coef + 4u * (bn + col + 4 * i));
+        for (int i = 0; i < 4; i++) {
+          const float4 x1 = k1[i];
+          float4 x0 = make_float4(c0s, c0s, c0s, c0s);
+          if (FILM) x0 = k0[i];
           float a0 = __uint_as_float(r[4 * i]), a1 = __uint_as_float(r[4 * i + 1]);
           float a2 = __uint_as_float(r[4 * i + 2]), a3 = __uint_as_float(r[4 * i + 3]);
           if (NADD > 0) {
@@ -373,7 +450,8 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& a, const Ctx& c, int
           a0 = fmaf(x0.x, a0, x1.x), a1 = fmaf(x0.y, a1, x1.y);
           a2 = fmaf(x0.z, a2, x1.z), a3 = fmaf(x0.w, a3, x1.w);
           if (NADD > 1) {
-            const float4 x2 = lds_f4(coef + 4u * (2 * bn + col + 4 * i));
+            float4 x2 = make_float4(s2, s2, s2, s2);
+            if (FILM) x2 = k2[i];
             const float2 fa = bf2_to_f2(cur2.w[2 * i]), fb = bf2_to_f2(cur2.w[2 * i + 1]);
             a0 = fmaf(x2.x, fa.x, a0), a1 = fmaf(x2.y, fa.y, a1);
             a2 = fmaf(x2.z, fb.x, a2), a3 = fmaf(x2.w, fb.y, a3);
@@ -392,6 +470,7 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& a, const Ctx& c, int
 #pragma unroll
         for (int i = 0; i < 8; i++) o.w[i] = f2_to_bf2(v[2 * i], v[2 * i + 1]);
         stg_v8(outp + off, o);
+        EPI_DETAIL(3)
       }
     }
     if (row == 0 && half == 0) trace_ev(a, 3, ti, 3);
@@ -423,6 +502,7 @@ conv1d_tc_kernel(const TcArgs a, const __grid_constant__ CUtensorMap tm_a,
   c.tmem_empty = c.tmem_full + 16u;
   const uint32_t tmem_slot = c.tmem_empty + 16u;
   c.coef = tmem_slot + 16u;
+  c.coef_ptr = reinterpret_cast<const float*>(smem_raw + (c.coef - raw));
 
   const bool use_xf = p.has_prelu_in != 0;
 
@@ -458,6 +538,38 @@ conv1d_tc_kernel(const TcArgs a, const __grid_constant__ CUtensorMap tm_a,
     if (lane == 0) producer_role(a, c, &tm_a, &tm_w);
   } else if (warp == 1) {
     const int k16 = a.cb / 16;
+    if (a.resident) {
+      switch ((p.taps * 8 + k16) * 4 + (a.m_sub == 4 ? 2 : a.m_sub - 1)) {
+        case (1 * 8 + 1) * 4 + 0: mma_role_resident<1, 1, 1>(a, c, use_xf, lane); break;
+        case (1 * 8 + 2) * 4 + 0: mma_role_resident<1, 2, 1>(a, c, use_xf, lane); break;
+        case (1 * 8 + 4) * 4 + 0: mma_role_resident<1, 4, 1>(a, c, use_xf, lane); break;
+        case (3 * 8 + 1) * 4 + 0: mma_role_resident<3, 1, 1>(a, c, use_xf, lane); break;
+        case (3 * 8 + 2) * 4 + 0: mma_role_resident<3, 2, 1>(a, c, use_xf, lane); break;
+        case (3 * 8 + 4) * 4 + 0: mma_role_resident<3, 4, 1>(a, c, use_xf, lane); break;
+        case (5 * 8 + 1) * 4 + 0: mma_role_resident<5, 1, 1>(a, c, use_xf, lane); break;
+        case (5 * 8 + 2) * 4 + 0: mma_role_resident<5, 2, 1>(a, c, use_xf, lane); break;
+        case (5 * 8 + 4) * 4 + 0: mma_role_resident<5, 4, 1>(a, c, use_xf, lane); break;
+        case (1 * 8 + 1) * 4 + 1: mma_role_resident<1, 1, 2>(a, c, use_xf, lane); break;
+        case (1 * 8 + 2) * 4 + 1: mma_role_resident<1, 2, 2>(a, c, use_xf, lane); break;
+        case (1 * 8 + 4) * 4 + 1: mma_role_resident<1, 4, 2>(a, c, use_xf, lane); break;
+        case (3 * 8 + 1) * 4 + 1: mma_role_resident<3, 1, 2>(a, c, use_xf, lane); break;
+        case (3 * 8 + 2) * 4 + 1: mma_role_resident<3, 2, 2>(a, c, use_xf, lane); break;
+        case (3 * 8 + 4) * 4 + 1: mma_role_resident<3, 4, 2>(a, c, use_xf, lane); break;
+        case (5 * 8 + 1) * 4 + 1: mma_role_resident<5, 1, 2>(a, c, use_xf, lane); break;
+        case (5 * 8 + 2) * 4 + 1: mma_role_resident<5, 2, 2>(a, c, use_xf, lane); break;
+        case (5 * 8 + 4) * 4 + 1: mma_role_resident<5, 4, 2>(a, c, use_xf, lane); break;
+        case (1 * 8 + 1) * 4 + 2: mma_role_resident<1, 1, 4>(a, c, use_xf, lane); break;
+        case (1 * 8 + 2) * 4 + 2: mma_role_resident<1, 2, 4>(a, c, use_xf, lane); break;
+        case (1 * 8 + 4) * 4 + 2: mma_role_resident<1, 4, 4>(a, c, use_xf, lane); break;
+        case (3 * 8 + 1) * 4 + 2: mma_role_resident<3, 1, 4>(a, c, use_xf, lane); break;
+        case (3 * 8 + 2) * 4 + 2: mma_role_resident<3, 2, 4>(a, c, use_xf, lane); break;
+        case (3 * 8 + 4) * 4 + 2: mma_role_resident<3, 4, 4>(a, c, use_xf, lane); break;
+        case (5 * 8 + 1) * 4 + 2: mma_role_resident<5, 1, 4>(a, c, use_xf, lane); break;
+        case (5 * 8 + 2) * 4 + 2: mma_role_resident<5, 2, 4>(a, c, use_xf, lane); break;
+        case (5 * 8 + 4) * 4 + 2: mma_role_resident<5, 4, 4>(a, c, use_xf, lane); break;
+        default: break;   // rejected on the host
+      }
+    } else
     switch (p.taps * 8 + k16) {
       case 1 * 8 + 1: mma_role<1, 1>(a, c, use_xf, lane); break;
       case 1 * 8 + 2: mma_role<1, 2>(a, c, use_xf, lane); break;
@@ -476,18 +588,30 @@ conv1d_tc_kernel(const TcArgs a, const __grid_constant__ CUtensorMap tm_a,
     const int nadd = p.add2 ? 2 : (p.add1 ? 1 : 0);
     const int nprelu = p.has_prelu_out2 ? 2 : (p.has_prelu_out ? 1 : 0);
     if (p.out_f32_tm) {
-      epilogue_role<0, 0, true>(a, c, warp, lane);
+      epilogue_role<0, 0, true, false>(a, c, warp, lane);
+    } else if (p.gamma != nullptr) {
+      switch (nadd * 3 + nprelu) {
+        case 0: epilogue_role<0, 0, false, true>(a, c, warp, lane); break;
+        case 1: epilogue_role<0, 1, false, true>(a, c, warp, lane); break;
+        case 2: epilogue_role<0, 2, false, true>(a, c, warp, lane); break;
+        case 3: epilogue_role<1, 0, false, true>(a, c, warp, lane); break;
+        case 4: epilogue_role<1, 1, false, true>(a, c, warp, lane); break;
+        case 5: epilogue_role<1, 2, false, true>(a, c, warp, lane); break;
+        case 6: epilogue_role<2, 0, false, true>(a, c, warp, lane); break;
+        case 7: epilogue_role<2, 1, false, true>(a, c, warp, lane); break;
+        default: epilogue_role<2, 2, false, true>(a, c, warp, lane); break;
+      }
     } else {
       switch (nadd * 3 + nprelu) {
-        case 0: epilogue_role<0, 0, false>(a, c, warp, lane); break;
-        case 1: epilogue_role<0, 1, false>(a, c, warp, lane); break;
-        case 2: epilogue_role<0, 2, false>(a, c, warp, lane); break;
-        case 3: epilogue_role<1, 0, false>(a, c, warp, lane); break;
-        case 4: epilogue_role<1, 1, false>(a, c, warp, lane); break;
-        case 5: epilogue_role<1, 2, false>(a, c, warp, lane); break;
-        case 6: epilogue_role<2, 0, false>(a, c, warp, lane); break;
-        case 7: epilogue_role<2, 1, false>(a, c, warp, lane); break;
-        default: epilogue_role<2, 2, false>(a, c, warp, lane); break;
+        case 0: epilogue_role<0, 0, false, false>(a, c, warp, lane); break;
+        case 1: epilogue_role<0, 1, false, false>(a, c, warp, lane); break;
+        case 2: epilogue_role<0, 2, false, false>(a, c, warp, lane); break;
+        case 3: epilogue_role<1, 0, false, false>(a, c, warp, lane); break;
+        case 4: epilogue_role<1, 1, false, false>(a, c, warp, lane); break;
+        case 5: epilogue_role<1, 2, false, false>(a, c, warp, lane); break;
+        case 6: epilogue_role<2, 0, false, false>(a, c, warp, lane); break;
+        case 7: epilogue_role<2, 1, false, false>(a, c, warp, lane); break;
+        default: epilogue_role<2, 2, false, false>(a, c, warp, lane); break;
       }
     }
   }
@@ -546,19 +670,32 @@ int plan(const ou_conv_params* p, TcArgs* a) {
   a->n_kblocks = p->s * a->cin_blocks;
   a->bn = bn;
   a->n_ntiles = p->npad / bn;
-  static const int pair_env = [] { const char* e = getenv("OU_TC_PAIR"); return e ? atoi(e) : 1; }();
-  // measured on B200: pairing wins 30-50 % at N = 32 and is neutral-to-negative from N = 64 up
-  a->m_sub = (bn <= 32 && pair_env && p->rows > 2 * BM) ? 2 : 1;
-  a->m_tiles = ceil_div(p->rows, BM * a->m_sub);
-  a->total_m_tiles = a->m_tiles * p->batch;
   a->arows = BM + p->taps - 1;
   a->a_tx_bytes = (uint32_t)(a->arows * a->row_bytes);
   a->b_tx_bytes = (uint32_t)(bn * a->row_bytes);
   a->a_sub_bytes = (a->a_tx_bytes + 1023u) & ~1023u;
-  a->a_stage_bytes = a->a_sub_bytes * a->m_sub;
   a->b_stage_bytes = (a->b_tx_bytes + 1023u) & ~1023u;
   const int budget = 232448 - 2048 - 6 * bn * 4;   // 227 KB minus alignment slack, barriers, coefficients
   const int nb_all = p->taps * a->n_kblocks;
+  // Sub-tiles of 128 rows per scheduling unit.  A unit costs a fixed round of barrier hand-overs
+  // between the five warp roles (~2 000 clk measured) whatever its size, which dominates layers whose
+  // 128-row tile is only a handful of 32-64 clk MMAs: take the largest of 4 / 2 / 1 that fits the
+  // 512 TMEM columns (two accumulator buffers) and the shared-memory budget and leaves every SM a
+  // few units (measured at C = 128, k5: streamed weights with 2 sub-tiles beat resident weights
+  // with 1).  OU_TC_MSUB caps it (A/B runs).
+  static const int msub_cap = [] { const char* e = getenv("OU_TC_MSUB"); return e ? atoi(e) : 4; }();
+  a->m_sub = 1;
+  for (int ms : {4, 2}) {
+    if (ms > msub_cap || 2 * bn * ms > 512 || p->rows <= ms * BM) continue;
+    // three A stages next to the resident weights, or next to a ring of at least two weight stages
+    if ((budget - 3 * (int)a->a_sub_bytes * ms) / (int)a->b_stage_bytes < 2) continue;
+    if ((long)ceil_div(p->rows, BM * ms) * p->batch < 4L * g_num_sms) continue;
+    a->m_sub = ms;
+    break;
+  }
+  a->m_tiles = ceil_div(p->rows, BM * a->m_sub);
+  a->total_m_tiles = a->m_tiles * p->batch;
+  a->a_stage_bytes = a->a_sub_bytes * a->m_sub;
   if (nb_all <= MAX_B_STAGES && nb_all * (int)a->b_stage_bytes + 3 * (int)a->a_stage_bytes <= budget) {
     a->resident = 1;
     a->b_stages = nb_all;
