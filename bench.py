@@ -72,9 +72,13 @@ def peaks():
 
 
 # --------------------------------------------------------------------------------- CPU reference
-def cpu_affine_sample(n_lo=2, n_hi=4, seconds=CLIP_SECONDS, diffusion_steps=DIFFUSION_STEPS, batch=BATCH):
-    """Time the CPU oracle on 1 clip at two small step counts and extrapolate with t = a + b*N
-    (cost is exactly affine in N: one conditioner pass + N identical score passes)."""
+CPU_SAMPLE_CLIPS = 2
+
+
+def cpu_affine_sample(n_lo=16, n_hi=48, seconds=CLIP_SECONDS, diffusion_steps=DIFFUSION_STEPS, batch=BATCH):
+    """Time the CPU oracle on CPU_SAMPLE_CLIPS clips at two step counts (about 10-15 s of CPU work on
+    a 16-thread host) and extrapolate with t = a + b*N: the cost is exactly affine in N (one
+    conditioner pass + N identical score passes) and linear in the number of clips."""
     import torch
     from open_universe_b200.config import builtin_config, instantiate
     from oracle.universe_oracle import UniverseOracle
@@ -84,13 +88,13 @@ def cpu_affine_sample(n_lo=2, n_hi=4, seconds=CLIP_SECONDS, diffusion_steps=DIFF
     model = instantiate(cfg, _recursive_=False)
     o = UniverseOracle(cfg, model.state_dict())
     g = torch.Generator().manual_seed(0)
-    mix = 0.05 * torch.randn(1, int(FS * seconds), generator=g)
+    mix = 0.05 * torch.randn(CPU_SAMPLE_CLIPS, int(FS * seconds), generator=g)
     times = {}
     with torch.no_grad():
         for n in (n_lo, n_hi):
             t0 = time.perf_counter()
             o.enhance(mix, n_steps=n, rng=torch.Generator().manual_seed(1028282))
-            times[n] = time.perf_counter() - t0
+            times[n] = (time.perf_counter() - t0) / CPU_SAMPLE_CLIPS     # per clip
     b = (times[n_hi] - times[n_lo]) / (n_hi - n_lo)
     a = times[n_lo] - n_lo * b
     t_clip = a + b * diffusion_steps
@@ -102,10 +106,10 @@ def cpu_affine_sample(n_lo=2, n_hi=4, seconds=CLIP_SECONDS, diffusion_steps=DIFF
 def cpu_baseline_block(args):
     s = cpu_affine_sample(seconds=args.seconds, diffusion_steps=args.diffusion_steps, batch=args.batch)
     return {"value": round(s["value"], 5), "unit": "audio-s/s", "cores": s["cores"], "kind": "port",
-            "sample": f"oracle/universe_oracle.py on CPU (torch, {s['cores']} threads): 1 clip x "
-                      f"{args.seconds:g} s at 2 and 4 diffusion steps, affine fit t=a+b*N "
-                      f"(a={s['fit']['a_s']:.2f}s, b={s['fit']['b_s_per_step']:.2f}s/step) extrapolated to "
-                      f"{args.diffusion_steps} steps; per-clip cost, batch scales linearly",
+            "sample": f"oracle/universe_oracle.py on CPU (torch, {s['cores']} threads): {CPU_SAMPLE_CLIPS} clips x "
+                      f"{args.seconds:g} s at 16 and 48 diffusion steps, affine fit t=a+b*N per clip "
+                      f"(a={s['fit']['a_s']:.2f}s, b={s['fit']['b_s_per_step']:.3f}s/step) extrapolated to "
+                      f"{args.diffusion_steps} steps; batch scales linearly",
             "fit": s["fit"]}
 
 
@@ -130,9 +134,9 @@ def run_reference(args):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload(args),
         "cpu_baseline": {"value": round(v, 5), "unit": "audio-s/s", "cores": os.cpu_count(),
                          "kind": "port",
-                         "sample": "each step: 1 clip x 8 s at 2 and 4 diffusion steps on all host "
-                                   "threads, affine fit extrapolated to 64 steps; ms_per_step is the "
-                                   "projected time of the full 32-clip batch"},
+                         "sample": f"each step: {CPU_SAMPLE_CLIPS} clips x 8 s at 16 and 48 diffusion steps on "
+                                   "all host threads, affine fit per clip extrapolated to 64 steps; "
+                                   "ms_per_step is the projected time of the full 32-clip batch"},
         "e2e": {"value": round(v, 5), "unit": "audio-s/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
