@@ -36,10 +36,12 @@ using namespace ou::tc;
 
 constexpr int S = 3;                          // item slots per CTA
 // Warps per slot: 4 (one per TMEM lane quarter, a thread owns a whole accumulator row) or 8 (two column
-// halves per quarter).  Measured on B200: 8 is 25 % SLOWER -- the kernel is bound by shared-memory
-// bandwidth (the N = 32 / 64 MMAs re-read their 4 KB A tile for every 16-wide k step: ~260 KB of
-// operand reads per item against ~115 KB of tile traffic), not by thread-level parallelism, and 25
-// warps leave only 72 registers per thread.
+// halves per quarter).  Measured on B200: 8 is 25 % SLOWER -- 25 warps leave only 72 registers per
+// thread (spills), and shared memory is already the busiest unit: the N = 32 / 64 MMAs re-read their
+// 4 KB A tile for every 16-wide k step (~260 KB of operand reads per item against ~115 KB of tile
+// traffic).  ncu at C = 64: tensor pipe 33 % active, issue slots 36 %, i.e. what is left on the table
+// is the latency of each slot's serial T0 -> MMA -> E1 -> MMA -> E2 -> MMA -> E3 chain; more slots would
+// hide it but do not fit the 227 KB of shared memory next to the 11 resident weight taps.
 constexpr int WPS = 4;
 constexpr int NTHREADS = (1 + WPS * S) * 32;  // 416
 constexpr int TAPS1 = 5, TAPS2 = 3, TAPS3 = 3, NTAPS = TAPS1 + TAPS2 + TAPS3;
