@@ -218,8 +218,11 @@ __device__ __forceinline__ void mma_role_resident(const TcArgs& a, const Ctx& c,
   const int n_kblocks = a.n_kblocks, a_stages = a.a_stages;
   const uint32_t a_ready = use_xf ? c.ready_a : c.full_a;
   const bool issuer = lane == 0;   // tracing only
-  for (int i = 0; i < TAPS * n_kblocks; i++) mbar_wait(c.full_b + 8u * i, 0);
-  tc_fence_after();
+  // The weight taps of K block kb arrive right behind its first A stage (producer order A(0), B(0, *),
+  // A(1), B(1, *), ...): wait for them K block by K block during the first tile only.  Waiting for the
+  // whole slice up front would deadlock when a layer has more K blocks than A stages (the producer
+  // cannot reach B(kb >= a_stages, *) before this warp has released an A stage).
+  bool b_waited = false;
   int ti = 0;
   for (int mt = c.mt0; mt < a.total_m_tiles; mt += c.mt_stride, ti++) {
     mbar_wait(c.tmem_empty + 8u * acc, acc_phase ^ 1);
@@ -230,6 +233,11 @@ __device__ __forceinline__ void mma_role_resident(const TcArgs& a, const Ctx& c,
       mbar_wait(a_ready + 8u * ra.stage, ra.phase);
       tc_fence_after();
       if (issuer && kb == 0) trace_ev(a, 1, ti, 1);
+      if (!b_waited) {
+#pragma unroll
+        for (int q = 0; q < TAPS; q++) mbar_wait(c.full_b + 8u * (uint32_t)(kb * TAPS + q), 0);
+        tc_fence_after();
+      }
       const uint32_t a_lo0 = a_lo_base + (uint32_t)ra.stage * a_stride16;
       const uint32_t b_lo0 = b_lo_base + (uint32_t)(kb * TAPS) * b_stride16;
       const uint32_t first = kb != 0 ? 1u : 0u;
@@ -253,6 +261,7 @@ __device__ __forceinline__ void mma_role_resident(const TcArgs& a, const Ctx& c,
       ra.advance(a_stages);
     }
     if (issuer) trace_ev(a, 1, ti, 3);
+    b_waited = true;
     acc ^= 1;
     if (acc == 0) acc_phase ^= 1;
   }

@@ -20,6 +20,15 @@ def pytest_collection_modifyitems(config, items):
     except Exception:
         has_gpu = False
     if has_gpu:
+        # a deadlocked kernel must fail ONE test quickly, not hang the whole session: pytest-timeout in
+        # "thread" mode kills the process (the only way out of a stuck cudaDeviceSynchronize)
+        try:
+            import pytest_timeout  # noqa: F401
+            for item in items:
+                if "gpu" in item.keywords and item.get_closest_marker("timeout") is None:
+                    item.add_marker(pytest.mark.timeout(240, method="thread"))
+        except ImportError:
+            pass
         return
     skip = pytest.mark.skip(reason="no CUDA device")
     for item in items:

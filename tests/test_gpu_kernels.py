@@ -338,3 +338,23 @@ def test_alias_free_snake_and_decoupling_conv(C, B, T, beta):
     want_b = O.aux_to_wav(cfg, sd2, xb)
     got_b = R.prelu_conv_forward(pc, R.pack_blocked(xb.to(DEV)), blocked=True).cpu()
     assert rel_rms(got_b, want_b) < 2e-5
+
+
+def test_conv_resident_weights_with_more_k_blocks_than_a_stages():
+    """Regression: a layer whose weights stay resident in shared memory but that has more K blocks
+    than A stages (UNIVERSE++ 24 kHz conditioner enc.1.down: 96 -> 192, stride 3, k = 3 -> 9 K blocks,
+    8 stages) must not wait for the whole weight slice before releasing A stages (deadlock)."""
+    g = torch.Generator().manual_seed(11)
+    B, cin, cout, s, t = 2, 96, 192, 3, 3 * 700
+    fc = rand_fc(g, cin, cout, s=s, taps=1, tap_off=0, prelu_in=0.25)
+    prog = P.Program(B)
+    prog.buf("in", "blocked", cin, t)
+    P.add_conv(prog, "c", "in", "out", fc, t)
+    x = bf(torch.randn(B, cin, t, generator=g))
+    bufs = {"in": x}
+    E.run_conv(prog.ops[0], bufs, quant=True)
+    exe = R.Executor(prog, DEV, external=["in"])
+    exe.bufs["in"] = R.pack_blocked(x.to(DEV))
+    exe.run()
+    torch.cuda.synchronize()
+    assert rel_rms(R.unpack_blocked(exe.bufs["out"]).cpu(), bufs["out"]) < 3e-3
