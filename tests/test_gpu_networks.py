@@ -218,3 +218,30 @@ def test_cli_batched_directory(tmp_path):
     want = m.enhance(clips["a.wav"].to(DEV), n_steps=2, rng=rng).cpu()
     got, _ = cli.load_audio(one)
     assert torch.allclose(got, want, atol=1e-6)
+
+
+def test_in_place_noise_draw_matches_reference_draw_order(monkeypatch):
+    """enhance() draws the per-step noise straight into its persistent buffers (unit variance, sigma
+    folded into the update coefficient) when ``randn`` is the stock function; a patched ``randn``
+    takes the reference's literal path ``randn(x, sigma)``.  Same generator seed -> same noise, and the
+    same result up to the re-association (beta * sigma) * n  vs  beta * (sigma * n)."""
+    from open_universe_b200.config import builtin_config, instantiate
+    from open_universe_b200.networks.universe import universe as U
+    # the generator is consumed identically by randn(out=<slice of a buffer>) and randn(shape)
+    buf = torch.empty(3, 2, 1, 4160, device=DEV)
+    g1, g2 = (torch.Generator(device=DEV).manual_seed(5) for _ in range(2))
+    for n in range(3):
+        torch.randn(buf[n].shape, device=DEV, generator=g1, out=buf[n])
+        assert torch.equal(buf[n], torch.randn(buf[n].shape, device=DEV, generator=g2))
+    torch.manual_seed(4)
+    m = instantiate(builtin_config("universepp_16k").model, _recursive_=False)   # reference init scheme
+    m.eval(no_ema=True)
+    m = m.to(DEV)
+    mix = det_audio((2, 4000), 31).to(DEV)
+    fast = m.enhance(mix, n_steps=5, rng=torch.Generator(device=DEV).manual_seed(7))
+    stock = U.randn
+    monkeypatch.setattr(U, "randn", lambda x, sigma, rng=None: stock(x, sigma, rng=rng))
+    literal = m.enhance(mix, n_steps=5, rng=torch.Generator(device=DEV).manual_seed(7))
+    err = rel_rms(fast.cpu(), literal.cpu())
+    print("fast vs literal noise path: rel rms", err)
+    assert err < 2e-3, err
