@@ -174,12 +174,14 @@ int ou_gru_bidir(const float* gx, const float* w_hh, const float* b_hh, const vo
  *                    energy fp32 [B][frames] = sum_mel mel^2.  frame m = samples
  *                    [hop*m - pad_left, hop*m - pad_left + n_fft), zero outside [0, t).
  *                    window fp32 [n_fft]; fb fp32 [n_fft/2+1][n_mels];
- *                    twiddle fp32 [n_fft][2] = (cos, sin)(2*pi*i/n_fft).
+ *                    dft fp32 [n_fft][2*(n_fft/2+1)]: columns (2k, 2k+1) = (cos, sin)(2*pi*i*k/n_fft)
+ *                    (the power spectrum is one fp32 GEMM against it; n_fft % 16 == 0);
+ *                    power fp32 [B*frames][n_fft/2+1] scratch, overwritten.
  *   ou_mel_finalize: per clip scale = 1 / max(sqrt(mean_frames energy), 1e-5); writes the
  *                    normalised mel as fp32 [B][n_mels][frames] (in place allowed, or NULL) and
  *                    blocked bf16 (B, n_mels, frames) (or NULL).
  * ------------------------------------------------------------------------------------------ */
-int ou_mel_power(const float* x, const float* window, const float* fb, const float* twiddle,
+int ou_mel_power(const float* x, const float* window, const float* fb, const float* dft, float* power,
                  float* mel, float* energy, int batch, int t, int n_fft, int hop, int n_mels,
                  int pad_left, int frames, void* stream);
 int ou_mel_finalize(const float* mel, const float* energy, float* mel_norm, void* mel_blocked,

@@ -53,6 +53,12 @@ __global__ void __launch_bounds__(256) input_conv_kernel(const float* __restrict
 }
 
 // ------------------------------------------------------------------------------ output conv + SDE
+// One lane per time step of the SOURCE row it loads (all cin channels, 32-byte loads); it forms the K
+// per-tap partial sums p_i[t] = sum_c w[c][i] * v[c][t] of its own row and the output
+// net[t] = bias + sum_i p_i[t + i - K/2] is assembled with warp shuffles, so every activation row is
+// read from memory once (a warp covers 32 rows and produces 32 - (K - 1) outputs; the first version
+// re-read each row K times through L1 and ran at 2.7 TB/s).  Weights tap-major in shared memory as in
+// input_conv_kernel.
 template <int K>
 __global__ void __launch_bounds__(256) output_sde_kernel(const __nv_bfloat16* __restrict__ src,
                                                          const float* __restrict__ w, float bias,
@@ -60,37 +66,49 @@ __global__ void __launch_bounds__(256) output_sde_kernel(const __nv_bfloat16* __
                                                          const float* __restrict__ x,
                                                          const float* __restrict__ noise, float* __restrict__ xout,
                                                          float* __restrict__ net_out, int cin, int t_src, int t_sig) {
-  extern __shared__ __align__(16) float sw[];  // [K][cin], tap-major (see input_conv_kernel)
+  extern __shared__ __align__(16) float sw[];  // [K][cin]
   for (int i = threadIdx.x; i < cin * K; i += blockDim.x) sw[(i % K) * cin + i / K] = w[i];
   __syncthreads();
+  constexpr int HALO = K / 2, OUT_PER_WARP = 32 - 2 * HALO;
   const int b = blockIdx.y;
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= t_sig) return;
-  float net = 0.f;
-  if (t < t_src) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = (blockIdx.x * (int)(blockDim.x >> 5) + warp) * OUT_PER_WARP + lane - HALO;   // row this lane loads
+  float p[K];
+#pragma unroll
+  for (int i = 0; i < K; i++) p[i] = 0.f;
+  if (t >= 0 && t < t_src) {
     const int cb = cl_cb(cin);
-    float4 acc = make_float4(bias, 0.f, 0.f, 0.f);   // four partial sums, added at the end
     for (int c16 = 0; c16 < cin / 16; c16++) {
+      uint32_t pv[8];   // 16 channels = one 32-byte (256-bit) load
+      asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                   : "=r"(pv[0]), "=r"(pv[1]), "=r"(pv[2]), "=r"(pv[3]), "=r"(pv[4]), "=r"(pv[5]),
+                     "=r"(pv[6]), "=r"(pv[7])
+                   : "l"(src + cl_off(b, c16 * 16, t, cin, t_src, cb)));
+      float f[16];
+#pragma unroll
+      for (int q = 0; q < 8; q++) {
+        const float2 v = bf2_to_f2(pv[q]);
+        f[2 * q] = v.x, f[2 * q + 1] = v.y;
+      }
 #pragma unroll
       for (int i = 0; i < K; i++) {
-        const int tt = t + i - K / 2;
-        if (tt < 0 || tt >= t_src) continue;
-        uint32_t pv[8];   // 16 channels = one 32-byte (256-bit) load
-        asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                     : "=r"(pv[0]), "=r"(pv[1]), "=r"(pv[2]), "=r"(pv[3]), "=r"(pv[4]), "=r"(pv[5]),
-                       "=r"(pv[6]), "=r"(pv[7])
-                     : "l"(src + cl_off(b, c16 * 16, tt, cin, t_src, cb)));
 #pragma unroll
         for (int q = 0; q < 4; q++) {
           const float4 wv = *reinterpret_cast<const float4*>(sw + i * cin + c16 * 16 + q * 4);
-          const float2 f0 = bf2_to_f2(pv[2 * q]), f1 = bf2_to_f2(pv[2 * q + 1]);
-          acc.x = fmaf(wv.x, f0.x, acc.x), acc.y = fmaf(wv.y, f0.y, acc.y);
-          acc.z = fmaf(wv.z, f1.x, acc.z), acc.w = fmaf(wv.w, f1.y, acc.w);
+          p[i] = fmaf(wv.x, f[4 * q], p[i]);
+          p[i] = fmaf(wv.y, f[4 * q + 1], p[i]);
+          p[i] = fmaf(wv.z, f[4 * q + 2], p[i]);
+          p[i] = fmaf(wv.w, f[4 * q + 3], p[i]);
         }
       }
     }
-    net = (acc.x + acc.y) + (acc.z + acc.w);
   }
+  // output at this lane's time step: tap i multiplies the row at t + i - HALO, i.e. lane + i - HALO
+  float net = bias;
+#pragma unroll
+  for (int i = 0; i < K; i++) net += __shfl_sync(0xffffffffu, p[i], (lane + i - HALO) & 31);
+  if (lane < HALO || lane >= 32 - HALO || t >= t_sig) return;   // halo lanes only feed their neighbours
+  if (t >= t_src) net = 0.f;                                     // right padding of the signal
   const size_t o = (size_t)b * t_sig + t;
   if (net_out) net_out[o] = net;
   if (coef) {
@@ -254,7 +272,7 @@ extern "C" int ou_output_sde(const void* src, const float* w, float bias, const 
   OU_REQUIRE(k >= 1 && (k & 1) && k <= 7, "ou_output_sde: kernel size must be odd and <= 7");
   OU_REQUIRE(coef == nullptr || (x && xout), "ou_output_sde: coef needs x and xout");
   OU_REQUIRE(coef || net_out, "ou_output_sde: nothing to write");
-  dim3 grid(ou::ceil_div(t_sig, 256), batch);
+  dim3 grid(ou::ceil_div(t_sig, 8 * (32 - 2 * (k / 2))), batch);   // 8 warps x (32 - halo) outputs per CTA
   const size_t smem = (size_t)cin * k * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
   const __nv_bfloat16* s = (const __nv_bfloat16*)src;

@@ -60,8 +60,8 @@ SIGNATURES = {
                               c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "ou_gru_bidir": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int,
                              c_int, c_int, c_void_p]),
-    "ou_mel_power": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
-                             c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "ou_mel_power": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                             c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "ou_mel_finalize": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                 c_void_p]),
     "ou_sigma_embed_simple": (c_int, [c_void_p, c_float, c_float, c_void_p, c_int, c_int, c_void_p]),

@@ -97,6 +97,15 @@ def alloc_buffers(prog, device, skip=()):
     return bufs
 
 
+def dft_matrix(n_fft):
+    """fp32 [n_fft][2 * (n_fft/2 + 1)]: columns (2k, 2k + 1) = (cos, sin)(2 pi i k / n_fft), evaluated in
+    double precision on the exact residue i*k mod n_fft (ou_mel_power's GEMM operand)."""
+    i = torch.arange(n_fft, dtype=torch.int64)[:, None]
+    k = torch.arange(n_fft // 2 + 1, dtype=torch.int64)[None, :]
+    ang = 2.0 * math.pi * ((i * k) % n_fft).to(torch.float64) / n_fft
+    return torch.stack([torch.cos(ang), torch.sin(ang)], dim=2).reshape(n_fft, -1).float().contiguous()
+
+
 def prepare_ops(prog, device):
     """Upload packed weights / small tables for every op of a program."""
     for op in P.flat_ops(prog.ops):
@@ -110,11 +119,10 @@ def prepare_ops(prog, device):
             op.packed = {"w_hh": op.w_hh.to(device).contiguous(),
                          "b_hh": op.b_hh.to(device).contiguous()}
         elif isinstance(op, P.MelOp):
-            i = torch.arange(op.n_fft, dtype=torch.float64)
-            ang = 2.0 * math.pi * i / op.n_fft
-            tw = torch.stack([torch.cos(ang), torch.sin(ang)], dim=1).float()
             op.packed = {"window": op.window.to(device).contiguous(),
-                         "fb": op.fb.to(device).contiguous(), "twiddle": tw.to(device).contiguous(),
+                         "fb": op.fb.to(device).contiguous(), "dft": dft_matrix(op.n_fft).to(device),
+                         "power": torch.empty(prog.batch * op.frames, op.n_fft // 2 + 1,
+                                              dtype=torch.float32, device=device),
                          "mel": torch.empty(prog.batch, op.n_mels, op.frames, dtype=torch.float32,
                                             device=device),
                          "energy": torch.empty(prog.batch, op.frames, dtype=torch.float32,
@@ -247,7 +255,8 @@ class Executor:
             elif isinstance(op, P.MelOp):
                 pk = op.packed
                 lib.check(L.ou_mel_power(_ptr(bufs[op.src]), _ptr(pk["window"]), _ptr(pk["fb"]),
-                                         _ptr(pk["twiddle"]), _ptr(pk["mel"]), _ptr(pk["energy"]),
+                                         _ptr(pk["dft"]), _ptr(pk["power"]), _ptr(pk["mel"]),
+                                         _ptr(pk["energy"]),
                                          B, op.t, op.n_fft, op.hop, op.n_mels, op.pad_left,
                                          op.frames, _stream()))
                 lib.check(L.ou_mel_finalize(_ptr(pk["mel"]), _ptr(pk["energy"]), _ptr(pk["mel"]),
@@ -563,8 +572,9 @@ def compute_mel_spec(mel_adapter, x):
     pk = op.packed
     L = lib.load()
     xc = x.contiguous().float()
-    lib.check(L.ou_mel_power(_ptr(xc), _ptr(pk["window"]), _ptr(pk["fb"]), _ptr(pk["twiddle"]),
-                             _ptr(pk["mel"]), _ptr(pk["energy"]), b, t, op.n_fft, hop, op.n_mels,
+    lib.check(L.ou_mel_power(_ptr(xc), _ptr(pk["window"]), _ptr(pk["fb"]), _ptr(pk["dft"]),
+                             _ptr(pk["power"]), _ptr(pk["mel"]), _ptr(pk["energy"]), b, t, op.n_fft, hop,
+                             op.n_mels,
                              op.pad_left, frames, _stream()))
     lib.check(L.ou_mel_finalize(_ptr(pk["mel"]), _ptr(pk["energy"]), _ptr(pk["mel"]), None, b,
                                 op.n_mels, frames, _stream()))
