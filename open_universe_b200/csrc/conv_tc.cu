@@ -659,8 +659,9 @@ int plan(const ou_conv_params* p, TcArgs* a) {
   if (p->w_tc == nullptr || p->t_in % p->s != 0) return OU_ERR_UNSUPPORTED;
   if (p->taps != 1 && p->taps != 3 && p->taps != 5) return OU_ERR_UNSUPPORTED;
   int bn = 0;
+  static const int bn_max = [] { const char* e = getenv("OU_TC_BN_MAX"); return e ? atoi(e) : 256; }();
   for (int cand : {256, 128, 64, 32})
-    if (p->npad % cand == 0) {
+    if (cand <= bn_max && p->npad % cand == 0) {
       bn = cand;
       break;
     }

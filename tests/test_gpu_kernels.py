@@ -53,6 +53,13 @@ CONV_CASES = [
     dict(cin=512, cout=512, taps=3, off=-1, t=801, B=16, add1=True),
     dict(cin=512, cout=256, up=5, taps=3, off=-1, t=801, B=3, prelu_in=0.2, add1=True),
     dict(cin=512, cout=1536, taps=1, off=0, t=801, B=4, f32_tm=True),
+    # 2 / 4 sub-tiles of 128 rows per scheduling unit (the planner needs >= 4 units per SM):
+    # bn = 64 strided down conv, bn = 64 up conv with skip, bn = 128 streamed and resident weights
+    dict(cin=32, cout=64, s=2, taps=3, off=-1, t=128160, B=5, prelu_in=0.25),
+    dict(cin=64, cout=32, up=2, taps=3, off=-1, t=64080, B=5, prelu_in=0.25, add1=True),
+    dict(cin=64, cout=128, s=4, taps=3, off=-1, t=64080, B=10, prelu_in=0.25),
+    dict(cin=128, cout=128, taps=3, off=-1, t=16020, B=10, add1=True),
+    dict(cin=128, cout=128, taps=5, off=-2, t=16020, B=10, prelu_in=0.25, film=True),
 ]
 
 
