@@ -86,8 +86,8 @@ __device__ __forceinline__ void trace_ev(const TcArgs& a, int role, int tile_i, 
     a.trace[(role * 64 + tile_i) * 4 + ev] = clock64();
 }
 
-__device__ __forceinline__ void epi_bar_sync() {
-  asm volatile("bar.sync 1, %0;" ::"n"(N_EPI_WARPS * 32) : "memory");
+__device__ __forceinline__ void epi_bar_sync(int n_threads) {
+  asm volatile("bar.sync 1, %0;" ::"r"(n_threads) : "memory");
 }
 
 // ================================================================================ producer
@@ -302,17 +302,22 @@ __device__ __forceinline__ void transform_role(const TcArgs& a, const Ctx& c, in
 
 // ================================================================================ epilogue
 // NADD: number of residual inputs (0, 1: add1, 2: add1 + add2); NPRELU: output PReLUs (0, 1, 2).
-// Eight warps: warp pair (w, w+4) shares TMEM lane quarter w%4 and splits every 32-column chunk
-// into two 16-column halves.
+// Eight warps (6-13): warp pair (w, w+4) shares TMEM lane quarter w%4.  Layers WITHOUT a fused input PReLU
+// leave the four transform warps (2-5) idle: they join as a third epilogue warp per quarter (the
+// epilogue, not the tensor pipe, bounds those layers at C <= 256).  A tile is cut into units of
+// (sub-tile, 16 columns); the `nw` warps of a quarter take them round-robin (`widx` = 0..nw-1).
 // FILM: per-clip gamma / beta present; without it the scale factors are per-launch scalars and only the
 // folded bias vector c1 is read per column.
 template <int NADD, int NPRELU, bool F32TM, bool FILM>
-__device__ __forceinline__ void epilogue_role(const TcArgs& a, const Ctx& c, int warp, int lane) {
+__device__ __forceinline__ void epilogue_role(const TcArgs& a, const Ctx& c, int warp, int lane, int widx,
+                                              int nw) {
   const ou_conv_params& p = a.p;
   const int quarter = warp & 3;
-  const int half = (warp - EPI_WARP0) >> 2;
   const int row = quarter * 32 + lane;
-  const int et = threadIdx.x - EPI_WARP0 * 32;   // 0..255
+  // ordinal among the epilogue threads (coefficient set-up): main warps 0..255, helper warps 256..383
+  const int et = warp >= EPI_WARP0 ? (int)threadIdx.x - EPI_WARP0 * 32
+                                   : N_EPI_WARPS * 32 + (int)threadIdx.x - XF_WARP0 * 32;
+  const int n_epi_threads = nw * 4 * 32;
   const int bn = a.bn;
   const int cout = p.cout, up = p.up, t_out = p.t_out, n_total = p.n;
   const int cbo = cl_cb(cout);
@@ -338,7 +343,7 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& a, const Ctx& c, int
     const uint32_t coef = c.coef + (uint32_t)(acc * 3 * bn) * 4u;
     const float* coefp = c.coef_ptr + acc * 3 * bn;
     if (ti < 2 || has_film) {
-      for (int i = et; i < bn; i += N_EPI_WARPS * 32) {
+      for (int i = et; i < bn; i += n_epi_threads) {
         const int n = n0 + i;
         float g = 1.f, be = 0.f, bias = 0.f;
         if (n < n_total) {
@@ -354,9 +359,9 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& a, const Ctx& c, int
         sts_f1(coef + 4u * (bn + i), F32TM ? bias : fmaf(c0, bias, be));
         sts_f1(coef + 4u * (2 * bn + i), g * s2);
       }
-      epi_bar_sync();   // coefficients visible to all eight epilogue warps
+      epi_bar_sync(n_epi_threads);   // coefficients visible to all epilogue warps
     }
-    if (row == 0 && half == 0) trace_ev(a, 3, ti, 0);
+    if (row == 0 && widx == 0) trace_ev(a, 3, ti, 0);
 
     const size_t clip_base = (size_t)b * cout * t_out;
     const int m_sub = a.m_sub;
@@ -369,20 +374,22 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& a, const Ctx& c, int
       if (jj >= p.rows || n0 + nl >= n_total || t >= t_out) return -1;
       return (long)(clip_base + (size_t)(co >> cbo_shift) * blk_stride + (size_t)t * cbo + (co & (cbo - 1)));
     };
-    // Work items of this thread: (sub-tile, 32-column chunk) -> its 16-column half = one 32-byte
-    // output vector (16 consecutive channels of one time step).  Residual vectors are prefetched D
-    // items ahead (the first D while the MMAs of this tile still run) so that their HBM latency
-    // never sits on the epilogue's critical path.
+    // Work units of this thread: (sub-tile, 16 columns) = one 32-byte output vector (16 consecutive
+    // channels of one time step); unit u = widx + k * nw is this warp's k-th.  Residual vectors are
+    // prefetched D units ahead (the first D while the MMAs of this tile still run) so that their HBM
+    // latency never sits on the epilogue's critical path.
     constexpr int D = NADD == 1 ? 3 : (NADD == 2 ? 2 : 1);
-    const int chunk_shift = bn == 256 ? 3 : (bn == 128 ? 2 : (bn == 64 ? 1 : 0));
-    const int nitems = m_sub << chunk_shift;
+    const int unit_shift = bn == 256 ? 4 : (bn == 128 ? 3 : (bn == 64 ? 2 : 1));   // log2(bn / 16)
+    const int n_units = m_sub << unit_shift;
+    const int nk = widx < n_units ? (n_units - widx + nw - 1) / nw : 0;
     U8 pre1[D], pre2[D];
-    auto prefetch = [&](int d, int item) {
-      const int sub = item >> chunk_shift;
-      const int col = ((item - (sub << chunk_shift)) << 5) + half * 16;
+    auto prefetch = [&](int d, int k) {
+      const int u = widx + k * nw;
+      const int sub = u >> unit_shift;
+      const int col = (u - (sub << unit_shift)) << 4;
 #pragma unroll
       for (int i = 0; i < 8; i++) pre1[d].w[i] = 0u, pre2[d].w[i] = 0u;
-      if (NADD > 0 && item < nitems) {
+      if (NADD > 0 && k < nk) {
         const long off = out_offset(sub, col);
         if (off >= 0) {
           pre1[d] = ldg_nc_v8(add1 + off);
@@ -397,34 +404,39 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& a, const Ctx& c, int
 
     mbar_wait(c.tmem_full + 8u * acc, acc_phase);
     tc_fence_after();
-    if (row == 0 && half == 0) trace_ev(a, 3, ti, 1);
-    const uint32_t taddr0 = c.tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * m_sub * bn + half * 16);
-    for (int base = 0; base < nitems; base += D) {
+    if (row == 0 && widx == 0) trace_ev(a, 3, ti, 1);
+    if (nk == 0) {   // more warps than units (N = 32, one sub-tile): nothing to read, release at once
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(c.tmem_empty + 8u * acc);
+    }
+    const uint32_t taddr0 = c.tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * m_sub * bn);
+    for (int base = 0; base < nk; base += D) {
 #pragma unroll
       for (int d = 0; d < D; d++) {
-        const int item = base + d;
-        if (item >= nitems) break;
-        const int sub = item >> chunk_shift;
-        const int c0 = (item - (sub << chunk_shift)) << 5;
-        const int col = c0 + half * 16;
+        const int k = base + d;
+        if (k >= nk) break;
+        const int u = widx + k * nw;
+        const int sub = u >> unit_shift;
+        const int col = (u - (sub << unit_shift)) << 4;
         const int j = m0 + sub * BM + row;
         uint32_t r[16];
 #define EPI_DETAIL(ev)                                                                                  \
-  if (a.trace != nullptr && blockIdx.x == 0 && ti == 8 && row == 0 && half == 0 && item < 8)           \
-    a.trace[1024 + item * 4 + (ev)] = clock64();
+  if (a.trace != nullptr && blockIdx.x == 0 && ti == 8 && row == 0 && widx == 0 && k < 8)              \
+    a.trace[1024 + k * 4 + (ev)] = clock64();
         EPI_DETAIL(0)
-        tmem_ld16(taddr0 + (uint32_t)(sub * bn + c0), r);
+        tmem_ld16(taddr0 + (uint32_t)(sub * bn + col), r);
         tmem_ld_wait();
         EPI_DETAIL(1)
-        if (item == nitems - 1) {
+        if (k == nk - 1) {
           // accumulators fully read by this warp: hand the TMEM buffer back before the store phase
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(c.tmem_empty + 8u * acc);
-          if (row == 0 && half == 0) trace_ev(a, 3, ti, 2);
+          if (row == 0 && widx == 0) trace_ev(a, 3, ti, 2);
         }
         const U8 cur1 = pre1[d], cur2 = pre2[d];
-        if (NADD > 0) prefetch(d, item + D);
+        if (NADD > 0) prefetch(d, k + D);
         EPI_DETAIL(2)
         if (j >= p.rows || n0 + col >= n_total) continue;
         if (F32TM) {
@@ -482,7 +494,7 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& a, const Ctx& c, int
         EPI_DETAIL(3)
       }
     }
-    if (row == 0 && half == 0) trace_ev(a, 3, ti, 3);
+    if (row == 0 && widx == 0) trace_ev(a, 3, ti, 3);
     acc ^= 1;
     if (acc == 0) acc_phase ^= 1;
   }
@@ -527,7 +539,7 @@ conv1d_tc_kernel(const TcArgs a, const __grid_constant__ CUtensorMap tm_a,
     }
     for (int i = 0; i < 2; i++) {
       mbar_init(c.tmem_full + 8u * i, 1);
-      mbar_init(c.tmem_empty + 8u * i, N_EPI_WARPS);
+      mbar_init(c.tmem_empty + 8u * i, use_xf ? N_EPI_WARPS : N_EPI_WARPS + 4);
     }
     fence_barrier_init();
   }
@@ -591,36 +603,40 @@ conv1d_tc_kernel(const TcArgs a, const __grid_constant__ CUtensorMap tm_a,
       case 5 * 8 + 4: mma_role<5, 4>(a, c, use_xf, lane); break;
       default: break;   // rejected on the host
     }
-  } else if (warp < EPI_WARP0) {
-    if (use_xf) transform_role(a, c, threadIdx.x - XF_WARP0 * 32, lane);
+  } else if (warp < EPI_WARP0 && use_xf) {
+    transform_role(a, c, threadIdx.x - XF_WARP0 * 32, lane);
   } else {
+    // epilogue: warps 6-13 always; warps 2-5 as a third warp per TMEM lane quarter when they have no
+    // input PReLU to apply
+    const int nw = use_xf ? 2 : 3;
+    const int widx = warp >= EPI_WARP0 ? (warp - EPI_WARP0) >> 2 : 2;
     const int nadd = p.add2 ? 2 : (p.add1 ? 1 : 0);
     const int nprelu = p.has_prelu_out2 ? 2 : (p.has_prelu_out ? 1 : 0);
     if (p.out_f32_tm) {
-      epilogue_role<0, 0, true, false>(a, c, warp, lane);
+      epilogue_role<0, 0, true, false>(a, c, warp, lane, widx, nw);
     } else if (p.gamma != nullptr) {
       switch (nadd * 3 + nprelu) {
-        case 0: epilogue_role<0, 0, false, true>(a, c, warp, lane); break;
-        case 1: epilogue_role<0, 1, false, true>(a, c, warp, lane); break;
-        case 2: epilogue_role<0, 2, false, true>(a, c, warp, lane); break;
-        case 3: epilogue_role<1, 0, false, true>(a, c, warp, lane); break;
-        case 4: epilogue_role<1, 1, false, true>(a, c, warp, lane); break;
-        case 5: epilogue_role<1, 2, false, true>(a, c, warp, lane); break;
-        case 6: epilogue_role<2, 0, false, true>(a, c, warp, lane); break;
-        case 7: epilogue_role<2, 1, false, true>(a, c, warp, lane); break;
-        default: epilogue_role<2, 2, false, true>(a, c, warp, lane); break;
+        case 0: epilogue_role<0, 0, false, true>(a, c, warp, lane, widx, nw); break;
+        case 1: epilogue_role<0, 1, false, true>(a, c, warp, lane, widx, nw); break;
+        case 2: epilogue_role<0, 2, false, true>(a, c, warp, lane, widx, nw); break;
+        case 3: epilogue_role<1, 0, false, true>(a, c, warp, lane, widx, nw); break;
+        case 4: epilogue_role<1, 1, false, true>(a, c, warp, lane, widx, nw); break;
+        case 5: epilogue_role<1, 2, false, true>(a, c, warp, lane, widx, nw); break;
+        case 6: epilogue_role<2, 0, false, true>(a, c, warp, lane, widx, nw); break;
+        case 7: epilogue_role<2, 1, false, true>(a, c, warp, lane, widx, nw); break;
+        default: epilogue_role<2, 2, false, true>(a, c, warp, lane, widx, nw); break;
       }
     } else {
       switch (nadd * 3 + nprelu) {
-        case 0: epilogue_role<0, 0, false, false>(a, c, warp, lane); break;
-        case 1: epilogue_role<0, 1, false, false>(a, c, warp, lane); break;
-        case 2: epilogue_role<0, 2, false, false>(a, c, warp, lane); break;
-        case 3: epilogue_role<1, 0, false, false>(a, c, warp, lane); break;
-        case 4: epilogue_role<1, 1, false, false>(a, c, warp, lane); break;
-        case 5: epilogue_role<1, 2, false, false>(a, c, warp, lane); break;
-        case 6: epilogue_role<2, 0, false, false>(a, c, warp, lane); break;
-        case 7: epilogue_role<2, 1, false, false>(a, c, warp, lane); break;
-        default: epilogue_role<2, 2, false, false>(a, c, warp, lane); break;
+        case 0: epilogue_role<0, 0, false, false>(a, c, warp, lane, widx, nw); break;
+        case 1: epilogue_role<0, 1, false, false>(a, c, warp, lane, widx, nw); break;
+        case 2: epilogue_role<0, 2, false, false>(a, c, warp, lane, widx, nw); break;
+        case 3: epilogue_role<1, 0, false, false>(a, c, warp, lane, widx, nw); break;
+        case 4: epilogue_role<1, 1, false, false>(a, c, warp, lane, widx, nw); break;
+        case 5: epilogue_role<1, 2, false, false>(a, c, warp, lane, widx, nw); break;
+        case 6: epilogue_role<2, 0, false, false>(a, c, warp, lane, widx, nw); break;
+        case 7: epilogue_role<2, 1, false, false>(a, c, warp, lane, widx, nw); break;
+        default: epilogue_role<2, 2, false, false>(a, c, warp, lane, widx, nw); break;
       }
     }
   }
