@@ -245,3 +245,33 @@ def test_in_place_noise_draw_matches_reference_draw_order(monkeypatch):
     err = rel_rms(fast.cpu(), literal.cpu())
     print("fast vs literal noise path: rel rms", err)
     assert err < 2e-3, err
+
+
+@pytest.mark.parametrize("name,shape,level", [
+    ("silence", (2, 1600), 0.0),          # zero variance: normalize_batch clamps the std at 1e-5 (norm.py:22-23)
+    ("ten_samples", (1, 10), 0.05),       # shorter than one latent frame: T_pad = 160, ONE GRU step
+    ("one_frame_exact", (3, 160), 0.05),  # exactly tot_ds: a full extra frame of padding (universe.py:221)
+    ("odd_batch_ragged_tail", (5, 4001), 0.05),
+])
+def test_enhance_edge_cases_vs_oracle(name, shape, level, monkeypatch):
+    """Degenerate inputs through the whole path against the CPU oracle (reference init scheme)."""
+    from open_universe_b200.config import builtin_config, instantiate
+    from oracle.universe_oracle import UniverseOracle
+    torch.manual_seed(99)
+    cfg = builtin_config("universepp_16k").model
+    m = instantiate(cfg, _recursive_=False)
+    m.eval(no_ema=True)
+    o = UniverseOracle(cfg, m.state_dict())
+    mix = det_audio(shape, 5, level=level) if level > 0 else torch.zeros(shape)
+    t_pad = shape[-1] + (m.tot_ds - shape[-1] % m.tot_ds)
+    n_steps = 3
+    noise = det_noise(n_steps, (shape[0], 1, t_pad), 6)
+    with torch.no_grad():
+        want = o.enhance(mix, n_steps=n_steps, noise=noise)
+    inject_noise(monkeypatch, noise)
+    got = m.to(DEV).enhance(mix.to(DEV), n_steps=n_steps).cpu()
+    assert got.shape == want.shape == mix.shape
+    assert torch.isfinite(got).all()
+    a = abs_rms(got, want)
+    print(name, "abs rms err", a, "out rms", float(want.square().mean().sqrt()))
+    assert a < 1e-3, a
