@@ -14,7 +14,8 @@ CASES = [("enc.0.down 32->64 s2", 32, 64, 2, 1, 3, 128160, 0.25, False),
          ("dec.3.up 128->64 x4", 128, 64, 1, 4, 3, 16020, 0.25, True),
          ("dec.4.up 64->32 x2", 64, 32, 1, 2, 3, 64080, 0.25, True),
          ("C128 k5 prelu", 128, 128, 1, 1, 5, 16020, 0.25, False),
-         ("C128 k3 add", 128, 128, 1, 1, 3, 16020, None, True)]
+         ("C128 k3 add", 128, 128, 1, 1, 3, 16020, None, True),
+         ("C128 k3", 128, 128, 1, 1, 3, 16020, None, False)]
 L = lib.load()
 g = torch.Generator().manual_seed(0)
 for name, c, cout, s_, up, taps, t, prelu, add1 in CASES:
@@ -47,7 +48,7 @@ for name, c, cout, s_, up, taps, t, prelu, add1 in CASES:
     det = trbuf[1024:1024 + 32].cpu().view(8, 4)
     tr = tr.cpu()
     t0 = int(tr[tr > 0].min())
-    per = [float((tr[r, 12:40, e] - tr[r, 11:39, e]).float().mean()) for r, e in ((0, 1), (2, 2), (1, 3), (3, 3))]
+    per = [float((tr[r, 5:12, e] - tr[r, 4:11, e]).float().mean()) for r, e in ((0, 1), (2, 2), (1, 3), (3, 3))]
     print(f"== {name}: {us:.1f} us; steady-state cycles per tile: producer {per[0]:.0f} transform {per[1]:.0f} "
           f"mma {per[2]:.0f} epilogue {per[3]:.0f}; cycles relative to first stamp (CTA 0)")
     if int(det.max()) > 0:
@@ -56,7 +57,7 @@ for name, c, cout, s_, up, taps, t, prelu, add1 in CASES:
         for i in range(8):
             print("   item", i, " ".join(f"{int(v) - d0:7d}" if v > 0 else "      -" for v in det[i]))
     print("tile | P:empty_ok issued | X:full0 fullN ready | M:tmem_ok ready0 readyN commit | E:wait full ldone stored")
-    for i in range(6, 12):
+    for i in range(3, 8):
         row = []
         for role, nev in ((0, 2), (2, 3), (1, 4), (3, 4)):
             row.append(" ".join(f"{int(tr[role, i, e]) - t0:8d}" if tr[role, i, e] > 0 else "       -" for e in range(nev)))
