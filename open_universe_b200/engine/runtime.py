@@ -68,15 +68,13 @@ def pack_conv_weights(fc, device):
     w = torch.zeros(taps, kpad, npad, dtype=torch.float32, device=device)
     w[:, :k, :n] = src
     w = w.reshape(taps, kpad // 8, 8, npad).permute(0, 1, 3, 2).contiguous()
-    out = {"w": w.to(torch.bfloat16), "bias": fc.bias.to(device).contiguous(), "kpad": kpad,
-           "npad": npad, "w_tc": None}
-    if True:   # K blocks of the tcgen05 path: c' = r*cin + ci split in channel blocks of the input
-        cb = channel_block(fc.cin)
-        wt = torch.zeros(taps, k, npad, dtype=torch.float32, device=device)
-        wt[:, :, :n] = src
-        wt = wt.reshape(taps, k // cb, cb, npad).permute(0, 1, 3, 2).contiguous()
-        out["w_tc"] = wt.to(torch.bfloat16)
-    return out
+    # K blocks of the tcgen05 path: c' = r*cin + ci split in channel blocks of the input layout
+    cb = channel_block(fc.cin)
+    wt = torch.zeros(taps, k, npad, dtype=torch.float32, device=device)
+    wt[:, :, :n] = src
+    wt = wt.reshape(taps, k // cb, cb, npad).permute(0, 1, 3, 2).contiguous()
+    return {"w": w.to(torch.bfloat16), "bias": fc.bias.to(device).contiguous(), "kpad": kpad,
+            "npad": npad, "w_tc": wt.to(torch.bfloat16)}
 
 
 def alloc_buffers(prog, device, skip=()):
