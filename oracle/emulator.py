@@ -93,7 +93,13 @@ def run_output(op, bufs, x, coef=None, noise=None):
     return net, x_new
 
 
+def _h16(x):
+    return x.to(torch.float16).float()
+
+
 def run_gru(op, bufs, quant=False):
+    """quant: the recurrent product W_hh . h_{t-1} takes fp16-rounded operands (fp32 accumulate), as
+    ou_gru_bidir's tensor-core kernel does; gates, the state update and h itself stay fp32."""
     gx = bufs[op.src]                                  # (B, T, 6H)
     B, T, _ = gx.shape
     H = op.hidden
@@ -101,10 +107,12 @@ def run_gru(op, bufs, quant=False):
     for d in range(2):
         xp = gx[:, :, d * 3 * H: (d + 1) * 3 * H]
         w, b = op.w_hh[d], op.b_hh[d]
+        if quant:
+            w = _h16(w)
         h = gx.new_zeros(B, H)
         out = gx.new_zeros(B, T, H)
         for t in (range(T) if d == 0 else range(T - 1, -1, -1)):
-            hp = h @ w.t() + b
+            hp = (_h16(h) if quant else h) @ w.t() + b
             r = torch.sigmoid(xp[:, t, :H] + hp[:, :H])
             z = torch.sigmoid(xp[:, t, H:2 * H] + hp[:, H:2 * H])
             n = torch.tanh(xp[:, t, 2 * H:] + r * hp[:, 2 * H:])
