@@ -34,8 +34,22 @@ def needs_build():
 
 
 def build(force=False, verbose=False):
+    """Compile and link in-tree.  Serialised across processes with a file lock: the ranks of a torchrun
+    launch all call ``lib.load()`` at start-up and must not run nvcc into the same files at once."""
     if not force and not needs_build():
         return LIB
+    import fcntl
+    with open(CSRC / ".build.lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():      # another rank built it while we waited
+                return LIB
+            return _build_locked(verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose):
     nvcc = _nvcc()
     objs = []
 
@@ -51,10 +65,12 @@ def build(force=False, verbose=False):
 
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    cmd = [nvcc, "-shared", "-o", str(LIB), *map(str, objs), "-lcudart"]
+    tmp = LIB.with_suffix(".so.tmp")                 # link aside, then rename: readers never see half a file
+    cmd = [nvcc, "-shared", "-o", str(tmp), *map(str, objs), "-lcudart"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    os.replace(tmp, LIB)
     return LIB
 
 
