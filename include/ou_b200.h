@@ -14,9 +14,12 @@
  *   - all pointers are DEVICE pointers unless stated otherwise;
  *   - ou_last_error() returns a thread-local human-readable message for the last failure.
  *
- * Activation layout ("blocked"): bf16 [B][C/CB][T][CB], CB = largest of {64, 32, 16} dividing C --
+ * Activation layout ("blocked"): 16-bit "act" elements [B][C/CB][T][CB], CB = largest of {64, 32, 16} dividing C --
  *   channel c of time step t of clip b lives at ((b * (C/CB) + c/CB) * T + t) * CB + c%CB
  *   (channels-last within blocks of CB channels; C must be a multiple of 16).
+ *   The element type of activations and packed conv weights is a build-time policy reported by
+ *   ou_act_dtype(): IEEE fp16 by default (11-bit significand = the TF32 the reference's cuDNN path
+ *   uses), act when built with -DOU_ACT_BF16.  "act" below means that type.
  * Signals are fp32 [B][T]; GRU pre-activations fp32 time-major [B][T][N].
  */
 #ifndef OU_B200_H
@@ -44,6 +47,12 @@ int ou_last_error(char* buf, size_t n);
 /* Number of kernels launched by this library in the calling process since load (bench.py's
  * gpu_launches claim). */
 int64_t ou_launch_count(void);
+/* Storage / tensor-core operand type of this build: 0 = IEEE fp16 (default), 1 = bf16. */
+int ou_act_dtype(void);
+/* Number of ou_conv1d calls that the tcgen05 kernel rejected (input length not a multiple of the
+ * stride: only reachable through the module-level entry points on odd lengths, never inside
+ * enhance()) and that ran on the mma.sync kernel instead.  The first one is also logged to stderr. */
+int64_t ou_conv_fallback_count(void);
 
 /* ------------------------------------------------------------------------------------------
  * Fused implicit-GEMM Conv1d.   Replaces, in ONE launch:
@@ -62,21 +71,21 @@ int64_t ou_launch_count(void);
  *   y = ((acc + bias[n] + add1[co][t]) * scale1 + add2[co][t]) * scale2
  *   y = gamma[b][co] * y + beta[b][co]                    (if gamma != NULL)
  *   y = PReLU(PReLU(y, prelu_out), prelu_out2)            (each if enabled)
- *   out (blocked bf16 (B, cout, t_out))  or  out_f32_tm (fp32 [B][rows][n], no add/film/prelu)
+ *   out (blocked act (B, cout, t_out))  or  out_f32_tm (fp32 [B][rows][n], no add/film/prelu)
  * ------------------------------------------------------------------------------------------ */
 typedef struct ou_conv_params {
-  const void* x;          /* blocked bf16 (B, cin, t_in)                                  */
-  const void* w;          /* packed bf16 [taps][kpad/8][npad][8]; element (q, c', n_) = W[n_][q][c'],
+  const void* x;          /* blocked act (B, cin, t_in)                                  */
+  const void* w;          /* packed act [taps][kpad/8][npad][8]; element (q, c', n_) = W[n_][q][c'],
                              zero padded; kpad % 32 == 0, npad % 32 == 0 (mma.sync / naive path) */
-  const void* w_tc;       /* same weights packed for the tcgen05 path, or NULL: bf16
+  const void* w_tc;       /* same weights packed for the tcgen05 path, or NULL: act
                              [taps][s*cin/CB][npad][CB], CB = channel block of the input layout
                              (K index c' = r*cin + ci cut into blocks of CB)                    */
   const float* bias;      /* fp32 [n] or NULL                                                   */
-  const void* add1;       /* blocked bf16 (B, cout, t_out) or NULL                         */
-  const void* add2;       /* blocked bf16 (B, cout, t_out) or NULL                         */
+  const void* add1;       /* blocked act (B, cout, t_out) or NULL                         */
+  const void* add2;       /* blocked act (B, cout, t_out) or NULL                         */
   const float* gamma;     /* fp32, element (b, co) at gamma[b*film_bstride + co], or NULL       */
   const float* beta;      /* fp32, same indexing                                                */
-  void* out;              /* blocked bf16 (B, cout, t_out) or NULL                         */
+  void* out;              /* blocked act (B, cout, t_out) or NULL                         */
   float* out_f32_tm;      /* fp32 [B][rows][n] or NULL (exactly one of out / out_f32_tm)        */
   int32_t batch, cin, t_in;
   int32_t s, taps, tap_off;
@@ -96,8 +105,8 @@ int ou_conv1d(const ou_conv_params* p, void* stream);
  * that reads the block input (and the conditioning tensor) once and writes the block output once;
  * the two intermediate activations stay in shared memory.  Replaces the middle of
  * ConvBlock.forward, networks/universe/blocks.py:385-399:
- *   c1 = PReLU(FiLM((conv1_k5(PReLU(x, prelu_in)) + b1 [+ sc]) * scale1), prelu_mid1)   (bf16)
- *   c2 = PReLU(conv2_k3(c1) + b2, prelu_mid2)                                            (bf16)
+ *   c1 = PReLU(FiLM((conv1_k5(PReLU(x, prelu_in)) + b1 [+ sc]) * scale1), prelu_mid1)   (act)
+ *   c2 = PReLU(conv2_k3(c1) + b2, prelu_mid2)                                            (act)
  *   v  = (conv3_k3(c2) + b3 + x) * scale3  -> PReLU(prelu_out) -> PReLU(prelu_out2)  (each if enabled)
  * All convs are 'same' (zero padded) C -> C channels; FiLM = gamma[b][c] * y + beta[b][c] when gamma
  * is not NULL.  Rounding points are those of three consecutive ou_conv1d calls.
@@ -105,17 +114,17 @@ int ou_conv1d(const ou_conv_params* p, void* stream);
  * caller runs the three ou_conv1d launches instead).
  * ------------------------------------------------------------------------------------------ */
 typedef struct ou_trunk_params {
-  const void* x;            /* blocked bf16 (B, C, t): raw block input                          */
+  const void* x;            /* blocked act (B, C, t): raw block input                          */
   const void* w1;           /* ou_conv_params.w_tc packing of conv1 / conv2 / conv3:            */
-  const void* w2;           /*   bf16 [taps][1][C][C]  (tap, out channel, in channel)            */
+  const void* w2;           /*   act [taps][1][C][C]  (tap, out channel, in channel)            */
   const void* w3;
   const float* b1;          /* fp32 [C] each                                                     */
   const float* b2;
   const float* b3;
-  const void* sc;           /* blocked bf16 (B, C, t) or NULL                                    */
+  const void* sc;           /* blocked act (B, C, t) or NULL                                    */
   const float* gamma;       /* fp32, element (b, c) at gamma[b*film_bstride + c], or NULL        */
   const float* beta;
-  void* out;                /* blocked bf16 (B, C, t)                                            */
+  void* out;                /* blocked act (B, C, t)                                            */
   int32_t batch, channels, t;
   int32_t taps1, taps2, taps3;
   int32_t film_bstride;
@@ -135,7 +144,7 @@ int ou_conv1d_naive(const ou_conv_params* p, void* stream);
  * Replaces ScoreNetwork.input_conv (score.py:239-241,285) + `w_in * x` of _edm_score_wrapper
  * (universe.py:197-203), and ConditionerNetwork.input_conv (condition.py:290-295,361).
  *   out[co][t] = bias[co] + sum_k w[co][k] * in_scale[b] * x[b][t + k - k/2]
- * x fp32 [B][t]; w fp32 [cout][k]; in_scale fp32 [B] or NULL; out blocked bf16 (B, cout, t).
+ * x fp32 [B][t]; w fp32 [cout][k]; in_scale fp32 [B] or NULL; out blocked act (B, cout, t).
  * ------------------------------------------------------------------------------------------ */
 int ou_input_conv(const float* x, const float* w, const float* bias, const float* in_scale,
                   void* out, int batch, int t, int cout, int k, void* stream);
@@ -146,7 +155,7 @@ int ou_input_conv(const float* x, const float* w, const float* bias, const float
  * (universe.py:204-206) and the reverse-SDE update (universe.py:337-339, 342-343):
  *   net[b][t]  = bias + sum_{ci,k} w[ci][k] * src[ci][t + k - k/2]      (t < t_src, else 0)
  *   xout[b][t] = ca[b]*x[b][t] + cb[b]*net[b][t] + cc[b]*noise[b][t]    (t < t_sig)
- * src blocked bf16 (B, cin, t_src) (already activated by the producer); w fp32 [cin][k];
+ * src blocked act (B, cin, t_src) (already activated by the producer); w fp32 [cin][k];
  * coef fp32 [B][3] = (ca, cb, cc) or NULL; noise fp32 [B][t_sig] or NULL; net_out fp32 [B][t_sig]
  * or NULL; x / xout fp32 [B][t_sig] (may alias) or NULL when coef is NULL.
  * ------------------------------------------------------------------------------------------ */
@@ -161,7 +170,7 @@ int ou_output_sde(const void* src, const float* w, float bias, const float* coef
  *   w_hh  fp32 [2][3H][H],  b_hh fp32 [2][3H]
  *   r = s(gx_r + W_hr h + b_hr); z = s(gx_z + W_hz h + b_hz); n = tanh(gx_n + r*(W_hn h + b_hn));
  *   h' = (1-z)*n + z*h; h0 = 0; backward direction runs t = T-1..0
- *   out blocked bf16 (B, 2H, T) = ((h_fwd | h_bwd) + add) * scale   (add blocked or NULL)
+ *   out blocked act (B, 2H, T) = ((h_fwd | h_bwd) + add) * scale   (add blocked or NULL)
  * ------------------------------------------------------------------------------------------ */
 int ou_gru_bidir(const float* gx, const float* w_hh, const float* b_hh, const void* add, float scale,
                  void* out, int batch, int t, int hidden, void* stream);
@@ -179,7 +188,7 @@ int ou_gru_bidir(const float* gx, const float* w_hh, const float* b_hh, const vo
  *                    power fp32 [B*frames][n_fft/2+1] scratch, overwritten.
  *   ou_mel_finalize: per clip scale = 1 / max(sqrt(mean_frames energy), 1e-5); writes the
  *                    normalised mel as fp32 [B][n_mels][frames] (in place allowed, or NULL) and
- *                    blocked bf16 (B, n_mels, frames) (or NULL).
+ *                    blocked act (B, n_mels, frames) (or NULL).
  * ------------------------------------------------------------------------------------------ */
 int ou_mel_power(const float* x, const float* window, const float* fb, const float* dft, float* power,
                  float* mel, float* energy, int batch, int t, int n_fft, int hop, int n_mels,
@@ -220,7 +229,7 @@ int ou_pad_normalize(const float* mix, float* out, float* stats, int batch, int 
 int ou_unpad_limit(const float* x, const float* mix_rms, float* out, int batch, int t_pad,
                    int pad_left, int t_valid, int t, void* stream);
 
-/* Layout converters between the reference's (B, C, T) fp32 tensors and the blocked bf16 layout
+/* Layout converters between the reference's (B, C, T) fp32 tensors and the blocked act layout
  * (module-level APIs: ScoreNetwork.forward's `cond` list, ConditionerNetwork's outputs). */
 int ou_pack_blocked(const float* src, void* dst, int batch, int channels, int t, void* stream);
 int ou_unpack_blocked(const void* src, float* dst, int batch, int channels, int t, void* stream);
@@ -234,7 +243,7 @@ int ou_film_f32(const float* x, const float* y, float* out, int batch, int chann
  * the k-tap 'same' convolution to ONE channel of UniverseGAN.signal_decoupling_layer
  * (universe_gan.py:117-126; PReLU_Conv.forward with act_type snake / snakebeta, blocks.py:205-227):
  * the `aux_to_wav` step of enhance(use_aux_signal=True / warm_start=n) (universe.py:317-331).
- *   x            activations, bf16 blocked [B][C/CB][T][CB] (x_blocked != 0) or fp32 [B][C][T]
+ *   x            activations, act blocked [B][C/CB][T][CB] (x_blocked != 0) or fp32 [B][C][T]
  *   alpha, beta  fp32 [C] Snake parameters (beta NULL = Snake, else SnakeBeta); exp() applied when
  *                logscale != 0 (snake.py:52-62, 116-124)
  *   up_kernel    fp32 [2][up_len]   torchaudio Resample(1 -> 2) `kernel` buffer (up_len odd)

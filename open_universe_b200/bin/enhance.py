@@ -156,6 +156,7 @@ def main(argv=None):
     if not torch.cuda.is_available():
         raise RuntimeError("CUDA is not available and there is no CPU fallback")
     device = torch.device(args.device)
+    torch.cuda.set_device(device)
     model = inference_utils.load_model(args.model, device=device, strict=args.model_strict,
                                        hf_token=args.hf_token)
     rng = torch.Generator(device=device)

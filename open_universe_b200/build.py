@@ -12,7 +12,10 @@ from concurrent.futures import ThreadPoolExecutor
 from pathlib import Path
 
 CSRC = Path(__file__).resolve().parent / "csrc"
-LIB = CSRC / "libou_b200.so"
+# OU_ACT_BF16=1 builds (and engine.lib loads) the bf16 storage policy as a separate library for A/B
+# runs; the product default is fp16 storage (csrc/common.cuh)
+BF16_VARIANT = os.environ.get("OU_ACT_BF16", "0") not in ("", "0")
+LIB = CSRC / ("libou_b200_bf16.so" if BF16_VARIANT else "libou_b200.so")
 SOURCES = ["api.cu", "conv.cu", "conv_tc.cu", "conv_trunk.cu", "gru.cu", "signal.cu", "mel.cu", "snake.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
@@ -54,8 +57,9 @@ def _build_locked(verbose):
     objs = []
 
     def compile_one(src):
-        obj = CSRC / (Path(src).stem + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-c", str(CSRC / src), "-o", str(obj)]
+        obj = CSRC / (Path(src).stem + (".bf16.o" if BF16_VARIANT else ".o"))
+        cmd = [nvcc, *NVCC_FLAGS, *(["-DOU_ACT_BF16"] if BF16_VARIANT else []), "-c", str(CSRC / src),
+               "-o", str(obj)]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")

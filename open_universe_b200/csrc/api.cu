@@ -6,6 +6,7 @@
 namespace ou {
 static thread_local char g_err[512] = "";
 std::atomic<int64_t> g_launches{0};
+std::atomic<int64_t> g_conv_fallbacks{0};
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -25,3 +26,7 @@ extern "C" int ou_last_error(char* buf, size_t n) {
 }
 
 extern "C" int64_t ou_launch_count(void) { return ou::g_launches.load(); }
+
+extern "C" int ou_act_dtype(void) { return OU_ACT_IS_BF16; }
+
+extern "C" int64_t ou_conv_fallback_count(void) { return ou::g_conv_fallbacks.load(); }

@@ -1,6 +1,7 @@
 // Shared helpers for libou_b200.so (sm_100a only).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -14,6 +15,7 @@ namespace ou {
 
 void set_error(const char* fmt, ...);
 extern std::atomic<int64_t> g_launches;
+extern std::atomic<int64_t> g_conv_fallbacks;
 
 inline int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
@@ -22,6 +24,41 @@ inline int check_launch(const char* what) {
     return OU_ERR_CUDA;
   }
   g_launches.fetch_add(1, std::memory_order_relaxed);
+  return OU_OK;
+}
+
+// Per-device caches (a process may drive several GPUs: cudaFuncSetAttribute and the SM count are
+// per device, so a per-process `static` would leave device 1 unconfigured after device 0 ran).
+constexpr int OU_MAX_DEVICES = 64;
+inline int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= OU_MAX_DEVICES) dev = 0;
+  return dev;
+}
+inline int num_sms() {
+  static std::atomic<int> cache[OU_MAX_DEVICES];
+  const int dev = current_device();
+  int n = cache[dev].load(std::memory_order_relaxed);
+  if (n == 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cache[dev].store(n, std::memory_order_relaxed);
+  }
+  return n;
+}
+struct SmemConfig {
+  std::atomic<size_t> configured[OU_MAX_DEVICES];
+};
+// raise the dynamic shared-memory limit of `kern` on the current device to at least `smem` bytes
+template <typename K>
+inline int ensure_smem(K kern, size_t smem, SmemConfig& cfg, const char* what) {
+  const int dev = current_device();
+  if (smem <= cfg.configured[dev].load(std::memory_order_relaxed)) return OU_OK;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) {
+    set_error("%s: cudaFuncSetAttribute(%zu): %s", what, smem, cudaGetErrorString(e));
+    return OU_ERR_CUDA;
+  }
+  cfg.configured[dev].store(smem, std::memory_order_relaxed);
   return OU_OK;
 }
 
@@ -48,13 +85,49 @@ __host__ __device__ inline size_t cl_off(int b, int c, int t, int channels, int 
 
 __device__ __forceinline__ float prelu_f(float x, float a) { return x >= 0.f ? x : a * x; }
 
-__device__ __forceinline__ float2 bf2_to_f2(uint32_t v) {
+// ---- storage / tensor-core operand type of every activation and conv weight ("act") ----
+// Default: IEEE fp16 -- the 11-bit significand of the TF32 the reference's own CUDA path computes its
+// convolutions in (cuDNN, allow_tf32), 8x finer than bf16 at the same tcgen05 kind::f16 throughput and
+// the same bytes.  Measured (tools/precision_study.py, profiles/README.md): one score-network
+// evaluation deviates 1e-3..5e-3 relative from the fp32 oracle with fp16, 0.9e-2..4e-2 with bf16.
+// Conversions to fp16 saturate (cvt.rn.satfinite) instead of producing inf.  -DOU_ACT_BF16 builds the
+// bf16 policy for A/B runs.
+#ifdef OU_ACT_BF16
+typedef __nv_bfloat16 act_t;
+#define OU_ACT_IS_BF16 1
+#define OU_ACT_PTX "bf16x2"
+__device__ __forceinline__ float act_to_f(act_t v) { return __bfloat162float(v); }
+__device__ __forceinline__ act_t f_to_act(float v) { return __float2bfloat16(v); }
+__device__ __forceinline__ float2 act2_to_f2(uint32_t v) {
   __nv_bfloat162 h = *reinterpret_cast<__nv_bfloat162*>(&v);
   return __bfloat1622float2(h);
 }
-__device__ __forceinline__ uint32_t f2_to_bf2(float a, float b) {
+__device__ __forceinline__ uint32_t f2_to_act2(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
+}
+#else
+typedef __half act_t;
+#define OU_ACT_IS_BF16 0
+#define OU_ACT_PTX "f16x2"
+__device__ __forceinline__ float act_to_f(act_t v) { return __half2float(v); }
+__device__ __forceinline__ float2 act2_to_f2(uint32_t v) {
+  __half2 h = *reinterpret_cast<__half2*>(&v);
+  return __half22float2(h);
+}
+__device__ __forceinline__ uint32_t f2_to_act2(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+__device__ __forceinline__ act_t f_to_act(float v) {
+  return __ushort_as_half((unsigned short)(f2_to_act2(v, 0.f) & 0xFFFFu));
+}
+#endif
+__device__ __forceinline__ unsigned short act_bits(act_t v) { return *reinterpret_cast<unsigned short*>(&v); }
+__device__ __forceinline__ float act_bits_to_f(unsigned short b) {
+  act_t v = *reinterpret_cast<act_t*>(&b);
+  return act_to_f(v);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -74,3 +147,5 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 }  // namespace ou
+
+using ou::act_t;   // the extern "C" entry points live outside the namespace

@@ -43,10 +43,15 @@ __device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* smem) 
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
                : "r"(s));
 }
-__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0,
+#if OU_ACT_IS_BF16
+#define OU_MMA_SYNC_OP "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32"
+#else
+#define OU_MMA_SYNC_OP "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32"
+#endif
+__device__ __forceinline__ void mma_act(float (&c)[4], const uint32_t (&a)[4], uint32_t b0,
                                          uint32_t b1) {
   asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, "
+      OU_MMA_SYNC_OP " {%0,%1,%2,%3}, {%4,%5,%6,%7}, "
       "{%8,%9}, {%0,%1,%2,%3};\n"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
@@ -71,14 +76,14 @@ __device__ __forceinline__ void epilogue_pair(const ou_conv_params& p, int b, in
   if (t >= p.t_out) return;
   const size_t off = cl_off(b, co, t, p.cout, p.t_out, cl_cb(p.cout));
   if (p.add1) {
-    float2 a = bf2_to_f2(*reinterpret_cast<const uint32_t*>((const __nv_bfloat16*)p.add1 + off));
+    float2 a = act2_to_f2(*reinterpret_cast<const uint32_t*>((const act_t*)p.add1 + off));
     v0 += a.x;
     v1 += a.y;
   }
   v0 *= p.scale1;
   v1 *= p.scale1;
   if (p.add2) {
-    float2 a = bf2_to_f2(*reinterpret_cast<const uint32_t*>((const __nv_bfloat16*)p.add2 + off));
+    float2 a = act2_to_f2(*reinterpret_cast<const uint32_t*>((const act_t*)p.add2 + off));
     v0 += a.x;
     v1 += a.y;
   }
@@ -98,7 +103,7 @@ __device__ __forceinline__ void epilogue_pair(const ou_conv_params& p, int b, in
     v0 = prelu_f(v0, p.prelu_out2);
     v1 = prelu_f(v1, p.prelu_out2);
   }
-  *reinterpret_cast<uint32_t*>((__nv_bfloat16*)p.out + off) = f2_to_bf2(v0, v1);
+  *reinterpret_cast<uint32_t*>((act_t*)p.out + off) = f2_to_act2(v0, v1);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -129,8 +134,8 @@ __global__ void __launch_bounds__(NTHREADS) conv1d_mma_kernel(const ConvArgs a) 
   const int n0 = blockIdx.y * BN;
   const int b = blockIdx.z;
 
-  const __nv_bfloat16* xg = (const __nv_bfloat16*)p.x + (size_t)b * a.cin_chunks * p.t_in * 8;
-  const __nv_bfloat16* wg = (const __nv_bfloat16*)p.w;
+  const act_t* xg = (const act_t*)p.x + (size_t)b * a.cin_chunks * p.t_in * 8;
+  const act_t* wg = (const act_t*)p.w;
   const int cbi = cl_cb(p.cin);
 
   auto load_stage = [&](int kb, int stage) {
@@ -149,7 +154,7 @@ __global__ void __launch_bounds__(NTHREADS) conv1d_mma_kernel(const ConvArgs a) 
       const int j = m0 + rr + p.tap_off;
       const long t = (long)j * p.s + r;
       valid = valid && j >= 0 && t < p.t_in;
-      const __nv_bfloat16* src =
+      const act_t* src =
           valid ? xg + ((size_t)((cic * 8) / cbi) * p.t_in + t) * cbi + ((cic * 8) % cbi) : xg;
       cp_async16(As + (size_t)i * 16, src, valid);
     }
@@ -203,8 +208,8 @@ __global__ void __launch_bounds__(NTHREADS) conv1d_mma_kernel(const ConvArgs a) 
         uint32_t* w = reinterpret_cast<uint32_t*>(&v);
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-          float2 f = bf2_to_f2(w[k]);
-          w[k] = f2_to_bf2(prelu_f(f.x, slope), prelu_f(f.y, slope));
+          float2 f = act2_to_f2(w[k]);
+          w[k] = f2_to_act2(prelu_f(f.x, slope), prelu_f(f.y, slope));
         }
         *reinterpret_cast<uint4*>(As + (size_t)i * 16) = v;
       }
@@ -228,8 +233,8 @@ __global__ void __launch_bounds__(NTHREADS) conv1d_mma_kernel(const ConvArgs a) 
           ldmatrix_x4(bf, src);
 #pragma unroll
           for (int mt = 0; mt < MT; mt++) {
-            mma_bf16(acc[mt][np * 2], af[mt], bf[0], bf[1]);
-            mma_bf16(acc[mt][np * 2 + 1], af[mt], bf[2], bf[3]);
+            mma_act(acc[mt][np * 2], af[mt], bf[0], bf[1]);
+            mma_act(acc[mt][np * 2 + 1], af[mt], bf[2], bf[3]);
           }
         }
       }
@@ -261,8 +266,8 @@ __global__ void conv1d_naive_kernel(const ConvArgs a) {
     const int j = rest % p.rows;
     const int b = rest / p.rows;
     const int n = np * 2;
-    const __nv_bfloat16* xg = (const __nv_bfloat16*)p.x + (size_t)b * a.cin_chunks * p.t_in * 8;
-    const __nv_bfloat16* wg = (const __nv_bfloat16*)p.w;
+    const act_t* xg = (const act_t*)p.x + (size_t)b * a.cin_chunks * p.t_in * 8;
+    const act_t* wg = (const act_t*)p.w;
     const int cbi = cl_cb(p.cin);
     float v0 = 0.f, v1 = 0.f;
     for (int q = 0; q < p.taps; q++) {
@@ -272,12 +277,12 @@ __global__ void conv1d_naive_kernel(const ConvArgs a) {
         const long t = (long)jj * p.s + r;
         if (t >= p.t_in) continue;
         for (int ci = 0; ci < p.cin; ci++) {
-          float x = __bfloat162float(xg[((size_t)(ci / cbi) * p.t_in + t) * cbi + (ci % cbi)]);
-          if (p.has_prelu_in) x = __bfloat162float(__float2bfloat16(prelu_f(x, p.prelu_in)));
+          float x = act_to_f(xg[((size_t)(ci / cbi) * p.t_in + t) * cbi + (ci % cbi)]);
+          if (p.has_prelu_in) x = act_to_f(f_to_act(prelu_f(x, p.prelu_in)));
           const int cp = r * p.cin + ci;
           const size_t wo = (((size_t)q * (p.kpad >> 3) + (cp >> 3)) * p.npad + n) * 8 + (cp & 7);
-          v0 += x * __bfloat162float(wg[wo]);
-          v1 += x * __bfloat162float(wg[wo + 8]);
+          v0 += x * act_to_f(wg[wo]);
+          v1 += x * act_to_f(wg[wo + 8]);
         }
       }
     }
@@ -314,16 +319,8 @@ template <int BN, int STAGES>
 static int launch_mma(const ConvArgs& a, cudaStream_t st) {
   const ou_conv_params& p = a.p;
   const size_t smem = (size_t)STAGES * (KCH * a.arows * 16 + p.taps * KCH * BN * 16);
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv1d_mma_kernel<BN, STAGES>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) {
-      set_error("ou_conv1d: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
-      return OU_ERR_CUDA;
-    }
-    configured = smem;
-  }
+  static SmemConfig cfg;
+  if (int rc = ensure_smem(conv1d_mma_kernel<BN, STAGES>, smem, cfg, "ou_conv1d")) return rc;
   dim3 grid(ceil_div(p.rows, BM), p.npad / BN, p.batch);
   conv1d_mma_kernel<BN, STAGES><<<grid, NTHREADS, smem, st>>>(a);
   return check_launch("ou_conv1d");
@@ -355,6 +352,14 @@ extern "C" int ou_conv1d(const ou_conv_params* p, void* stream) {
   if (ou::use_tc()) {
     rc = ou::tc::launch(p, st);
     if (rc != OU_ERR_UNSUPPORTED) return rc;
+    // Only reachable from the module-level entry points on lengths that are not a multiple of the
+    // stride (enhance() pads to a multiple of the total down-sampling factor): counted and logged
+    // once, never silent.
+    if (ou::g_conv_fallbacks.fetch_add(1, std::memory_order_relaxed) == 0)
+      fprintf(stderr,
+              "libou_b200: ou_conv1d: tcgen05 kernel does not cover this geometry (cin=%d s=%d taps=%d "
+              "t_in=%d); using the mma.sync kernel (ou_conv_fallback_count() counts these)\n",
+              p->cin, p->s, p->taps, p->t_in);
   }
   if (p->npad % 128 == 0) return ou::launch_mma<128, 3>(a, st);
   if (p->npad % 64 == 0) return ou::launch_mma<64, 3>(a, st);

@@ -284,12 +284,12 @@ __device__ __forceinline__ void transform_role(const TcArgs& a, const Ctx& c, in
       for (; i + 3 * 128 < nvec; i += 4 * 128) {   // 4 independent vectors in flight
         uint4 v0 = lds_u4(base + (uint32_t)i * 16), v1 = lds_u4(base + (uint32_t)(i + 128) * 16);
         uint4 v2 = lds_u4(base + (uint32_t)(i + 256) * 16), v3 = lds_u4(base + (uint32_t)(i + 384) * 16);
-        sts_u4(base + (uint32_t)i * 16, prelu_bf16x8(v0, slope, slope_lo));
-        sts_u4(base + (uint32_t)(i + 128) * 16, prelu_bf16x8(v1, slope, slope_lo));
-        sts_u4(base + (uint32_t)(i + 256) * 16, prelu_bf16x8(v2, slope, slope_lo));
-        sts_u4(base + (uint32_t)(i + 384) * 16, prelu_bf16x8(v3, slope, slope_lo));
+        sts_u4(base + (uint32_t)i * 16, prelu_act8(v0, slope, slope_lo));
+        sts_u4(base + (uint32_t)(i + 128) * 16, prelu_act8(v1, slope, slope_lo));
+        sts_u4(base + (uint32_t)(i + 256) * 16, prelu_act8(v2, slope, slope_lo));
+        sts_u4(base + (uint32_t)(i + 384) * 16, prelu_act8(v3, slope, slope_lo));
       }
-      for (; i < nvec; i += 128) sts_u4(base + (uint32_t)i * 16, prelu_bf16x8(lds_u4(base + (uint32_t)i * 16), slope, slope_lo));
+      for (; i < nvec; i += 128) sts_u4(base + (uint32_t)i * 16, prelu_act8(lds_u4(base + (uint32_t)i * 16), slope, slope_lo));
       }
       fence_proxy_async();
       __syncwarp();
@@ -325,9 +325,9 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& a, const Ctx& c, int
   const size_t blk_stride = (size_t)t_out * cbo;
   const int n0 = c.n0;
   const int n0_ph = n0 / cout, n0_co = n0 - n0_ph * cout;
-  const __nv_bfloat16* add1 = (const __nv_bfloat16*)p.add1;
-  const __nv_bfloat16* add2 = (const __nv_bfloat16*)p.add2;
-  __nv_bfloat16* outp = (__nv_bfloat16*)p.out;
+  const act_t* add1 = (const act_t*)p.add1;
+  const act_t* add2 = (const act_t*)p.add2;
+  act_t* outp = (act_t*)p.out;
   const float s1 = p.scale1, s2 = p.scale2;
   const float slope1 = p.prelu_out, slope2 = p.prelu_out2;
   const bool has_film = FILM;
@@ -465,7 +465,7 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& a, const Ctx& c, int
           float a0 = __uint_as_float(r[4 * i]), a1 = __uint_as_float(r[4 * i + 1]);
           float a2 = __uint_as_float(r[4 * i + 2]), a3 = __uint_as_float(r[4 * i + 3]);
           if (NADD > 0) {
-            const float2 fa = bf2_to_f2(cur1.w[2 * i]), fb = bf2_to_f2(cur1.w[2 * i + 1]);
+            const float2 fa = act2_to_f2(cur1.w[2 * i]), fb = act2_to_f2(cur1.w[2 * i + 1]);
             a0 += fa.x, a1 += fa.y, a2 += fb.x, a3 += fb.y;
           }
           a0 = fmaf(x0.x, a0, x1.x), a1 = fmaf(x0.y, a1, x1.y);
@@ -473,7 +473,7 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& a, const Ctx& c, int
           if (NADD > 1) {
             float4 x2 = make_float4(s2, s2, s2, s2);
             if (FILM) x2 = k2[i];
-            const float2 fa = bf2_to_f2(cur2.w[2 * i]), fb = bf2_to_f2(cur2.w[2 * i + 1]);
+            const float2 fa = act2_to_f2(cur2.w[2 * i]), fb = act2_to_f2(cur2.w[2 * i + 1]);
             a0 = fmaf(x2.x, fa.x, a0), a1 = fmaf(x2.y, fa.y, a1);
             a2 = fmaf(x2.z, fb.x, a2), a3 = fmaf(x2.w, fb.y, a3);
           }
@@ -489,7 +489,7 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& a, const Ctx& c, int
         }
         U8 o;
 #pragma unroll
-        for (int i = 0; i < 8; i++) o.w[i] = f2_to_bf2(v[2 * i], v[2 * i + 1]);
+        for (int i = 0; i < 8; i++) o.w[i] = f2_to_act2(v[2 * i], v[2 * i + 1]);
         stg_v8(outp + off, o);
         EPI_DETAIL(3)
       }
@@ -647,7 +647,6 @@ conv1d_tc_kernel(const TcArgs a, const __grid_constant__ CUtensorMap tm_a,
 }
 
 // ------------------------------------------------------------------------------------ host side
-static int g_num_sms = 0;
 long long* g_trace = nullptr;
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -683,12 +682,7 @@ int plan(const ou_conv_params* p, TcArgs* a) {
     }
   if (!bn || p->cin % 16 || p->cout % 16) return OU_ERR_UNSUPPORTED;
   if (p->add2 && !p->add1) return OU_ERR_UNSUPPORTED;
-  if (g_num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_num_sms <= 0) g_num_sms = 148;
-  }
+  const int g_num_sms = num_sms();
   a->p = *p;
   a->cb = cl_cb(p->cin);
   a->row_bytes = a->cb * 2;
@@ -735,7 +729,7 @@ int plan(const ou_conv_params* p, TcArgs* a) {
   if (as < 2) return OU_ERR_UNSUPPORTED;
   a->a_stages = as > MAX_A_STAGES ? MAX_A_STAGES : as;
   // instruction descriptor: D=f32, A=B=bf16, K-major both, N = bn, M = 128
-  a->idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+  a->idesc = (1u << 4) | ((uint32_t)OU_ACT_IS_BF16 << 7) | ((uint32_t)OU_ACT_IS_BF16 << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
   uint32_t cols = 32;
   while (cols < (uint32_t)(2 * bn * a->m_sub)) cols <<= 1;
   a->tmem_cols = cols;
@@ -765,7 +759,7 @@ int launch(const ou_conv_params* p, cudaStream_t st) {
     cuuint64_t strides[4] = {rowb, rowb * p->s, rowb * p->t_in, rowb * p->t_in * a.cin_blocks};
     cuuint32_t box[5] = {(cuuint32_t)a.cb, 1, (cuuint32_t)a.arows, 1, 1};
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = g_encode(&tm_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(p->x), dims, strides,
+    CUresult r = g_encode(&tm_a, OU_TMA_ACT, 5, const_cast<void*>(p->x), dims, strides,
                           box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(a.row_bytes),
                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -779,7 +773,7 @@ int launch(const ou_conv_params* p, cudaStream_t st) {
     cuuint64_t strides[2] = {(cuuint64_t)a.row_bytes, (cuuint64_t)p->npad * a.row_bytes};
     cuuint32_t box[3] = {(cuuint32_t)a.cb, (cuuint32_t)a.bn, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = g_encode(&tm_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(p->w_tc), dims, strides,
+    CUresult r = g_encode(&tm_w, OU_TMA_ACT, 3, const_cast<void*>(p->w_tc), dims, strides,
                           box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(a.row_bytes),
                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -790,17 +784,9 @@ int launch(const ou_conv_params* p, cudaStream_t st) {
   const size_t smem = 1024 + (size_t)a.a_stages * a.a_stage_bytes + (size_t)a.b_stages * a.b_stage_bytes +
                       (3 * MAX_A_STAGES + 2 * MAX_B_STAGES + 4) * sizeof(uint64_t) + 16 +
                       (size_t)6 * a.bn * sizeof(float);
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv1d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem);
-    if (e != cudaSuccess) {
-      set_error("ou_conv1d(tc): cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
-      return OU_ERR_CUDA;
-    }
-    configured = smem;
-  }
-  int per = g_num_sms / a.n_ntiles;
+  static SmemConfig cfg;
+  if ((rc = ensure_smem(conv1d_tc_kernel, smem, cfg, "ou_conv1d(tc)"))) return rc;
+  int per = num_sms() / a.n_ntiles;
   if (per < 1) per = 1;
   if (per > a.total_m_tiles) per = a.total_m_tiles;
   a.ctas_per_ntile = per;

@@ -226,7 +226,7 @@ __device__ __forceinline__ void slot_role(const TrunkArgs& a, const Smem& sm, ui
   uint32_t a_in_hi, a_in_lo;
   split_slope(slope_in, a_in_hi, a_in_lo);
   const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(slot * SLOT_COLS);
-  __nv_bfloat16* outp = (__nv_bfloat16*)p.out;
+  act_t* outp = (act_t*)p.out;
 
   auto item_pos = [&](int n, int& b, int& t0) {
     const int item = (int)blockIdx.x + (int)gridDim.x * n;
@@ -309,11 +309,11 @@ __device__ __forceinline__ void slot_role(const TrunkArgs& a, const Smem& sm, ui
 #pragma unroll
         for (int c = 0; c < CHH; c++)
           sts_u4(swz<C>(X, (uint32_t)((sub * 128 + row + 4) * G::ROWB + (ch0 + c) * 16)),
-                 prelu_bf16x8(res[sub][c], a_in_hi, a_in_lo));
+                 prelu_act8(res[sub][c], a_in_hi, a_in_lo));
       if (row < 4) {
 #pragma unroll
         for (int c = 0; c < CHH; c++)
-          sts_u4(swz<C>(X, (uint32_t)(row * G::ROWB + (ch0 + c) * 16)), prelu_bf16x8(halo[c], a_in_hi, a_in_lo));
+          sts_u4(swz<C>(X, (uint32_t)(row * G::ROWB + (ch0 + c) * 16)), prelu_act8(halo[c], a_in_hi, a_in_lo));
       }
     }
     fence_proxy_async();
@@ -370,13 +370,13 @@ __device__ __forceinline__ void slot_role(const TrunkArgs& a, const Smem& sm, ui
           float a0 = __uint_as_float(r[e]), a1 = __uint_as_float(r[e + 1]);
           float a2 = __uint_as_float(r[e + 2]), a3 = __uint_as_float(r[e + 3]);
           if (HAS_SC) {
-            const float2 fa = bf2_to_f2(sw[2 * k]), fb = bf2_to_f2(sw[2 * k + 1]);
+            const float2 fa = act2_to_f2(sw[2 * k]), fb = act2_to_f2(sw[2 * k + 1]);
             a0 += fa.x, a1 += fa.y, a2 += fb.x, a3 += fb.y;
           }
           a0 = prelu_f(fmaf(c0.x, a0, c1.x), slope_m1), a1 = prelu_f(fmaf(c0.y, a1, c1.y), slope_m1);
           a2 = prelu_f(fmaf(c0.z, a2, c1.z), slope_m1), a3 = prelu_f(fmaf(c0.w, a3, c1.w), slope_m1);
-          ow[2 * k] = inside ? f2_to_bf2(a0, a1) : 0u;
-          ow[2 * k + 1] = inside ? f2_to_bf2(a2, a3) : 0u;
+          ow[2 * k] = inside ? f2_to_act2(a0, a1) : 0u;
+          ow[2 * k + 1] = inside ? f2_to_act2(a2, a3) : 0u;
         }
         sts_u4(swz<C>(Cb, (uint32_t)(i * G::ROWB + (ch0 + 2 * cc + h) * 16)), o);
       }
@@ -417,8 +417,8 @@ __device__ __forceinline__ void slot_role(const TrunkArgs& a, const Smem& sm, ui
           const float a1 = prelu_f(__uint_as_float(r[e + 1]) + b4.y, slope_m2);
           const float a2 = prelu_f(__uint_as_float(r[e + 2]) + b4.z, slope_m2);
           const float a3 = prelu_f(__uint_as_float(r[e + 3]) + b4.w, slope_m2);
-          ow[2 * k] = inside ? f2_to_bf2(a0, a1) : 0u;
-          ow[2 * k + 1] = inside ? f2_to_bf2(a2, a3) : 0u;
+          ow[2 * k] = inside ? f2_to_act2(a0, a1) : 0u;
+          ow[2 * k + 1] = inside ? f2_to_act2(a2, a3) : 0u;
         }
         sts_u4(swz<C>(Cb, (uint32_t)(i * G::ROWB + (ch0 + 2 * cc + h) * 16)), o);
       }
@@ -442,7 +442,7 @@ __device__ __forceinline__ void slot_role(const TrunkArgs& a, const Smem& sm, ui
       const int i = sub * 128 + row;
       const int t = t0 + i;
       const bool valid = i < G::VALID && t < T;
-      __nv_bfloat16* dst = outp + ((size_t)b * T + t) * C;
+      act_t* dst = outp + ((size_t)b * T + t) * C;
       float4 kk[4];
 #pragma unroll
       for (int j = 0; j < 4; j++) kk[j] = lds_f4(coef3 + 4u * (col0 + cc * 16 + j * 4));
@@ -457,14 +457,14 @@ __device__ __forceinline__ void slot_role(const TrunkArgs& a, const Smem& sm, ui
         for (int k = 0; k < 2; k++) {
           const float4 c1 = kk[h * 2 + k];
           const int e = h * 8 + k * 4;
-          const float2 fa = bf2_to_f2(rw[2 * k]), fb = bf2_to_f2(rw[2 * k + 1]);
+          const float2 fa = act2_to_f2(rw[2 * k]), fb = act2_to_f2(rw[2 * k + 1]);
           const float a0 = fmaf(s3, __uint_as_float(r[e]) + fa.x, c1.x);
           const float a1 = fmaf(s3, __uint_as_float(r[e + 1]) + fa.y, c1.y);
           const float a2 = fmaf(s3, __uint_as_float(r[e + 2]) + fb.x, c1.z);
           const float a3 = fmaf(s3, __uint_as_float(r[e + 3]) + fb.y, c1.w);
-          o.w[h * 4 + 2 * k] = f2_to_bf2(out_act<NPRELU>(a0, p.prelu_out, p.prelu_out2),
+          o.w[h * 4 + 2 * k] = f2_to_act2(out_act<NPRELU>(a0, p.prelu_out, p.prelu_out2),
                                          out_act<NPRELU>(a1, p.prelu_out, p.prelu_out2));
-          o.w[h * 4 + 2 * k + 1] = f2_to_bf2(out_act<NPRELU>(a2, p.prelu_out, p.prelu_out2),
+          o.w[h * 4 + 2 * k + 1] = f2_to_act2(out_act<NPRELU>(a2, p.prelu_out, p.prelu_out2),
                                              out_act<NPRELU>(a3, p.prelu_out, p.prelu_out2));
         }
       }
@@ -555,7 +555,6 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
                                   CUtensorMapFloatOOBfill);
 static EncodeTiledFn g_encode = nullptr;
-static int g_num_sms = 0;
 
 static int init_once() {
   if (!g_encode) {
@@ -568,12 +567,6 @@ static int init_once() {
     }
     g_encode = (EncodeTiledFn)fn;
   }
-  if (g_num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_num_sms <= 0) g_num_sms = 148;
-  }
   return OU_OK;
 }
 
@@ -584,7 +577,7 @@ static int encode3(CUtensorMap* tm, const void* base, int c, uint64_t d1, uint64
   cuuint64_t strides[2] = {rowb, rowb * d1};
   cuuint32_t box[3] = {(cuuint32_t)c, box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box,
+  CUresult r = g_encode(tm, OU_TMA_ACT, 3, const_cast<void*>(base), dims, strides, box,
                         estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         rowb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, promo,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -608,7 +601,7 @@ static int launch_c(const ou_trunk_params* p, cudaStream_t st) {
   a.x_boxes = 1;
   while ((G::XPAD / a.x_boxes) > 256 || G::XPAD % a.x_boxes || (G::XPAD / a.x_boxes) % 8) a.x_boxes++;
   a.x_box_rows = G::XPAD / a.x_boxes;
-  a.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(C >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  a.idesc = (1u << 4) | ((uint32_t)OU_ACT_IS_BF16 << 7) | ((uint32_t)OU_ACT_IS_BF16 << 10) | ((uint32_t)(C >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   const uint32_t sbo = 8u * G::ROWB;
   const uint32_t layout = G::ROWB == 128 ? 2u : 4u;
   a.desc_hi = ((sbo >> 4) & 0x3FFFu) | (1u << (46 - 32)) | (layout << (61 - 32));
@@ -626,16 +619,10 @@ static int launch_c(const ou_trunk_params* p, cudaStream_t st) {
   if ((rc = encode3(&tm_w3, p->w3, C, (uint64_t)C, TAPS3, C, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, "w3"))) return rc;
 
   auto kern = p->sc ? trunk_kernel<C, true> : trunk_kernel<C, false>;
-  static bool configured[2] = {false, false};
-  if (!configured[p->sc ? 1 : 0]) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
-    if (e != cudaSuccess) {
-      set_error("ou_conv_trunk: cudaFuncSetAttribute(%zu): %s", (size_t)G::SMEM, cudaGetErrorString(e));
-      return OU_ERR_CUDA;
-    }
-    configured[p->sc ? 1 : 0] = true;
-  }
-  int grid = g_num_sms < a.total_items ? g_num_sms : a.total_items;
+  static SmemConfig cfg[2];
+  if ((rc = ensure_smem(kern, (size_t)G::SMEM, cfg[p->sc ? 1 : 0], "ou_conv_trunk"))) return rc;
+  const int n_sms = num_sms();
+  int grid = n_sms < a.total_items ? n_sms : a.total_items;
   kern<<<grid, NTHREADS, G::SMEM, st>>>(a, tm_x, tm_sc, tm_w1, tm_w2, tm_w3);
   return check_launch("ou_conv_trunk");
 }

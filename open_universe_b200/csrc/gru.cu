@@ -29,8 +29,8 @@ struct GruArgs {
   const float* gx;
   const float* w_hh;
   const float* b_hh;
-  const __nv_bfloat16* add;
-  __nv_bfloat16* out;
+  const act_t* add;
+  act_t* out;
   float scale;
   int batch, t;
 };
@@ -163,8 +163,8 @@ __global__ void __launch_bounds__(3 * (H / CS) * (H / KPT)) gru_cluster_kernel(c
       const float hnew = h_buf_own_new;
       const size_t off = out_base + (size_t)t * cl_cb(2 * H);
       float v = hnew;
-      if (a.add) v += __bfloat162float(a.add[off]);
-      a.out[off] = __float2bfloat16(v * a.scale);
+      if (a.add) v += act_to_f(a.add[off]);
+      a.out[off] = f_to_act(v * a.scale);
     }
     gxr = nxr, gxz = nxz, gxn = nxn;
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -551,8 +551,8 @@ __global__ void __launch_bounds__(G16<H>::NT) gru_cluster_f16_kernel(const GruAr
 #pragma unroll
     for (int e = 0; e < 2; e++) {
       if (valid[e]) {
-        const float addv = __uint_as_float((uint32_t)ad0[e] << 16);
-        a.out[out_base[e] + (size_t)t * ocb] = __float2bfloat16((hnew[e] + addv) * a.scale);
+        const float addv = act_bits_to_f(ad0[e]);
+        a.out[out_base[e] + (size_t)t * ocb] = f_to_act((hnew[e] + addv) * a.scale);
       }
 #pragma unroll
       for (int q = 0; q < 3; q++) x0[e][q] = x1[e][q], x1[e][q] = x2[e][q];
@@ -628,7 +628,7 @@ extern "C" int ou_gru_bidir(const float* gx, const float* w_hh, const float* b_h
                             float scale, void* out, int batch, int t, int hidden, void* stream) {
   OU_REQUIRE(gx && w_hh && b_hh && out, "ou_gru_bidir: null pointer");
   OU_REQUIRE(batch > 0 && t > 0, "ou_gru_bidir: empty problem");
-  ou::GruArgs a{ou::tc::g_trace, gx, w_hh, b_hh, (const __nv_bfloat16*)add, (__nv_bfloat16*)out, scale, batch, t};
+  ou::GruArgs a{ou::tc::g_trace, gx, w_hh, b_hh, (const act_t*)add, (act_t*)out, scale, batch, t};
   cudaStream_t st = (cudaStream_t)stream;
   const int impl = ou::gru_impl();
   switch (hidden) {

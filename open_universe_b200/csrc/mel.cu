@@ -106,7 +106,7 @@ __global__ void mel_project_kernel(const float* __restrict__ power, const float*
 
 // One CTA per clip: scale = 1 / max(sqrt(mean_frames energy), 1e-5), applied to every mel bin.
 __global__ void mel_finalize_kernel(const float* __restrict__ mel, const float* __restrict__ energy,
-                                    float* __restrict__ mel_norm, __nv_bfloat16* __restrict__ blocked,
+                                    float* __restrict__ mel_norm, act_t* __restrict__ blocked,
                                     int n_mels, int frames) {
   __shared__ float red[32];
   __shared__ float s_scale;
@@ -130,7 +130,7 @@ __global__ void mel_finalize_kernel(const float* __restrict__ mel, const float* 
     const int j = i / frames, m = i - j * frames;
     if (mel_norm) mel_norm[(size_t)b * n_mels * frames + i] = v;
     if (blocked)
-      blocked[cl_off(b, j, m, n_mels, frames, cl_cb(n_mels))] = __float2bfloat16(v);
+      blocked[cl_off(b, j, m, n_mels, frames, cl_cb(n_mels))] = f_to_act(v);
   }
 }
 
@@ -199,7 +199,7 @@ extern "C" int ou_mel_finalize(const float* mel, const float* energy, float* mel
   OU_REQUIRE(batch > 0 && n_mels > 0 && frames > 0, "ou_mel_finalize: bad shape");
   OU_REQUIRE(mel_blocked == nullptr || n_mels % 16 == 0, "ou_mel_finalize: n_mels % 16 != 0");
   ou::mel_finalize_kernel<<<batch, 512, 0, (cudaStream_t)stream>>>(
-      mel, energy, mel_norm, (__nv_bfloat16*)mel_blocked, n_mels, frames);
+      mel, energy, mel_norm, (act_t*)mel_blocked, n_mels, frames);
   return ou::check_launch("ou_mel_finalize");
 }
 

@@ -13,7 +13,7 @@ template <int K>
 __global__ void __launch_bounds__(256) input_conv_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                          const float* __restrict__ bias,
                                                          const float* __restrict__ in_scale,
-                                                         __nv_bfloat16* __restrict__ out, int t_len, int cout) {
+                                                         act_t* __restrict__ out, int t_len, int cout) {
   extern __shared__ __align__(16) float sw[];  // [K][cout] weights then [cout] bias
   for (int i = threadIdx.x; i < cout * K; i += blockDim.x) sw[(i % K) * cout + i / K] = w[i];
   for (int i = threadIdx.x; i < cout; i += blockDim.x) sw[cout * K + i] = bias ? bias[i] : 0.f;
@@ -42,12 +42,12 @@ __global__ void __launch_bounds__(256) input_conv_kernel(const float* __restrict
         acc[q].z = fmaf(wv.z, xin[i], acc[q].z), acc[q].w = fmaf(wv.w, xin[i], acc[q].w);
       }
     }
-    __nv_bfloat16* dst = out + cl_off(b, c16 * 16, t, cout, t_len, cb);
-    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "r"(f2_to_bf2(acc[0].x, acc[0].y)),
-                 "r"(f2_to_bf2(acc[0].z, acc[0].w)), "r"(f2_to_bf2(acc[1].x, acc[1].y)),
-                 "r"(f2_to_bf2(acc[1].z, acc[1].w)), "r"(f2_to_bf2(acc[2].x, acc[2].y)),
-                 "r"(f2_to_bf2(acc[2].z, acc[2].w)), "r"(f2_to_bf2(acc[3].x, acc[3].y)),
-                 "r"(f2_to_bf2(acc[3].z, acc[3].w))
+    act_t* dst = out + cl_off(b, c16 * 16, t, cout, t_len, cb);
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "r"(f2_to_act2(acc[0].x, acc[0].y)),
+                 "r"(f2_to_act2(acc[0].z, acc[0].w)), "r"(f2_to_act2(acc[1].x, acc[1].y)),
+                 "r"(f2_to_act2(acc[1].z, acc[1].w)), "r"(f2_to_act2(acc[2].x, acc[2].y)),
+                 "r"(f2_to_act2(acc[2].z, acc[2].w)), "r"(f2_to_act2(acc[3].x, acc[3].y)),
+                 "r"(f2_to_act2(acc[3].z, acc[3].w))
                  : "memory");
   }
 }
@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(256) input_conv_kernel(const float* __restrict
 // re-read each row K times through L1 and ran at 2.7 TB/s).  Weights tap-major in shared memory as in
 // input_conv_kernel.
 template <int K>
-__global__ void __launch_bounds__(256) output_sde_kernel(const __nv_bfloat16* __restrict__ src,
+__global__ void __launch_bounds__(256) output_sde_kernel(const act_t* __restrict__ src,
                                                          const float* __restrict__ w, float bias,
                                                          const float* __restrict__ coef,
                                                          const float* __restrict__ x,
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(256) output_sde_kernel(const __nv_bfloat16* __
       float f[16];
 #pragma unroll
       for (int q = 0; q < 8; q++) {
-        const float2 v = bf2_to_f2(pv[q]);
+        const float2 v = act2_to_f2(pv[q]);
         f[2 * q] = v.x, f[2 * q + 1] = v.y;
       }
 #pragma unroll
@@ -205,7 +205,7 @@ __global__ void unpad_limit_kernel(const float* __restrict__ x, const float* __r
 }
 
 // ------------------------------------------------------------------------------ layout converters
-__global__ void pack_blocked_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+__global__ void pack_blocked_kernel(const float* __restrict__ src, act_t* __restrict__ dst,
                                     int channels, int t_len) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int c8 = blockIdx.y, b = blockIdx.z;
@@ -213,12 +213,12 @@ __global__ void pack_blocked_kernel(const float* __restrict__ src, __nv_bfloat16
   float f[8];
 #pragma unroll
   for (int e = 0; e < 8; e++) f[e] = src[((size_t)b * channels + c8 * 8 + e) * t_len + t];
-  uint4 v = make_uint4(f2_to_bf2(f[0], f[1]), f2_to_bf2(f[2], f[3]), f2_to_bf2(f[4], f[5]),
-                       f2_to_bf2(f[6], f[7]));
+  uint4 v = make_uint4(f2_to_act2(f[0], f[1]), f2_to_act2(f[2], f[3]), f2_to_act2(f[4], f[5]),
+                       f2_to_act2(f[6], f[7]));
   *reinterpret_cast<uint4*>(dst + cl_off(b, c8 * 8, t, channels, t_len, cl_cb(channels))) = v;
 }
 
-__global__ void unpack_blocked_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst,
+__global__ void unpack_blocked_kernel(const act_t* __restrict__ src, float* __restrict__ dst,
                                       int channels, int t_len) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int c8 = blockIdx.y, b = blockIdx.z;
@@ -228,7 +228,7 @@ __global__ void unpack_blocked_kernel(const __nv_bfloat16* __restrict__ src, flo
   const uint32_t* pv = reinterpret_cast<const uint32_t*>(&v);
 #pragma unroll
   for (int h = 0; h < 4; h++) {
-    const float2 f = bf2_to_f2(pv[h]);
+    const float2 f = act2_to_f2(pv[h]);
     dst[((size_t)b * channels + c8 * 8 + h * 2) * t_len + t] = f.x;
     dst[((size_t)b * channels + c8 * 8 + h * 2 + 1) * t_len + t] = f.y;
   }
@@ -254,7 +254,7 @@ extern "C" int ou_input_conv(const float* x, const float* w, const float* bias, 
   dim3 grid(ou::ceil_div(t, 256), batch);
   const size_t smem = (size_t)(cout * k + cout) * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
-  __nv_bfloat16* o = (__nv_bfloat16*)out;
+  act_t* o = (act_t*)out;
   switch (k) {
     case 1: ou::input_conv_kernel<1><<<grid, 256, smem, st>>>(x, w, bias, in_scale, o, t, cout); break;
     case 3: ou::input_conv_kernel<3><<<grid, 256, smem, st>>>(x, w, bias, in_scale, o, t, cout); break;
@@ -275,7 +275,7 @@ extern "C" int ou_output_sde(const void* src, const float* w, float bias, const 
   dim3 grid(ou::ceil_div(t_sig, 8 * (32 - 2 * (k / 2))), batch);   // 8 warps x (32 - halo) outputs per CTA
   const size_t smem = (size_t)cin * k * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
-  const __nv_bfloat16* s = (const __nv_bfloat16*)src;
+  const act_t* s = (const act_t*)src;
   switch (k) {
     case 1: ou::output_sde_kernel<1><<<grid, 256, smem, st>>>(s, w, bias, coef, x, noise, xout, net_out, cin, t_src, t_sig); break;
     case 3: ou::output_sde_kernel<3><<<grid, 256, smem, st>>>(s, w, bias, coef, x, noise, xout, net_out, cin, t_src, t_sig); break;
@@ -310,7 +310,7 @@ extern "C" int ou_pack_blocked(const float* src, void* dst, int batch, int chann
   OU_REQUIRE(src && dst, "ou_pack_blocked: null pointer");
   OU_REQUIRE(batch > 0 && t > 0 && channels > 0 && channels % 16 == 0, "ou_pack_blocked: bad shape");
   dim3 grid(ou::ceil_div(t, 256), channels / 8, batch);
-  ou::pack_blocked_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, channels, t);
+  ou::pack_blocked_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, (act_t*)dst, channels, t);
   return ou::check_launch("ou_pack_blocked");
 }
 
@@ -319,7 +319,7 @@ extern "C" int ou_unpack_blocked(const void* src, float* dst, int batch, int cha
   OU_REQUIRE(src && dst, "ou_unpack_blocked: null pointer");
   OU_REQUIRE(batch > 0 && t > 0 && channels > 0 && channels % 16 == 0, "ou_unpack_blocked: bad shape");
   dim3 grid(ou::ceil_div(t, 256), channels / 8, batch);
-  ou::unpack_blocked_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src, dst,
+  ou::unpack_blocked_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const act_t*)src, dst,
                                                                     channels, t);
   return ou::check_launch("ou_unpack_blocked");
 }

@@ -66,12 +66,12 @@ __global__ void __launch_bounds__(SNK_THREADS) alias_free_snake_kernel(const Sna
 
   // ---- x tile
   if (a.x_blocked) {
-    const __nv_bfloat16* xb = (const __nv_bfloat16*)a.x;
+    const act_t* xb = (const act_t*)a.x;
     const int cb = cl_cb(C);
     for (int i = tid; i < C * a.nx; i += SNK_THREADS) {
       const int c = i % C, p = i / C;     // channel fastest: contiguous in the blocked layout
       const int t = x0 + p;
-      xs[c * ldx + p] = (t >= 0 && t < T) ? __bfloat162float(xb[cl_off(b, c, t, C, T, cb)]) : 0.f;
+      xs[c * ldx + p] = (t >= 0 && t < T) ? act_to_f(xb[cl_off(b, c, t, C, T, cb)]) : 0.f;
     }
   } else {
     const float* xf = (const float*)a.x;
@@ -160,16 +160,9 @@ extern "C" int ou_alias_free_snake(const void* x, int x_blocked, const float* al
     ou::set_error("ou_alias_free_snake: %d channels need %zu bytes of shared memory", channels, smem);
     return OU_ERR_UNSUPPORTED;
   }
-  static size_t configured = 48 * 1024;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(ou::alias_free_snake_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem);
-    if (e != cudaSuccess) {
-      ou::set_error("ou_alias_free_snake: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
-      return OU_ERR_CUDA;
-    }
-    configured = smem;
-  }
+  static ou::SmemConfig cfg;
+  if (smem > 48 * 1024)
+    if (int rc = ou::ensure_smem(ou::alias_free_snake_kernel, smem, cfg, "ou_alias_free_snake")) return rc;
   dim3 grid(ou::ceil_div(t, ou::SNK_NT), batch);
   ou::alias_free_snake_kernel<<<grid, ou::SNK_THREADS, smem, (cudaStream_t)stream>>>(a);
   return ou::check_launch("ou_alias_free_snake");

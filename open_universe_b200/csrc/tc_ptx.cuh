@@ -5,6 +5,12 @@
 
 #include "common.cuh"
 
+#if OU_ACT_IS_BF16
+#define OU_TMA_ACT CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+#else
+#define OU_TMA_ACT CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+#endif
+
 namespace ou {
 namespace tc {
 
@@ -183,15 +189,15 @@ __device__ __forceinline__ void sts_u4(uint32_t addr, const uint4& v) {
 // split as a = a_hi + a_lo (two bf16x2 registers, ~17 significant bits) so that the result is the
 // correctly rounded bf16 of the fp32 product to within 2^-17 relative -- 4 instructions per PAIR
 // against ~9 for unpack / select / multiply / repack.
-__device__ __forceinline__ uint32_t prelu_bf16x2(uint32_t x, uint32_t a_hi2, uint32_t a_lo2) {
+__device__ __forceinline__ uint32_t prelu_act2(uint32_t x, uint32_t a_hi2, uint32_t a_lo2) {
   uint32_t r;
   asm("{\n"
       ".reg .b32 zero, mn, mx;\n"
       "mov.b32 zero, 0;\n"
-      "max.bf16x2 mx, %1, zero;\n"
-      "min.bf16x2 mn, %1, zero;\n"
-      "fma.rn.bf16x2 mx, mn, %3, mx;\n"
-      "fma.rn.bf16x2 %0, mn, %2, mx;\n"
+      "max." OU_ACT_PTX " mx, %1, zero;\n"
+      "min." OU_ACT_PTX " mn, %1, zero;\n"
+      "fma.rn." OU_ACT_PTX " mx, mn, %3, mx;\n"
+      "fma.rn." OU_ACT_PTX " %0, mn, %2, mx;\n"
       "}\n"
       : "=r"(r)
       : "r"(x), "r"(a_hi2), "r"(a_lo2));
@@ -199,15 +205,15 @@ __device__ __forceinline__ uint32_t prelu_bf16x2(uint32_t x, uint32_t a_hi2, uin
 }
 // slope -> (a_hi, a_lo) replicated in both halves of a bf16x2 register
 __device__ __forceinline__ void split_slope(float a, uint32_t& hi2, uint32_t& lo2) {
-  const __nv_bfloat16 hi = __float2bfloat16(a);
-  const __nv_bfloat16 lo = __float2bfloat16(a - __bfloat162float(hi));
-  const uint32_t h = (uint32_t)__bfloat16_as_ushort(hi), l = (uint32_t)__bfloat16_as_ushort(lo);
+  const act_t hi = f_to_act(a);
+  const act_t lo = f_to_act(a - act_to_f(hi));
+  const uint32_t h = (uint32_t)act_bits(hi), l = (uint32_t)act_bits(lo);
   hi2 = h | (h << 16);
   lo2 = l | (l << 16);
 }
-__device__ __forceinline__ uint4 prelu_bf16x8(uint4 v, uint32_t a_hi2, uint32_t a_lo2) {
-  v.x = prelu_bf16x2(v.x, a_hi2, a_lo2), v.y = prelu_bf16x2(v.y, a_hi2, a_lo2);
-  v.z = prelu_bf16x2(v.z, a_hi2, a_lo2), v.w = prelu_bf16x2(v.w, a_hi2, a_lo2);
+__device__ __forceinline__ uint4 prelu_act8(uint4 v, uint32_t a_hi2, uint32_t a_lo2) {
+  v.x = prelu_act2(v.x, a_hi2, a_lo2), v.y = prelu_act2(v.y, a_hi2, a_lo2);
+  v.z = prelu_act2(v.z, a_hi2, a_lo2), v.w = prelu_act2(v.w, a_hi2, a_lo2);
   return v;
 }
 

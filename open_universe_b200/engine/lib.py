@@ -10,7 +10,7 @@ from ctypes import (POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int
                     c_void_p)
 from pathlib import Path
 
-LIB_PATH = Path(__file__).resolve().parent.parent / "csrc" / "libou_b200.so"
+from ..build import LIB as LIB_PATH
 OU_ABI_VERSION = 1
 
 
@@ -51,6 +51,8 @@ SIGNATURES = {
     "ou_abi_version": (c_int, []),
     "ou_last_error": (c_int, [c_char_p, c_size_t]),
     "ou_launch_count": (c_int64, []),
+    "ou_act_dtype": (c_int, []),
+    "ou_conv_fallback_count": (c_int64, []),
     "ou_conv1d": (c_int, [POINTER(ConvParams), c_void_p]),
     "ou_conv1d_naive": (c_int, [POINTER(ConvParams), c_void_p]),
     "ou_conv_trunk": (c_int, [POINTER(TrunkParams), c_void_p]),
@@ -130,3 +132,18 @@ def check(rc):
 
 def launch_count():
     return int(load().ou_launch_count())
+
+
+def conv_fallback_count():
+    """ou_conv1d calls served by the mma.sync kernel because the tcgen05 kernel rejected the geometry."""
+    return int(load().ou_conv_fallback_count())
+
+
+def act_dtype():
+    """torch dtype of blocked activations and packed conv weights in this build of the library."""
+    import torch
+    return torch.bfloat16 if load().ou_act_dtype() == 1 else torch.float16
+
+
+def act_name():
+    return "bf16" if load().ou_act_dtype() == 1 else "f16"

@@ -434,6 +434,10 @@ def lower_conditioner(net, batch, t, need_signal_tail=True):
                 None)
     if last is None or last.add2 is not None:
         raise RuntimeError("unexpected producer of the encoder output")
+    if any(isinstance(op, TrunkOp) and last in op.parts for op in prog.ops):
+        # the fused trunk kernel has no second residual input: run this block conv by conv
+        idx = next(i for i, op in enumerate(prog.ops) if isinstance(op, TrunkOp) and last in op.parts)
+        prog.ops[idx:idx + 1] = prog.ops[idx].parts
     if tl != frames:
         raise ValueError("encoder output length does not match the mel frame count")
     last.add2, last.scale2 = acc, 1.0 / math.sqrt(n_sum)

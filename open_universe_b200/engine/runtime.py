@@ -4,8 +4,10 @@ PyTorch is used for device memory (``torch.empty`` / ``Tensor.data_ptr``), the c
 stream and tiny host-side scalar math only; every FLOP of the networks is issued by a kernel of
 ``csrc/``.  There is NO CPU path: any entry point called with non-CUDA tensors raises.
 """
+import functools
 import math
 import os
+from collections import OrderedDict
 from ctypes import byref, c_void_p
 
 import torch
@@ -28,6 +30,44 @@ def require_cuda(*tensors):
 
 def _stream():
     return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _first_cuda_tensor(obj):
+    if torch.is_tensor(obj):
+        return obj if obj.is_cuda else None
+    if isinstance(obj, (list, tuple)):
+        for o in obj:
+            t = _first_cuda_tensor(o)
+            if t is not None:
+                return t
+    return None
+
+
+def on_tensor_device(fn):
+    """Run ``fn`` with the CUDA device of its first CUDA tensor argument made current: kernels are
+    launched through ctypes on ``torch.cuda.current_stream()``, which belongs to the CURRENT device,
+    not to the device the tensors live on (``model.to('cuda:1')`` without ``torch.cuda.set_device``)."""
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        t = _first_cuda_tensor(list(args) + list(kwargs.values()))
+        if t is None or t.device.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(t.device):
+            return fn(*args, **kwargs)
+    return wrapper
+
+
+def same_device(*tensors):
+    """All CUDA tensors of one call must live on one device (pointers are passed raw to the kernels)."""
+    dev = None
+    for t in tensors:
+        if t is None or not torch.is_tensor(t):
+            continue
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise ValueError(f"tensors on different devices in one call: {dev} and {t.device}")
+    return dev
 
 
 def _ptr(t):
@@ -56,7 +96,7 @@ def channel_block(c):
 
 def alloc_blocked(b, c, t, device):
     cb = channel_block(c)
-    return torch.empty(b, c // cb, t, cb, dtype=torch.bfloat16, device=device)
+    return torch.empty(b, c // cb, t, cb, dtype=lib.act_dtype(), device=device)
 
 
 def pack_conv_weights(fc, device):
@@ -73,8 +113,9 @@ def pack_conv_weights(fc, device):
     wt = torch.zeros(taps, k, npad, dtype=torch.float32, device=device)
     wt[:, :, :n] = src
     wt = wt.reshape(taps, k // cb, cb, npad).permute(0, 1, 3, 2).contiguous()
-    return {"w": w.to(torch.bfloat16), "bias": fc.bias.to(device).contiguous(), "kpad": kpad,
-            "npad": npad, "w_tc": wt.to(torch.bfloat16)}
+    dt = lib.act_dtype()
+    return {"w": w.to(dt), "bias": fc.bias.to(device).contiguous(), "kpad": kpad,
+            "npad": npad, "w_tc": wt.to(dt)}
 
 
 def alloc_buffers(prog, device, skip=()):
@@ -104,27 +145,41 @@ def dft_matrix(n_fft):
     return torch.stack([torch.cos(ang), torch.sin(ang)], dim=2).reshape(n_fft, -1).float().contiguous()
 
 
-def prepare_ops(prog, device):
-    """Upload packed weights / small tables for every op of a program."""
+def prepare_ops(prog, device, shared=None, tag=""):
+    """Upload packed weights / small tables for every op of a program.  ``shared``: dict that keeps
+    ONE packed copy per (program kind, op name, device) for all runners of a module -- the packed
+    weights depend on the weights only, not on (batch, length)."""
+    def packed_for(op, make):
+        key = (tag, op.name, str(device))
+        if shared is not None and key in shared:
+            return shared[key]
+        pk = make()
+        if shared is not None:
+            shared[key] = pk
+        return pk
+
     for op in P.flat_ops(prog.ops):
         if isinstance(op, P.ConvOp):
-            op.packed = pack_conv_weights(op.fc, device)
+            op.packed = packed_for(op, lambda: pack_conv_weights(op.fc, device))
         elif isinstance(op, P.InputConvOp):
-            op.packed = {"w": op.w.to(device).contiguous(), "bias": op.bias.to(device).contiguous()}
+            op.packed = packed_for(op, lambda: {"w": op.w.to(device).contiguous(),
+                                                "bias": op.bias.to(device).contiguous()})
         elif isinstance(op, P.OutputOp):
-            op.packed = {"w": op.w.to(device).contiguous()}
+            op.packed = packed_for(op, lambda: {"w": op.w.to(device).contiguous()})
         elif isinstance(op, P.GruOp):
-            op.packed = {"w_hh": op.w_hh.to(device).contiguous(),
-                         "b_hh": op.b_hh.to(device).contiguous()}
+            op.packed = packed_for(op, lambda: {"w_hh": op.w_hh.to(device).contiguous(),
+                                                "b_hh": op.b_hh.to(device).contiguous()})
         elif isinstance(op, P.MelOp):
-            op.packed = {"window": op.window.to(device).contiguous(),
-                         "fb": op.fb.to(device).contiguous(), "dft": dft_matrix(op.n_fft).to(device),
-                         "power": torch.empty(prog.batch * op.frames, op.n_fft // 2 + 1,
-                                              dtype=torch.float32, device=device),
-                         "mel": torch.empty(prog.batch, op.n_mels, op.frames, dtype=torch.float32,
-                                            device=device),
-                         "energy": torch.empty(prog.batch, op.frames, dtype=torch.float32,
-                                               device=device)}
+            tables = packed_for(op, lambda: {"window": op.window.to(device).contiguous(),
+                                             "fb": op.fb.to(device).contiguous(),
+                                             "dft": dft_matrix(op.n_fft).to(device)})
+            op.packed = dict(tables,
+                             power=torch.empty(prog.batch * op.frames, op.n_fft // 2 + 1,
+                                               dtype=torch.float32, device=device),
+                             mel=torch.empty(prog.batch, op.n_mels, op.frames, dtype=torch.float32,
+                                             device=device),
+                             energy=torch.empty(prog.batch, op.frames, dtype=torch.float32,
+                                                device=device))
 
 
 # ------------------------------------------------------------------------------------ op launch
@@ -210,11 +265,11 @@ def launch_trunk(op, bufs, batch, film=None, film_bstride=0):
 class Executor:
     """A lowered program bound to device buffers."""
 
-    def __init__(self, prog, device, external=()):
+    def __init__(self, prog, device, external=(), shared=None, tag=""):
         self.prog = prog
         self.device = device
         self.batch = prog.batch
-        prepare_ops(prog, device)
+        prepare_ops(prog, device, shared, tag)
         self.bufs = alloc_buffers(prog, device, skip=external)
         self.naive = False   # tests: route ConvOps through the fp32 CUDA-core reference kernel
 
@@ -264,8 +319,9 @@ class Executor:
 
 
 # ------------------------------------------------------------------------------------ layouts
+@on_tensor_device
 def pack_blocked(x):
-    """(B, C, T) fp32 -> blocked bf16 [B][C/CB][T][CB]."""
+    """(B, C, T) fp32 -> blocked 16-bit [B][C/CB][T][CB] (fp16 / bf16 per ``lib.act_dtype()``)."""
     require_cuda(x)
     b, c, t = x.shape
     x = x.contiguous().float()
@@ -274,8 +330,9 @@ def pack_blocked(x):
     return out
 
 
+@on_tensor_device
 def unpack_blocked(xb):
-    """blocked bf16 [B][C/CB][T][CB] -> (B, C, T) fp32."""
+    """blocked 16-bit [B][C/CB][T][CB] -> (B, C, T) fp32."""
     require_cuda(xb)
     b, nblk, t, cb = xb.shape
     out = torch.empty(b, nblk * cb, t, dtype=torch.float32, device=xb.device)
@@ -286,20 +343,50 @@ def unpack_blocked(xb):
 # ------------------------------------------------------------------------------------ caching
 def weights_version(module):
     """Cheap fingerprint that changes whenever a parameter / buffer is written in place, replaced,
-    or moved (EMA swap in eval()/train(), load_state_dict, .to())."""
-    v = 0
+    or moved (EMA swap in eval()/train(), load_state_dict, .to()).  Writes
+    through ``p.data`` do NOT bump ``_version``: ``utils.ema`` therefore copies through the parameter
+    itself, and ``invalidate(module)`` is the explicit hook for anything else."""
+    v = module.__dict__.get("_ou_generation", 0)
     for t in list(module.parameters()) + list(module.buffers()):
         v = (v * 1000003 + t._version + (t.data_ptr() & 0xFFFFFFFF)) & 0xFFFFFFFFFFFF
     return v
+
+
+def invalidate(module):
+    """Drop every cached runner / packed weight of ``module`` (and bump its generation)."""
+    for m in module.modules():
+        m.__dict__["_ou_generation"] = m.__dict__.get("_ou_generation", 0) + 1
+        m.__dict__.pop("_ou_cache", None)
+
+
+# Per-module cache: runners (lowered program + activation buffers + captured graphs) per
+# (kind, batch, length, device) in a small LRU -- a folder of files with many different lengths
+# must not accumulate gigabytes of buffers -- and ONE copy of the packed weights shared by all of them.
+MAX_CACHED_SHAPES = int(os.environ.get("OU_CACHE_SHAPES", "4"))
+MAX_CACHED_LOOPS = 2
 
 
 def _cache(module):
     c = module.__dict__.get("_ou_cache")
     ver = weights_version(module)
     if c is None or c["version"] != ver:
-        c = {"version": ver, "runners": {}}
+        c = {"version": ver, "runners": OrderedDict(), "packed": {}}
         module.__dict__["_ou_cache"] = c
-    return c["runners"]
+    return c
+
+
+def _get_runner(module, key, make):
+    c = _cache(module)
+    runners = c["runners"]
+    if key in runners:
+        runners.move_to_end(key)
+        return runners[key]
+    r = make(c["packed"])
+    runners[key] = r
+    # one slot per kind and shape: a score runner and a conditioner runner of the same shape are two entries
+    while len(runners) > 2 * MAX_CACHED_SHAPES:
+        runners.popitem(last=False)
+    return r
 
 
 # ------------------------------------------------------------------------------------ sigma embedding
@@ -339,15 +426,16 @@ def sigma_embedding(spec, dim, log10_sigma):
 class ScoreRunner:
     """ScoreNetwork lowered for a fixed (batch, length) and bound to device buffers."""
 
-    def __init__(self, net, batch, t, device):
+    def __init__(self, net, batch, t, device, shared=None):
         self.batch, self.t, self.device = batch, t, device
         with torch.no_grad():
             self.prog = P.lower_score_network(net, batch, t)
             self.proj = P.lower_cond_projection(net, batch, self.prog.meta["lengths"])
-            self.exe = Executor(self.prog, device)
+            self.exe = Executor(self.prog, device, shared=shared, tag="score")
             # the projection program writes straight into the score program's 'sc{lvl}' buffers
             self.proj_exe = Executor(self.proj, device,
-                                     external=[n for n in self.proj.bufs if n.startswith("sc")])
+                                     external=[n for n in self.proj.bufs if n.startswith("sc")],
+                                     shared=shared, tag="proj")
             for name in self.proj.bufs:
                 if name.startswith("sc"):
                     self.proj_exe.bufs[name] = self.exe.bufs[name]
@@ -475,31 +563,35 @@ class SamplerLoop:
 def get_sampler_loop(sr, n_steps, n_start=0):
     """Cached SamplerLoop of a ScoreRunner; captured as a CUDA graph unless disabled, profiled
     (bench.py's per-launch events) or too large."""
-    loops = sr.__dict__.setdefault("_loops", {})
+    loops = sr.__dict__.setdefault("_loops", OrderedDict())
     want_graph = (USE_GRAPH and PROFILE is None and
                   (n_steps - 1) * sr.batch * sr.t * 4 <= GRAPH_NOISE_LIMIT)
     key = (n_steps, n_start, want_graph)
-    if key not in loops:
-        loop = SamplerLoop(sr, n_steps, n_start)
-        if want_graph:
-            if sr.film is None or sr.film.shape[0] < n_steps:
-                raise RuntimeError("set_sigmas() must run before the sampler loop is captured")
-            loop.capture()
-        loops[key] = loop
-    return loops[key]
+    if key in loops:
+        loops.move_to_end(key)
+        return loops[key]
+    while len(loops) >= MAX_CACHED_LOOPS:     # each loop owns an (N-1) x B x T fp32 noise buffer + a graph
+        loops.popitem(last=False)
+    loop = SamplerLoop(sr, n_steps, n_start)
+    if want_graph:
+        if sr.film is None or sr.film.shape[0] < n_steps:
+            raise RuntimeError("set_sigmas() must run before the sampler loop is captured")
+        loop.capture()
+    loops[key] = loop
+    return loop
 
 
 def get_score_runner(net, batch, t, device):
-    runners = _cache(net)
-    key = ("score", batch, t, str(device))
-    if key not in runners:
-        runners[key] = ScoreRunner(net, batch, t, device)
-    return runners[key]
+    device = torch.device(device)
+    return _get_runner(net, ("score", batch, t, str(device)),
+                       lambda shared: ScoreRunner(net, batch, t, device, shared))
 
 
+@on_tensor_device
 def score_forward(net, x, sigma, cond):
     """ScoreNetwork.forward(x, sigma, cond) on reference-layout tensors (score.py:277-297)."""
     require_cuda(x, sigma, *cond)
+    same_device(x, sigma, *cond)
     b, c, t = x.shape
     if c != 1:
         raise ValueError("ScoreNetwork expects a (B, 1, T) input")
@@ -514,11 +606,11 @@ def score_forward(net, x, sigma, cond):
 
 # ------------------------------------------------------------------------------------ conditioner
 class ConditionerRunner:
-    def __init__(self, net, batch, t, device, need_signal_tail=True):
+    def __init__(self, net, batch, t, device, need_signal_tail=True, shared=None):
         self.batch, self.t, self.device = batch, t, device
         with torch.no_grad():
             self.prog = P.lower_conditioner(net, batch, t, need_signal_tail)
-            self.exe = Executor(self.prog, device)
+            self.exe = Executor(self.prog, device, shared=shared, tag="cond")
         self.n_cond = len([k for k in self.prog.outputs if k.startswith("cond")])
 
     def run(self, x, x_wav=None):
@@ -532,13 +624,12 @@ class ConditionerRunner:
 
 
 def get_conditioner_runner(net, batch, t, device, need_signal_tail=True):
-    runners = _cache(net)
-    key = ("cond", batch, t, str(device), need_signal_tail)
-    if key not in runners:
-        runners[key] = ConditionerRunner(net, batch, t, device, need_signal_tail)
-    return runners[key]
+    device = torch.device(device)
+    return _get_runner(net, ("cond", batch, t, str(device), need_signal_tail),
+                       lambda shared: ConditionerRunner(net, batch, t, device, need_signal_tail, shared))
 
 
+@on_tensor_device
 def conditioner_forward(net, x, x_wav=None):
     """ConditionerNetwork.forward on reference-layout tensors -> (conditions, y_hat, h) fp32."""
     require_cuda(x, x_wav)
@@ -555,6 +646,7 @@ def conditioner_forward(net, x, x_wav=None):
         return cond, y_hat, unpack_blocked(h)
 
 
+@on_tensor_device
 def compute_mel_spec(mel_adapter, x):
     """MelAdapter.compute_mel_spec (condition.py:92-108): (B,1,T) -> (B, n_mels, frames) fp32."""
     require_cuda(x)
@@ -580,6 +672,7 @@ def compute_mel_spec(mel_adapter, x):
 
 
 # ------------------------------------------------------------------------------------ block-level
+@on_tensor_device
 def conv_block_forward(blk, h, noise_cond=None, input_cond=None, res=None, length=None):
     """ConvBlock.forward on (B, C, T) fp32 tensors -> (h_out, skip, cond_out)  (blocks.py:327-412).
     Layer-level entry point (parity tests, LoRA-style consumers); the networks never call it."""
@@ -623,6 +716,7 @@ class _FilmPassthrough:
         self.c = c
 
 
+@on_tensor_device
 def alias_free_snake(mod, x, conv=None, blocked=False, t=None):
     """AliasFreeSnake.forward (bigvgan/snake.py:127-157), optionally fused with the k-tap conv to one
     channel behind it (``conv``: a Conv1d with out_channels == 1, 'same' padding).
@@ -666,6 +760,7 @@ def alias_free_snake(mod, x, conv=None, blocked=False, t=None):
     return out
 
 
+@on_tensor_device
 def prelu_conv_forward(pc, x, blocked=False):
     """PReLU_Conv.forward on a (B, C, T) fp32 tensor (blocks.py:205-227)."""
     require_cuda(x)
@@ -694,8 +789,12 @@ def prelu_conv_forward(pc, x, blocked=False):
         return unpack_blocked(exe.bufs[dst])
 
 
+@on_tensor_device
 def film(x, y):
+    """film(x, y) = y[:, :C] * x + y[:, C:]  (blocks.py:53-59) on (B, C, T) / (B, 2C) fp32 tensors."""
     require_cuda(x, y)
+    if y.shape[1] != 2 * x.shape[1]:
+        raise ValueError("g should have 2 times more channels than y")
     b, c, t = x.shape
     out = torch.empty_like(x, dtype=torch.float32)
     xc, yc = x.contiguous().float(), y.contiguous().float()   # keep alive across the launch
@@ -709,6 +808,7 @@ def lowpass(x, taps):
         "standalone kernel")
 
 
+@on_tensor_device
 def sigma_embed(block, log10_sigma):
     """sigma_block(log10 sigma) -> (B, noise_cond_dim) fp32 (sigma_block.py:50-57, 73-78)."""
     require_cuda(log10_sigma)

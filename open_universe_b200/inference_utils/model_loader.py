@@ -6,10 +6,19 @@ A local checkpoint path is paired with ``./config.yaml`` or ``../.hydra/config.y
 ``state_dict`` and optionally ``ema`` (torch_ema state); EMA weights are preferred (:119-130).
 The model is returned in ``eval()`` mode on ``device``.
 
-Differences from upstream, all on the safe side: training-only ``loss_*`` entries of the
-checkpoint are ignored (the discriminators / MDN heads are not instantiated here), and
-``torch.load`` is asked for ``weights_only`` tensors first.
+Differences from upstream, all on the safe side:
+* training-only ``loss_*`` entries of the checkpoint are ignored (the discriminators / MDN heads are
+  not instantiated here);
+* ``torch.load`` is asked for ``weights_only`` tensors; a checkpoint that needs full unpickling
+  (arbitrary code execution) is only accepted from a LOCAL path, or with ``OU_ALLOW_PICKLE=1`` for
+  hub downloads;
+* a checkpoint WITHOUT an ``"ema"`` entry: upstream calls ``ema.store(...)`` (model_loader.py:124-127)
+  and the following ``eval()`` then copies the EMA shadow -- still the constructor's random
+  initialisation -- over the weights it has just loaded.  Here the shadow is set to the loaded
+  weights instead, so that ``eval()`` / ``train()`` round-trip them.
 """
+import os
+import pickle
 from pathlib import Path
 
 import torch
@@ -33,10 +42,12 @@ def open_update_config(path):
     return load_config(path)
 
 
-def _torch_load(path, device):
+def _torch_load(path, device, trusted):
     try:
         return torch.load(path, map_location=device, weights_only=True)
-    except Exception:
+    except pickle.UnpicklingError:
+        if not (trusted or os.environ.get("OU_ALLOW_PICKLE", "0") == "1"):
+            raise
         return torch.load(path, map_location=device, weights_only=False)
 
 
@@ -45,7 +56,8 @@ def _inference_state_dict(state_dict):
 
 
 def load_model(ckpt_path, device=None, strict=True, return_config=False, hf_token=None):
-    if not Path(ckpt_path).exists():
+    local = Path(ckpt_path).exists()
+    if not local:
         try:
             from huggingface_hub import hf_hub_download
             ckpt_path = str(ckpt_path)
@@ -65,7 +77,7 @@ def load_model(ckpt_path, device=None, strict=True, return_config=False, hf_toke
     config = open_update_config(config_path)
     model = instantiate(config.model, _recursive_=False)
     model = model.to(device)
-    data = _torch_load(ckpt_path, device)
+    data = _torch_load(ckpt_path, device, trusted=local)
     state_dict = _inference_state_dict(data["state_dict"])
 
     ema = getattr(model, "ema", None)

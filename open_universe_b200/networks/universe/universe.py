@@ -161,6 +161,7 @@ class Universe(torch.nn.Module):
         return {"skip": sigma_data**2 / (sigma**2 + sigma_data**2), "in": 1.0 / sigma_norm,
                 "out": sigma * sigma_data / sigma_norm, "noise": self.edm_kwargs.noise}
 
+    @runtime.on_tensor_device
     def _edm_score_wrapper(self, x, sigma, cond, with_speech_est=False):
         """score = (w_skip x + w_out net(w_in x, c_noise sigma) - x) / sigma^2 (universe.py:197-209),
         with the affine combination evaluated inside the network's last kernel."""
@@ -219,6 +220,7 @@ class Universe(torch.nn.Module):
         coef = torch.stack([ca, cb, cc], dim=1)
         return sigma, net_sigma.float(), in_scale.float(), coef.float(), (eta, beta)
 
+    @runtime.on_tensor_device
     def enhance(
         self,
         mix,
@@ -252,6 +254,9 @@ class Universe(torch.nn.Module):
         elif x_ndim > 3:
             raise ValueError("The input should have at most 3 dimensions")
         runtime.require_cuda(mix)
+        p_dev = next(self.parameters()).device
+        if p_dev != mix.device:
+            raise ValueError(f"model weights are on {p_dev} but the input is on {mix.device}")
         if mix.shape[1] != 1:
             raise NotImplementedError("multi-channel clips: pass channels as batch rows (B, T)")
         L = lib.load()

@@ -47,12 +47,14 @@ def enhance_sharded(model, mix, group=None, seed=None, global_noise=True, enhanc
         local_mix = mix[lo:hi]
         if seed is not None and global_noise:
             from .networks.universe import universe as U
-            rng = torch.Generator(device=mix.device).manual_seed(seed)
+            gen = torch.Generator(device=mix.device).manual_seed(seed)
             orig = U.randn
 
-            def sliced_randn(x, sigma, rng=rng):
+            def sliced_randn(x, sigma, rng=None):
+                # enhance() always passes its own ``rng`` (None here): the seeded generator is
+                # closed over, not a default argument the caller would override
                 full = torch.randn((batch,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device,
-                                   generator=rng)
+                                   generator=gen)
                 return full[lo:hi] * sigma[:, None, None]
 
             U.randn = sliced_randn

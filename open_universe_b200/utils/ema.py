@@ -26,17 +26,21 @@ class ExponentialMovingAverage:
                 s.sub_((1.0 - decay) * (s - p))
 
     def copy_to(self, parameters):
-        for s, p in zip(self.shadow_params, parameters):
-            p.data.copy_(s.data)
+        # in-place through the parameter itself (not ``p.data``): bumps ``p._version`` so that
+        # ``engine.runtime.weights_version`` notices the swap and re-packs the device weights
+        with torch.no_grad():
+            for s, p in zip(self.shadow_params, parameters):
+                p.copy_(s)
 
     def store(self, parameters):
-        self.collected_params = [p.clone() for p in parameters]
+        self.collected_params = [p.detach().clone() for p in parameters]
 
     def restore(self, parameters):
         if self.collected_params is None:
             raise RuntimeError("no stored parameters to restore")
-        for c, p in zip(self.collected_params, parameters):
-            p.data.copy_(c.data)
+        with torch.no_grad():
+            for c, p in zip(self.collected_params, parameters):
+                p.copy_(c)
         self.collected_params = None
 
     def to(self, device=None, dtype=None):

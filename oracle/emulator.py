@@ -5,8 +5,8 @@ following the kernel contracts of ``include/ou_b200.h``.  Purpose:
   * ``quant=False`` (exact fp32): proves that the host-side lowering (weight-norm /
     anti-alias folding, epilogue wiring, buffer lengths) is algebraically identical to the
     oracle -- runs in the CPU test-suite, no GPU needed;
-  * ``quant=True``: additionally rounds weights and every stored activation to bf16 exactly
-    where the CUDA kernels do, which bounds the error the precision policy (bf16 storage and
+  * ``quant=True``: additionally rounds weights and every stored activation to ``QDTYPE`` exactly
+    where the CUDA kernels do, which bounds the error the precision policy (16-bit storage and
     MMA operands, fp32 accumulation / epilogues / GRU state) can introduce -- the measured
     numbers are quoted in DESIGN.md.
 Activations are kept as plain (B, C, T) float tensors here; only the values matter.
@@ -19,8 +19,14 @@ import torch.nn.functional as F
 from open_universe_b200.engine import program as P
 
 
+# storage / MMA-operand type of the emulated kernels when ``quant`` is on: fp16 is the library's
+# default policy (csrc/common.cuh); GPU tests set it from ``lib.act_dtype()`` and
+# tools/precision_study.py switches it to compare policies (torch.bfloat16 | torch.float16)
+QDTYPE = torch.float16
+
+
 def _q(x, quant):
-    return x.to(torch.bfloat16).float() if quant else x
+    return x.to(QDTYPE).float() if quant else x
 
 
 def prelu(x, a):

@@ -1,8 +1,8 @@
 """Per-kernel parity on the GPU: every C-ABI entry point against the PyTorch emulator / oracle.
 
 Tolerances: bit-level agreement is not expected for floating point -- the tensor-core kernel
-accumulates in a different order than ATen.  The kernel and the emulator round to bf16 at the
-SAME points, so they agree to ~1e-3 of the tensor RMS (a few bf16 ulp flips); fp32-only kernels
+accumulates in a different order than ATen.  The kernel and the emulator round to the storage
+type (fp16 by default) at the SAME points, so they agree to ~1e-3 of the tensor RMS (a few ulp flips); fp32-only kernels
 agree to ~1e-5.
 """
 import math
@@ -20,8 +20,11 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 
+E.QDTYPE = lib.act_dtype()     # the emulator rounds where and how the loaded library does
+
+
 def bf(x):
-    return x.to(torch.bfloat16).float()
+    return x.to(E.QDTYPE).float()
 
 
 def rand_fc(g, cin, cout, s=1, up=1, taps=1, tap_off=0, prelu_in=None):

@@ -193,3 +193,61 @@ def test_weights_version_tracks_inplace_updates():
     with torch.no_grad():
         next(m.condition_model.parameters()).mul_(1.0)
     assert runtime.weights_version(m.condition_model) != v0
+
+
+def test_weights_version_tracks_ema_swap():
+    """eval() / train() / eval(no_ema=True) swap the live parameters with the EMA shadow
+    (universe.py:841-865): the packed-weight cache key must change every time."""
+    from open_universe_b200.engine import runtime
+    torch.manual_seed(0)
+    cfg = builtin_config("universepp_16k").model
+    cfg["training"] = dict(cfg.get("training") or {}, ema_decay=0.999)
+    m = instantiate(cfg, _recursive_=False)
+    assert m.ema is not None
+    with torch.no_grad():
+        for s in m.ema.shadow_params:
+            s.mul_(0.5)
+    net = m.get_score_model()
+    v_train = runtime.weights_version(net)
+    m.eval()
+    v_eval = runtime.weights_version(net)
+    assert v_eval != v_train
+    m.train()
+    v_back = runtime.weights_version(net)
+    assert v_back != v_eval
+    m.eval(no_ema=True)
+    assert runtime.weights_version(net) == v_back          # no swap, no change
+    runtime.invalidate(net)
+    assert runtime.weights_version(net) != v_back
+
+
+def test_runner_cache_is_bounded_and_shares_packed_weights():
+    """The per-module runner cache is a small LRU and keeps one packed-weight copy."""
+    from open_universe_b200.engine import runtime
+
+    class Dummy(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.zeros(3))
+
+    mod = Dummy()
+    made = []
+
+    def make(key):
+        def f(shared):
+            shared.setdefault("packed", object())
+            made.append(key)
+            return ("runner", key, shared["packed"])
+        return f
+
+    n = 2 * runtime.MAX_CACHED_SHAPES
+    rs = [runtime._get_runner(mod, ("score", 1, t, "cpu"), make(t)) for t in range(n + 3)]
+    cache = runtime._cache(mod)["runners"]
+    assert len(cache) == n and ("score", 1, 0, "cpu") not in cache
+    assert len({id(r[2]) for r in rs}) == 1                  # one shared packed-weight object
+    runtime._get_runner(mod, ("score", 1, n + 2, "cpu"), make("again"))
+    assert "again" not in made                                # cache hit
+    with torch.no_grad():
+        mod.w.add_(1.0)                                       # weights changed: everything is rebuilt
+    runtime._get_runner(mod, ("score", 1, n + 2, "cpu"), make("rebuilt"))
+    assert "rebuilt" in made and len(runtime._cache(mod)["runners"]) == 1

@@ -77,8 +77,11 @@ def test_lowering_exact(case):
 
 
 @pytest.mark.parametrize("case", [NET_CASES[0], NET_CASES[2]], ids=lambda c: c["name"])
-def test_lowering_bf16_policy(case):
-    """bf16 storage / operands, fp32 accumulate: single-evaluation error stays ~1e-2 relative."""
+def test_lowering_storage_policy(case):
+    """fp16 storage / operands, fp32 accumulate (the library default): the error of a single
+    evaluation on the unit-gain stress weights stays below 5e-3 relative (bf16: ~2e-2)."""
+    from oracle import emulator as E
+    assert E.QDTYPE == torch.float16
     errs = run_case(case, quant=True)
     print(errs)
-    assert max(errs.values()) < 3e-2, errs
+    assert max(errs.values()) < 5e-3, errs

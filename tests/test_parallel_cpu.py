@@ -62,3 +62,25 @@ def test_shard_bounds():
         lo, hi, per = parallel.shard_bounds(10, 4, r)
         covered += list(range(lo, hi))
     assert covered == list(range(10))
+
+
+def test_global_noise_uses_the_seeded_generator():
+    """enhance_sharded(seed=..., global_noise=True): the per-rank enhance() calls ``randn(x, sigma,
+    rng=None)`` -- the patched function must still draw from the SEEDED generator (closure, not a
+    default argument the caller overrides) and hand every shard its own rows of the
+    global draw."""
+    from open_universe_b200.networks.universe import universe as U
+
+    def fake_enhance(mix, **kw):
+        sigma = torch.ones(mix.shape[0])
+        return mix + U.randn(mix[:, None, :], sigma, rng=kw.get("rng"))[:, 0, :]
+
+    mix = torch.zeros(6, 11)
+    a = parallel.enhance_sharded(None, mix, seed=5, enhance_fn=fake_enhance)
+    torch.manual_seed(123)                      # the global generator must not matter
+    b = parallel.enhance_sharded(None, mix, seed=5, enhance_fn=fake_enhance)
+    want = torch.randn(6, 1, 11, generator=torch.Generator().manual_seed(5))[:, 0, :]
+    assert torch.equal(a, b) and torch.equal(a, want)
+    c = parallel.enhance_sharded(None, mix, seed=6, enhance_fn=fake_enhance)
+    assert not torch.equal(a, c)
+    assert U.randn is U._default_randn          # the hook is restored
