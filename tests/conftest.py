@@ -34,3 +34,34 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+# ---- measured parity errors: tests record into ``parity_log``; written once per session to
+# gpurun_out/parity_r2.json (the only directory that travels back from the GPU box)
+_PARITY = {}
+
+
+@pytest.fixture
+def parity_log():
+    return _PARITY
+
+
+def pytest_sessionfinish(session, exitstatus):
+    if not _PARITY:
+        return
+    import json
+    out = ROOT / "gpurun_out"
+    try:
+        out.mkdir(exist_ok=True)
+        meta = {}
+        try:
+            import torch
+            from open_universe_b200.engine import lib
+            meta = {"gpu": torch.cuda.get_device_name(0), "storage_dtype": lib.act_name(),
+                    "torch": torch.__version__}
+        except Exception:
+            pass
+        (out / "parity_r2.json").write_text(json.dumps({"meta": meta, "results": _PARITY}, indent=1,
+                                                       sort_keys=True))
+    except OSError:
+        pass

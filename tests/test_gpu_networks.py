@@ -1,8 +1,8 @@
 """Network-level and end-to-end parity of the CUDA path (through the drop-in module API, i.e.
 through the C ABI) against the golden vectors of the unmodified reference and the CPU oracle.
 
-Precision policy under test: bf16 storage + bf16 tensor-core operands, fp32 accumulation,
-fp32 FiLM / GRU state / EDM + SDE update.  Two weight sets:
+Precision policy under test: fp16 storage + fp16 tensor-core operands (csrc/common.cuh; bf16 with
+OU_ACT_BF16=1), fp32 accumulation, fp32 FiLM / GRU state / EDM + SDE update.  Two weight sets:
   * "det"  -- tests/golden/detweights.py, unit-gain random weights: a deliberately harsh
     stress set (a single score evaluation amplifies a 2^-9 bf16 rounding to ~2e-2 relative
     even when ONLY the MMA operands are rounded, see DESIGN.md "Precision"); tolerances for
@@ -111,7 +111,7 @@ def test_enhance_vs_reference_golden(case, monkeypatch):
     ("universe_original_16k", (1, 16000), 8),
     ("universepp_24k", (1, 12000), 4),
 ])
-def test_enhance_north_star_tolerance(cfg_name, shape, n_steps, monkeypatch):
+def test_enhance_north_star_tolerance(cfg_name, shape, n_steps, monkeypatch, parity_log):
     """north_star gate: CUDA enhance() vs the oracle on identical inputs and identical injected
     diffusion noise, weights drawn by the reference's own init scheme: <= 1e-3 RMS."""
     from open_universe_b200.config import builtin_config, instantiate
@@ -130,9 +130,15 @@ def test_enhance_north_star_tolerance(cfg_name, shape, n_steps, monkeypatch):
     got = m.to(DEV).enhance(mix.to(DEV), n_steps=n_steps).cpu()
     a, r = abs_rms(got, want), rel_rms(got, want)
     print(cfg_name, shape, n_steps, "abs rms err", a, "rel", r, "out rms", float(want.square().mean().sqrt()))
+    parity_log[f"north_star_{cfg_name}_{shape[0]}x{shape[1]}_{n_steps}"] = {
+        "config": cfg_name, "shape": list(shape), "n_steps": n_steps, "abs_rms_err": a, "rel_rms_err": r,
+        "out_rms": float(want.square().mean().sqrt())}
     assert got.shape == want.shape
-    assert a < 1e-3, (a, r)
-    assert r < 1e-2, (a, r)
+    # north_star: 1e-3 RMS.  Measured with fp16 storage: 3e-6 .. 1e-5 absolute, 1e-4 .. 4e-4 relative; the
+    # gates keep ~10x headroom over that (VERDICT round 1 item 1c asked for abs <= 1e-4, rel <= 4e-3).
+    # tests/test_gpu_parity_at_size.py adds the gates normalised by the network's contribution.
+    assert a < 1e-4, (a, r)
+    assert r < 4e-3, (a, r)
 
 
 def test_full_size_properties():
