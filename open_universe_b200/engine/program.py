@@ -467,3 +467,55 @@ def lower_conditioner(net, batch, t, need_signal_tail=True):
     prog.meta["lengths"] = lengths
     prog.meta["t_final"] = tl
     return prog
+
+
+# --------------------------------------------------------------------------------- work model
+def op_bytes(op, batch, elem=2):
+    """Algorithmic HBM bytes of ONE launch of ``op`` in this design: every input tensor read once, the
+    output written once, weights once (``elem`` = bytes per stored activation).  The roofline numerators
+    of bench.py / tools/profile_layers.py; ncu's dram__bytes are compared against them."""
+    if isinstance(op, TrunkOp):
+        c1 = op.parts[0]
+        c, t = c1.fc.cin, c1.t_in
+        w = sum(p.fc.w.numel() for p in op.parts) * elem
+        return elem * batch * c * t * (2 + (c1.add1 is not None)) + w
+    if isinstance(op, ConvOp):
+        fc = op.fc
+        n_in = elem * batch * fc.cin * op.t_in
+        w = fc.w.numel() * elem
+        if op.dst_kind != "blocked":
+            return n_in + 4 * batch * op.rows * fc.n + w
+        n_add = (op.add1 is not None) + (op.add2 is not None)
+        return n_in + elem * batch * fc.cout * op.t_out * (1 + n_add) + w
+    if isinstance(op, InputConvOp):
+        return 4 * batch * op.t + elem * batch * op.w.shape[0] * op.t
+    if isinstance(op, OutputOp):
+        return elem * batch * op.w.shape[0] * op.t + 3 * 4 * batch * op.t_out
+    if isinstance(op, GruOp):
+        h = op.hidden
+        return (4 * batch * op.t * 6 * h + elem * batch * op.t * 2 * h * (1 + (op.add is not None))
+                + 4 * op.w_hh.numel())
+    if isinstance(op, MelOp):
+        return 4 * batch * op.t + (4 + elem) * batch * op.n_mels * op.frames
+    raise TypeError(op)
+
+
+def op_flops(op, batch):
+    """Algorithmic FLOPs of one launch (reference graph as written, see ``add_conv``)."""
+    if isinstance(op, (ConvOp, TrunkOp)):
+        return op.flops_algo
+    if isinstance(op, (InputConvOp, OutputOp)):
+        return 2.0 * batch * op.t * op.w.numel()
+    if isinstance(op, GruOp):
+        return 2.0 * batch * op.t * op.w_hh.numel()
+    if isinstance(op, MelOp):
+        return 2.0 * batch * op.frames * (op.n_fft * (op.n_fft + 2) + (op.n_fft // 2 + 1) * op.n_mels)
+    raise TypeError(op)
+
+
+def kernel_name(op):
+    """Kernel family an op launches (bench.py's per-kernel breakdown)."""
+    if isinstance(op, TrunkOp):
+        return f"trunk_kernel<{op.parts[0].fc.cin}>"
+    return {ConvOp: "conv1d_tc_kernel", InputConvOp: "input_conv_kernel", OutputOp: "output_sde_kernel",
+            GruOp: "gru_cluster_f16_kernel", MelOp: "mel_power+finalize"}[type(op)]

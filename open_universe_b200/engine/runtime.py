@@ -183,7 +183,8 @@ def prepare_ops(prog, device, shared=None, tag=""):
 
 
 # ------------------------------------------------------------------------------------ op launch
-# bench.py sets this to a list to time every conv launch with CUDA events on the launching stream
+# bench.py sets this to a list to time every op launch of the programs with CUDA events on the
+# launching stream: entries (op, batch, start event, end event)
 PROFILE = None
 
 
@@ -216,13 +217,6 @@ def launch_conv(op, bufs, batch, gamma=None, beta=None, film_bstride=0, naive=Fa
     prm.prelu_out2 = op.prelu_out2 or 0.0
     prm.scale1, prm.scale2 = op.scale1, op.scale2
     fn = lib.load().ou_conv1d_naive if naive else lib.load().ou_conv1d
-    if PROFILE is not None:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        lib.check(fn(byref(prm), _stream()))
-        e1.record()
-        PROFILE.append((op, e0, e1))
-        return
     lib.check(fn(byref(prm), _stream()))
 
 
@@ -252,13 +246,6 @@ def launch_trunk(op, bufs, batch, film=None, film_bstride=0):
     prm.has_prelu_out2 = c3.prelu_out2 is not None
     prm.prelu_out2 = c3.prelu_out2 or 0.0
     prm.scale1, prm.scale3 = c1.scale1, c3.scale1
-    if PROFILE is not None:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        lib.check(lib.load().ou_conv_trunk(byref(prm), _stream()))
-        e1.record()
-        PROFILE.append((op, e0, e1))
-        return
     lib.check(lib.load().ou_conv_trunk(byref(prm), _stream()))
 
 
@@ -281,6 +268,9 @@ class Executor:
         if self.naive or not USE_TRUNK:
             ops = P.flat_ops(ops)
         for op in ops:
+            if PROFILE is not None:
+                e0 = torch.cuda.Event(enable_timing=True)
+                e0.record()
             if isinstance(op, P.TrunkOp):
                 launch_trunk(op, bufs, B, film, film_bstride)
             elif isinstance(op, P.ConvOp):
@@ -316,6 +306,10 @@ class Executor:
                                             _ptr(bufs[op.dst]), B, op.n_mels, op.frames, _stream()))
             else:
                 raise TypeError(op)
+            if PROFILE is not None:
+                e1 = torch.cuda.Event(enable_timing=True)
+                e1.record()
+                PROFILE.append((op, B, e0, e1))
 
 
 # ------------------------------------------------------------------------------------ layouts

@@ -80,6 +80,10 @@ def run_case(monkeypatch, cfg_name, shape, n_steps, out_gain=1.0, with_zero=Fals
     return res
 
 
+def abs_gate(cfg_name):
+    return 3e-4 if cfg_name == "universe_original_16k" else 3e-5
+
+
 # BASELINE.json configs[1..3] at their clip length and step count (batch reduced to what the CPU oracle
 # finishes in under a minute on the GPU box's host; rows are independent, see test_full_size_properties)
 AT_SIZE = [
@@ -96,9 +100,11 @@ def test_enhance_at_baseline_size(name, cfg_name, shape, n_steps, monkeypatch, p
     r = run_case(monkeypatch, cfg_name, shape, n_steps)
     parity_log[name] = r
     print(name, r)
-    # north_star: <= 1e-3 RMS.  Measured 4e-6 .. 2e-5 absolute (profiles/parity_r2.json): gate with ~5x headroom
-    assert r["abs_rms_err"] < 1e-4, r
-    assert r["rel_rms_err"] < 4e-3, r
+    # north_star: <= 1e-3 RMS.  Measured (profiles/parity_r2.json): UNIVERSE++ 16k / 24k 3.6e-6 .. 4.9e-6
+    # absolute, 8e-5 .. 2.5e-4 relative; UNIVERSE original (no EDM wrapper, output RMS 0.17) 5.7e-5 / 3.4e-4.
+    # Gates at ~4x the measurement.
+    assert r["abs_rms_err"] < abs_gate(cfg_name), r
+    assert r["rel_rms_err"] < 2e-3, r
 
 
 @pytest.mark.timeout(600, method="thread")
@@ -114,8 +120,8 @@ def test_error_normalised_by_network_contribution(cfg_name, shape, n_steps, monk
     parity_log[f"contribution_{cfg_name}_{shape[0]}x{shape[1]}_{n_steps}"] = r
     print(r)
     assert r["net_contribution_rms"] > 1e-3          # the denominator is not degenerate
-    assert r["err_over_contribution"] < 1e-2, r      # VERDICT asks <= 2e-2; measured ~1.5e-3
-    assert r["abs_rms_err"] < 1e-4, r
+    assert r["err_over_contribution"] < 5e-3, r      # VERDICT asks <= 2e-2; measured 3e-4 .. 1.2e-3
+    assert r["abs_rms_err"] < abs_gate(cfg_name), r
 
 
 @pytest.mark.timeout(600, method="thread")
@@ -131,8 +137,11 @@ def test_enhance_with_network_dominated_weights(cfg_name, shape, n_steps, monkey
     parity_log[f"out16_{cfg_name}_{shape[0]}x{shape[1]}_{n_steps}"] = r
     print(r)
     assert r["net_contribution_rms"] > 0.3 * r["out_rms"], r
-    assert r["abs_rms_err"] < 3e-4, r                # north_star: 1e-3
-    assert r["err_over_contribution"] < 1e-2, r
+    # measured: 16k 5e-5 .. 6e-5 absolute (output RMS 0.05), 24k 2.4e-4 (output RMS 0.67); 8e-4 .. 1.2e-3
+    # of the network's contribution
+    assert r["abs_rms_err"] < 1e-3, r                # north_star
+    assert r["rel_rms_err"] < 4e-3, r
+    assert r["err_over_contribution"] < 5e-3, r
 
 
 @pytest.mark.timeout(600, method="thread")
