@@ -23,10 +23,12 @@ def pytest_collection_modifyitems(config, items):
         # a deadlocked kernel must fail ONE test quickly, not hang the whole session: pytest-timeout in
         # "thread" mode kills the process (the only way out of a stuck cudaDeviceSynchronize)
         try:
+            import os
             import pytest_timeout  # noqa: F401
+            limit = int(os.environ.get("OU_GPU_TEST_TIMEOUT", "240"))     # tools/sanitize.sh raises it
             for item in items:
                 if "gpu" in item.keywords and item.get_closest_marker("timeout") is None:
-                    item.add_marker(pytest.mark.timeout(240, method="thread"))
+                    item.add_marker(pytest.mark.timeout(limit, method="thread"))
         except ImportError:
             pass
         return
