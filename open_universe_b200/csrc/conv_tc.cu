@@ -451,45 +451,37 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& a, const Ctx& c, int
         }
         const long off = out_offset(sub, col);
         if (off < 0) continue;
-        float v[16];
         // coefficient vectors as plain shared-memory loads: the compiler is free to hoist them over the
-        // arithmetic of the previous group (volatile asm accessors would serialise every load)
+        // arithmetic of the previous group (volatile asm accessors would serialise every load).
+        // Arithmetic on packed fp32 pairs (FFMA2 / FADD2 / FMUL2): these layers are bound by the issue
+        // rate of the epilogue warps, not by the tensor pipe or HBM.
         const float4* k0 = reinterpret_cast<const float4*>(coefp + col);
         const float4* k1 = reinterpret_cast<const float4*>(coefp + bn + col);
         const float4* k2 = reinterpret_cast<const float4*>(coefp + 2 * bn + col);
+        U8 o;
 #pragma unroll
         for (int i = 0; i < 4; i++) {
           const float4 x1 = k1[i];
           float4 x0 = make_float4(c0s, c0s, c0s, c0s);
           if (FILM) x0 = k0[i];
-          float a0 = __uint_as_float(r[4 * i]), a1 = __uint_as_float(r[4 * i + 1]);
-          float a2 = __uint_as_float(r[4 * i + 2]), a3 = __uint_as_float(r[4 * i + 3]);
+          float2 a01 = u2_as_f2(r[4 * i], r[4 * i + 1]), a23 = u2_as_f2(r[4 * i + 2], r[4 * i + 3]);
           if (NADD > 0) {
-            const float2 fa = act2_to_f2(cur1.w[2 * i]), fb = act2_to_f2(cur1.w[2 * i + 1]);
-            a0 += fa.x, a1 += fa.y, a2 += fb.x, a3 += fb.y;
+            a01 = fadd2(a01, act2_to_f2(cur1.w[2 * i]));
+            a23 = fadd2(a23, act2_to_f2(cur1.w[2 * i + 1]));
           }
-          a0 = fmaf(x0.x, a0, x1.x), a1 = fmaf(x0.y, a1, x1.y);
-          a2 = fmaf(x0.z, a2, x1.z), a3 = fmaf(x0.w, a3, x1.w);
+          a01 = ffma2(make_float2(x0.x, x0.y), a01, make_float2(x1.x, x1.y));
+          a23 = ffma2(make_float2(x0.z, x0.w), a23, make_float2(x1.z, x1.w));
           if (NADD > 1) {
             float4 x2 = make_float4(s2, s2, s2, s2);
             if (FILM) x2 = k2[i];
-            const float2 fa = act2_to_f2(cur2.w[2 * i]), fb = act2_to_f2(cur2.w[2 * i + 1]);
-            a0 = fmaf(x2.x, fa.x, a0), a1 = fmaf(x2.y, fa.y, a1);
-            a2 = fmaf(x2.z, fb.x, a2), a3 = fmaf(x2.w, fb.y, a3);
+            a01 = ffma2(make_float2(x2.x, x2.y), act2_to_f2(cur2.w[2 * i]), a01);
+            a23 = ffma2(make_float2(x2.z, x2.w), act2_to_f2(cur2.w[2 * i + 1]), a23);
           }
-          if (NPRELU > 0) {
-            a0 = prelu_f(a0, slope1), a1 = prelu_f(a1, slope1);
-            a2 = prelu_f(a2, slope1), a3 = prelu_f(a3, slope1);
-          }
-          if (NPRELU > 1) {
-            a0 = prelu_f(a0, slope2), a1 = prelu_f(a1, slope2);
-            a2 = prelu_f(a2, slope2), a3 = prelu_f(a3, slope2);
-          }
-          v[4 * i] = a0, v[4 * i + 1] = a1, v[4 * i + 2] = a2, v[4 * i + 3] = a3;
+          if (NPRELU > 0) a01 = prelu2<false>(a01, slope1), a23 = prelu2<false>(a23, slope1);
+          if (NPRELU > 1) a01 = prelu2<false>(a01, slope2), a23 = prelu2<false>(a23, slope2);
+          o.w[2 * i] = f2_to_act2(a01.x, a01.y);
+          o.w[2 * i + 1] = f2_to_act2(a23.x, a23.y);
         }
-        U8 o;
-#pragma unroll
-        for (int i = 0; i < 8; i++) o.w[i] = f2_to_act2(v[2 * i], v[2 * i + 1]);
         stg_v8(outp + off, o);
         EPI_DETAIL(3)
       }

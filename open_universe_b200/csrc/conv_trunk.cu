@@ -16,12 +16,14 @@
 //     smem  Cb  : sc rows (TMA) -> conv1 epilogue output c1 (in place) -> conv2 epilogue output c2
 //                 (in place); always in the swizzled K-major layout = A operand of conv2 / conv3
 //     TMEM      : 64 fp32 accumulator columns, reused by the three stages
-// Warp roles: warp 0 loads the 11 weight taps once (TMA) and then issues every tcgen05.mma of the
-// CTA, serving whichever slot has its operand ready (mbarrier.test_wait polling: the three stages
-// of S slots interleave on the tensor pipe); warps 1.. form S warpgroups, one per slot, that run
-// the slot's PReLU transform and its three epilogues (thread = accumulator row) and issue the
-// slot's own TMA loads as soon as a tcgen05.commit has released the buffer.
+// What bounds the kernel (measured, tools/ubench/mma_bench.cu): a tcgen05.mma of M = 128, K = 16 costs
+// 67 cycles for ANY N <= 128 -- the A operand (128 rows x 32 B) is fetched from shared memory at 64 B per
+// cycle -- so an item costs 44-48 MMAs x 67 cycles on the tensor pipe whatever the channel count: 177 /
+// 187 us per launch at cfg-2 sizes for C = 64 / 32.  Epilogue arithmetic is packed fp32 (FFMA2 / FMUL2).
 #include <cuda.h>
+
+#include <cstdio>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "tc_ptx.cuh"
@@ -34,7 +36,7 @@ namespace trunk {
 
 using namespace ou::tc;
 
-constexpr int S = 3;                          // item slots per CTA
+constexpr int MAXS = 6;                       // most item slots per CTA any configuration uses
 // Warps per slot: 4 (one per TMEM lane quarter, a thread owns a whole accumulator row) or 8 (two column
 // halves per quarter).  Measured on B200: 8 is 25 % SLOWER -- 25 warps leave only 72 registers per
 // thread (spills), and shared memory is already the busiest unit: the N = 32 / 64 MMAs re-read their
@@ -42,14 +44,14 @@ constexpr int S = 3;                          // item slots per CTA
 // traffic).  ncu at C = 64: tensor pipe 33 % active, issue slots 36 %, i.e. what is left on the table
 // is the latency of each slot's serial T0 -> MMA -> E1 -> MMA -> E2 -> MMA -> E3 chain; more slots would
 // hide it but do not fit the 227 KB of shared memory next to the 11 resident weight taps.
-constexpr int WPS = 4;
-constexpr int NTHREADS = (1 + WPS * S) * 32;  // 416
+// Both are template parameters of the kernel (S slots x WPS warps); launch_c picks the configuration per
+// channel count (OU_TRUNK_CFG32 / OU_TRUNK_CFG64 = "S,WPS" override it for A/B runs).
 constexpr int TAPS1 = 5, TAPS2 = 3, TAPS3 = 3, NTAPS = TAPS1 + TAPS2 + TAPS3;
 constexpr int SLOT_COLS = 64;                 // TMEM columns per slot (= W * C)
 
 struct TrunkArgs {
-  long long* trace;   // debug (ou_debug_set_trace): CTA 0 stamps clock64(): [0..63][8] slot-0 items, then
-                      // [64..127][8] MMA-warp issue log (event = slot * 3 + stage, round-robin over 64 rows)
+  long long* trace;   // debug (ou_debug_set_trace): CTA 0 stamps clock64(): [0..31][16] slot-0 items (leader thread:
+                      // start, x landed, T0 done, handed over, MMA1 issued, acc1, E1 done, handed over, MMA2 issued, ...)
   ou_trunk_params p;
   int items_per_clip, total_items;
   int x_box_rows, x_boxes;
@@ -70,7 +72,7 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
   return ok != 0;
 }
 
-template <int C>
+template <int C, int S = 3>
 struct Geo {
   static constexpr int W = 64 / C;                     // 128-row sub-tiles per item
   static constexpr int ROWB = C * 2;                   // bytes per activation row
@@ -82,7 +84,7 @@ struct Geo {
   static constexpr uint32_t W_TAP_BYTES = (uint32_t)(C * ROWB);
   static constexpr uint32_t SWZ_MASK = ROWB == 128 ? 7u : 3u;
   static constexpr uint32_t W_BYTES = NTAPS * W_TAP_BYTES;
-  static constexpr uint32_t TAIL_BYTES = 8u * (1 + 5 * S) + 16u + 4u * (S * 2 * C + 2 * C);
+  static constexpr uint32_t TAIL_BYTES = 8u * (1 + 5 * S) + 32u + 4u * (S * 2 * C + 2 * C);   // barriers, TMEM slot, coefficients
   static constexpr size_t SMEM = 1024 + W_BYTES + (size_t)S * 2 * BUF_BYTES + TAIL_BYTES;
 };
 
@@ -95,11 +97,11 @@ __device__ __forceinline__ uint32_t swz(uint32_t base, uint32_t off) {
 
 struct Smem {
   uint32_t w;                    // NTAPS weight tiles
-  uint32_t x[S], cb[S];
+  uint32_t x[MAXS], cb[MAXS];
   uint32_t w_full;
-  uint32_t x_full[S], sc_full[S], xp_ready[S], c_ready[S], acc_full[S];
+  uint32_t x_full[MAXS], sc_full[MAXS], acc_full[MAXS];
   uint32_t tmem_slot;
-  uint32_t coef1[S];             // fp32 [c0 | c1][C] of the slot's current clip (conv1 epilogue)
+  uint32_t coef1[MAXS];           // fp32 [c0 | c1][C] of the slot's current clip (conv1 epilogue)
   uint32_t bias2, coef3;         // fp32 [C]: conv2 bias; s3 * conv3 bias
 };
 
@@ -126,90 +128,22 @@ __device__ __forceinline__ void issue_stage(uint32_t a_buf, uint32_t w_buf, uint
   __syncwarp();
 }
 
-template <int C>
-__device__ __forceinline__ void mma_role(const TrunkArgs& a, const Smem& sm, uint32_t tmem_base,
-                                         int n_items, const CUtensorMap* tm_w1, const CUtensorMap* tm_w2,
-                                         const CUtensorMap* tm_w3, int lane) {
-  using G = Geo<C>;
-  if (lane == 0) {
-    mbar_arrive_expect_tx(sm.w_full, G::W_BYTES);
-    for (int q = 0; q < TAPS1; q++) tma_load_3d(sm.w + q * G::W_TAP_BYTES, tm_w1, 0, 0, q, sm.w_full);
-    for (int q = 0; q < TAPS2; q++)
-      tma_load_3d(sm.w + (TAPS1 + q) * G::W_TAP_BYTES, tm_w2, 0, 0, q, sm.w_full);
-    for (int q = 0; q < TAPS3; q++)
-      tma_load_3d(sm.w + (TAPS1 + TAPS2 + q) * G::W_TAP_BYTES, tm_w3, 0, 0, q, sm.w_full);
-  }
-  __syncwarp();
-  mbar_wait(sm.w_full, 0);
-  tc_fence_after();
-
-  const uint64_t hi64 = (uint64_t)a.desc_hi << 32;
-  const uint32_t idesc = a.idesc;
-  int stage[S], left[S];
-  uint32_t ph_xp[S], ph_c[S];
-#pragma unroll
-  for (int s = 0; s < S; s++) {
-    stage[s] = 0;
-    left[s] = n_items > s ? (n_items - s + S - 1) / S : 0;
-    ph_xp[s] = 0, ph_c[s] = 0;
-  }
-  int remaining = 3 * n_items;
-  int issued = 0;
-  while (remaining > 0) {
-    bool any = false;
-#pragma unroll
-    for (int s = 0; s < S; s++) {
-      if (left[s] == 0) continue;
-      const uint32_t d_tmem = tmem_base + (uint32_t)(s * SLOT_COLS);
-      if (stage[s] == 0) {
-        if (!mbar_test(sm.xp_ready[s], ph_xp[s])) continue;
-        tc_fence_after();
-        issue_stage<C, TAPS1>(sm.x[s], sm.w, d_tmem, sm.acc_full[s], idesc, hi64);
-        ph_xp[s] ^= 1;
-        stage[s] = 1;
-      } else {
-        if (!mbar_test(sm.c_ready[s], ph_c[s])) continue;
-        tc_fence_after();
-        if (stage[s] == 1) {
-          issue_stage<C, TAPS2>(sm.cb[s], sm.w + TAPS1 * G::W_TAP_BYTES, d_tmem, sm.acc_full[s], idesc, hi64);
-          stage[s] = 2;
-        } else {
-          issue_stage<C, TAPS3>(sm.cb[s], sm.w + (TAPS1 + TAPS2) * G::W_TAP_BYTES, d_tmem, sm.acc_full[s],
-                                idesc, hi64);
-          stage[s] = 0;
-          left[s]--;
-        }
-        ph_c[s] ^= 1;
-      }
-      if (a.trace != nullptr && blockIdx.x == 0 && lane == 0 && issued >= 72 && issued < 72 + 64 * 8) {
-        a.trace[512 + (issued - 72)] = clock64() * 16 + s * 4 + (stage[s] + 2) % 3;
-      }
-      issued++;
-      remaining--;
-      any = true;
-    }
-    if (!any) __nanosleep(20);
-  }
-}
-
 // ---------------------------------------------------------------------------------- slot warpgroup
-template <int NPRELU>
-__device__ __forceinline__ float out_act(float y, float s1, float s2) {
-  if (NPRELU > 0) y = prelu_f(y, s1);
-  if (NPRELU > 1) y = prelu_f(y, s2);
-  return y;
-}
-
-template <int C, bool HAS_SC, int NPRELU>
+template <int C, int S, int WPS, bool HAS_SC, int NPRELU, bool FASTP>
 __device__ __forceinline__ void slot_role(const TrunkArgs& a, const Smem& sm, uint32_t tmem_base, int slot,
                                           int n_items, const CUtensorMap* tm_x, const CUtensorMap* tm_sc,
                                           int warp, int lane) {
-  using G = Geo<C>;
+  using G = Geo<C, S>;
   const ou_trunk_params& p = a.p;
   const int quarter = warp & 3;                 // TMEM lane quarter this warp may read
-  const int half = ((warp - 1) % WPS) >> 2;     // which part of the channels this thread handles
+  const int wis = warp % WPS;                   // warp index inside the slot's warpgroup
+  const int half = wis >> 2;                    // which part of the channels this thread handles
   const int row = quarter * 32 + lane;          // accumulator row inside a 128-row sub-tile
-  const int wg_tid = (int)threadIdx.x - 32 - slot * (WPS * 32);
+  const int wg_tid = (int)threadIdx.x - slot * (WPS * 32);
+  const bool issuer_warp = wis == 0;            // issues the slot's own tcgen05.mma (one elected lane)
+  const uint64_t hi64 = (uint64_t)a.desc_hi << 32;
+  const uint32_t idesc = a.idesc;
+  const uint32_t d_tmem = tmem_base + (uint32_t)(slot * SLOT_COLS);
   const bool leader = row == 0 && half == 0;
   constexpr int HC = C / (WPS / 4);             // channels per thread
   constexpr int CHH = G::CH / (WPS / 4);        // 16-byte chunks per thread and row
@@ -218,8 +152,14 @@ __device__ __forceinline__ void slot_role(const TrunkArgs& a, const Smem& sm, ui
   // per-slot addresses resolved once (the struct is indexed dynamically only here)
   const uint32_t X = sm.x[slot], Cb = sm.cb[slot];
   const uint32_t coef1 = sm.coef1[slot];
-  const uint32_t bar_x = sm.x_full[slot], bar_sc = sm.sc_full[slot], bar_xp = sm.xp_ready[slot];
-  const uint32_t bar_c = sm.c_ready[slot], bar_acc = sm.acc_full[slot];
+  const uint32_t bar_x = sm.x_full[slot], bar_sc = sm.sc_full[slot], bar_acc = sm.acc_full[slot];
+  // hand-over of an operand tile from the warpgroup (generic-proxy stores, TMEM reads) to the slot's own
+  // MMA issue: every thread fences, the warpgroup meets on its named barrier, the issuer warp goes on
+  auto wg_handover = [&]() {
+    fence_proxy_async();
+    tc_fence_before();
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + slot), "n"(WPS * 32) : "memory");
+  };
   const uint32_t bias2 = sm.bias2, coef3 = sm.coef3;
   const float slope_in = p.prelu_in, slope_m1 = p.prelu_mid1, slope_m2 = p.prelu_mid2;
   const float s3 = p.scale3;
@@ -258,11 +198,15 @@ __device__ __forceinline__ void slot_role(const TrunkArgs& a, const Smem& sm, ui
     if (HAS_SC) load_sc(slot);
   }
 
-  uint32_t ph_x = 0, ph_sc = 0, ph_acc = 0;
+  uint32_t ph_x = 0, ph_acc = 0, ph_sc = 0;
+  if (issuer_warp && slot < n_items) {   // the 11 weight taps (TMA, issued by thread 0) have landed
+    mbar_wait(sm.w_full, 0);
+    tc_fence_after();
+  }
   int last_b = -1;
 #define TRUNK_STAMP(ev)                                                                     \
-  if (a.trace != nullptr && blockIdx.x == 0 && slot == 0 && leader && n / S >= 8 && n / S < 72) \
-    a.trace[(n / S - 8) * 8 + (ev)] = clock64();
+  if (a.trace != nullptr && blockIdx.x == 0 && slot == 0 && leader && n / S >= 8 && n / S < 40) \
+    a.trace[(n / S - 8) * 16 + (ev)] = clock64();
   for (int n = slot; n < n_items; n += S) {
     int b, t0;
     item_pos(n, b, t0);
@@ -316,26 +260,33 @@ __device__ __forceinline__ void slot_role(const TrunkArgs& a, const Smem& sm, ui
           sts_u4(swz<C>(X, (uint32_t)(row * G::ROWB + (ch0 + c) * 16)), prelu_act8(halo[c], a_in_hi, a_in_lo));
       }
     }
-    fence_proxy_async();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(bar_xp);
     TRUNK_STAMP(2)
+    wg_handover();
+    TRUNK_STAMP(3)
+    if (issuer_warp) {
+      tc_fence_after();
+      issue_stage<C, TAPS1>(X, sm.w, d_tmem, bar_acc, idesc, hi64);
+    }
+    TRUNK_STAMP(4)
 
-    // ---- stage 1: c1 = PReLU(FiLM((conv1 + b1 + sc) * s1)) -> Cb (bf16, swizzled)
+    // ---- stage 1: c1 = PReLU(FiLM((conv1 + b1 + sc) * s1)) -> Cb (16-bit, swizzled)
     mbar_wait(bar_acc, ph_acc);
     ph_acc ^= 1;
     tc_fence_after();
-    TRUNK_STAMP(3)
+    TRUNK_STAMP(5)
     if (leader && has_next) load_x(n + S);      // conv1's MMAs are done with X
     if (HAS_SC) {
       mbar_wait(bar_sc, ph_sc);
       ph_sc ^= 1;
     }
     // The accumulator is read in NQ chunks of 16 columns, chunk q + 1 in flight (tcgen05.ld) while chunk
-    // q is processed; with the per-chunk shared loads issued before the wait.
+    // q is processed; with the per-chunk shared loads issued before the wait.  Rows outside the clip
+    // must read as zeros to the next conv ("same" padding of the intermediate activation): a per-row
+    // branch (taken only in the two items at the ends of a clip), not a select per element.
     constexpr int QS = HC / 16;   // chunks per sub-tile and thread
     constexpr int NQ = G::W * QS;
     auto q_taddr = [&](int q) { return taddr + (uint32_t)((q / QS) * C + col0 + (q % QS) * 16); };
+    const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
     uint32_t rbuf[2][16];
     tmem_ld16(q_taddr(0), rbuf[0]);
 #pragma unroll
@@ -351,47 +302,50 @@ __device__ __forceinline__ void slot_role(const TrunkArgs& a, const Smem& sm, ui
         k0[j] = lds_f4(coef1 + 4u * (col0 + cc * 16 + j * 4));
         k1[j] = lds_f4(coef1 + 4u * (C + col0 + cc * 16 + j * 4));
       }
-      if (HAS_SC) {
-        scv[0] = lds_u4(swz<C>(Cb, (uint32_t)(i * G::ROWB + (ch0 + 2 * cc) * 16)));
-        scv[1] = lds_u4(swz<C>(Cb, (uint32_t)(i * G::ROWB + (ch0 + 2 * cc + 1) * 16)));
-      }
+      const uint32_t dst = swz<C>(Cb, (uint32_t)(i * G::ROWB + (ch0 + 2 * cc) * 16));
+      const uint32_t dst1 = swz<C>(Cb, (uint32_t)(i * G::ROWB + (ch0 + 2 * cc + 1) * 16));
+      if (HAS_SC) scv[0] = lds_u4(dst), scv[1] = lds_u4(dst1);
       tmem_ld_wait();
       if (q + 1 < NQ) tmem_ld16(q_taddr(q + 1), rbuf[(q + 1) & 1]);
       const uint32_t(&r)[16] = rbuf[q & 1];
+      if (inside) {
 #pragma unroll
-      for (int h = 0; h < 2; h++) {
-        const uint32_t* sw = reinterpret_cast<const uint32_t*>(&scv[h]);
-        uint4 o;
-        uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+        for (int h = 0; h < 2; h++) {
+          const uint32_t* sw = reinterpret_cast<const uint32_t*>(&scv[h]);
+          uint4 o;
+          uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
 #pragma unroll
-        for (int k = 0; k < 2; k++) {
-          const float4 c0 = k0[h * 2 + k], c1 = k1[h * 2 + k];
-          const int e = h * 8 + k * 4;
-          float a0 = __uint_as_float(r[e]), a1 = __uint_as_float(r[e + 1]);
-          float a2 = __uint_as_float(r[e + 2]), a3 = __uint_as_float(r[e + 3]);
-          if (HAS_SC) {
-            const float2 fa = act2_to_f2(sw[2 * k]), fb = act2_to_f2(sw[2 * k + 1]);
-            a0 += fa.x, a1 += fa.y, a2 += fb.x, a3 += fb.y;
+          for (int k = 0; k < 2; k++) {
+            const float4 c0 = k0[h * 2 + k], c1 = k1[h * 2 + k];
+            const int e = h * 8 + k * 4;
+            float2 a01 = u2_as_f2(r[e], r[e + 1]), a23 = u2_as_f2(r[e + 2], r[e + 3]);
+            if (HAS_SC) a01 = fadd2(a01, act2_to_f2(sw[2 * k])), a23 = fadd2(a23, act2_to_f2(sw[2 * k + 1]));
+            const float2 v01 = prelu2<FASTP>(ffma2(a01, make_float2(c0.x, c0.y), make_float2(c1.x, c1.y)), slope_m1);
+            const float2 v23 = prelu2<FASTP>(ffma2(a23, make_float2(c0.z, c0.w), make_float2(c1.z, c1.w)), slope_m1);
+            ow[2 * k] = f2_to_act2(v01.x, v01.y);
+            ow[2 * k + 1] = f2_to_act2(v23.x, v23.y);
           }
-          a0 = prelu_f(fmaf(c0.x, a0, c1.x), slope_m1), a1 = prelu_f(fmaf(c0.y, a1, c1.y), slope_m1);
-          a2 = prelu_f(fmaf(c0.z, a2, c1.z), slope_m1), a3 = prelu_f(fmaf(c0.w, a3, c1.w), slope_m1);
-          ow[2 * k] = inside ? f2_to_act2(a0, a1) : 0u;
-          ow[2 * k + 1] = inside ? f2_to_act2(a2, a3) : 0u;
+          sts_u4(h == 0 ? dst : dst1, o);
         }
-        sts_u4(swz<C>(Cb, (uint32_t)(i * G::ROWB + (ch0 + 2 * cc + h) * 16)), o);
+      } else {
+        sts_u4(dst, zero4);
+        sts_u4(dst1, zero4);
       }
     }
-    fence_proxy_async();
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(bar_c);
-    TRUNK_STAMP(4)
+    TRUNK_STAMP(6)
+    wg_handover();
+    TRUNK_STAMP(7)
+    if (issuer_warp) {
+      tc_fence_after();
+      issue_stage<C, TAPS2>(Cb, sm.w + TAPS1 * G::W_TAP_BYTES, d_tmem, bar_acc, idesc, hi64);
+    }
+    TRUNK_STAMP(8)
 
     // ---- stage 2: c2 = PReLU(conv2 + b2) -> Cb in place
     mbar_wait(bar_acc, ph_acc);
     ph_acc ^= 1;
     tc_fence_after();
-    TRUNK_STAMP(5)
+    TRUNK_STAMP(9)
     tmem_ld16(q_taddr(0), rbuf[0]);
 #pragma unroll
     for (int q = 0; q < NQ; q++) {
@@ -405,37 +359,46 @@ __device__ __forceinline__ void slot_role(const TrunkArgs& a, const Smem& sm, ui
       tmem_ld_wait();
       if (q + 1 < NQ) tmem_ld16(q_taddr(q + 1), rbuf[(q + 1) & 1]);
       const uint32_t(&r)[16] = rbuf[q & 1];
+      const uint32_t dst = swz<C>(Cb, (uint32_t)(i * G::ROWB + (ch0 + 2 * cc) * 16));
+      const uint32_t dst1 = swz<C>(Cb, (uint32_t)(i * G::ROWB + (ch0 + 2 * cc + 1) * 16));
+      if (inside) {
 #pragma unroll
-      for (int h = 0; h < 2; h++) {
-        uint4 o;
-        uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+        for (int h = 0; h < 2; h++) {
+          uint4 o;
+          uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
 #pragma unroll
-        for (int k = 0; k < 2; k++) {
-          const float4 b4 = bb[h * 2 + k];
-          const int e = h * 8 + k * 4;
-          const float a0 = prelu_f(__uint_as_float(r[e]) + b4.x, slope_m2);
-          const float a1 = prelu_f(__uint_as_float(r[e + 1]) + b4.y, slope_m2);
-          const float a2 = prelu_f(__uint_as_float(r[e + 2]) + b4.z, slope_m2);
-          const float a3 = prelu_f(__uint_as_float(r[e + 3]) + b4.w, slope_m2);
-          ow[2 * k] = inside ? f2_to_act2(a0, a1) : 0u;
-          ow[2 * k + 1] = inside ? f2_to_act2(a2, a3) : 0u;
+          for (int k = 0; k < 2; k++) {
+            const float4 b4 = bb[h * 2 + k];
+            const int e = h * 8 + k * 4;
+            const float2 v01 = prelu2<FASTP>(fadd2(u2_as_f2(r[e], r[e + 1]), make_float2(b4.x, b4.y)), slope_m2);
+            const float2 v23 = prelu2<FASTP>(fadd2(u2_as_f2(r[e + 2], r[e + 3]), make_float2(b4.z, b4.w)), slope_m2);
+            ow[2 * k] = f2_to_act2(v01.x, v01.y);
+            ow[2 * k + 1] = f2_to_act2(v23.x, v23.y);
+          }
+          sts_u4(h == 0 ? dst : dst1, o);
         }
-        sts_u4(swz<C>(Cb, (uint32_t)(i * G::ROWB + (ch0 + 2 * cc + h) * 16)), o);
+      } else {
+        sts_u4(dst, zero4);
+        sts_u4(dst1, zero4);
       }
     }
-    fence_proxy_async();
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(bar_c);
-    TRUNK_STAMP(6)
+    TRUNK_STAMP(10)
+    wg_handover();
+    TRUNK_STAMP(11)
+    if (issuer_warp) {
+      tc_fence_after();
+      issue_stage<C, TAPS3>(Cb, sm.w + (TAPS1 + TAPS2) * G::W_TAP_BYTES, d_tmem, bar_acc, idesc, hi64);
+    }
+    TRUNK_STAMP(12)
 
     // ---- stage 3: v = (conv3 + b3 + x) * s3 -> PReLUs -> global
     mbar_wait(bar_acc, ph_acc);
     ph_acc ^= 1;
     tc_fence_after();
-    TRUNK_STAMP(7)
+    TRUNK_STAMP(13)
     if (HAS_SC && leader && has_next) load_sc(n + S);   // conv3's MMAs are done with Cb
     tmem_ld16(q_taddr(0), rbuf[0]);
+    const float2 s3v = make_float2(s3, s3);
 #pragma unroll
     for (int q = 0; q < NQ; q++) {
       const int sub = q / QS, cc = q % QS;
@@ -457,30 +420,30 @@ __device__ __forceinline__ void slot_role(const TrunkArgs& a, const Smem& sm, ui
         for (int k = 0; k < 2; k++) {
           const float4 c1 = kk[h * 2 + k];
           const int e = h * 8 + k * 4;
-          const float2 fa = act2_to_f2(rw[2 * k]), fb = act2_to_f2(rw[2 * k + 1]);
-          const float a0 = fmaf(s3, __uint_as_float(r[e]) + fa.x, c1.x);
-          const float a1 = fmaf(s3, __uint_as_float(r[e + 1]) + fa.y, c1.y);
-          const float a2 = fmaf(s3, __uint_as_float(r[e + 2]) + fb.x, c1.z);
-          const float a3 = fmaf(s3, __uint_as_float(r[e + 3]) + fb.y, c1.w);
-          o.w[h * 4 + 2 * k] = f2_to_act2(out_act<NPRELU>(a0, p.prelu_out, p.prelu_out2),
-                                         out_act<NPRELU>(a1, p.prelu_out, p.prelu_out2));
-          o.w[h * 4 + 2 * k + 1] = f2_to_act2(out_act<NPRELU>(a2, p.prelu_out, p.prelu_out2),
-                                             out_act<NPRELU>(a3, p.prelu_out, p.prelu_out2));
+          float2 v01 = ffma2(fadd2(u2_as_f2(r[e], r[e + 1]), act2_to_f2(rw[2 * k])), s3v,
+                             make_float2(c1.x, c1.y));
+          float2 v23 = ffma2(fadd2(u2_as_f2(r[e + 2], r[e + 3]), act2_to_f2(rw[2 * k + 1])), s3v,
+                             make_float2(c1.z, c1.w));
+          if (NPRELU > 0) v01 = prelu2<FASTP>(v01, p.prelu_out), v23 = prelu2<FASTP>(v23, p.prelu_out);
+          if (NPRELU > 1) v01 = prelu2<FASTP>(v01, p.prelu_out2), v23 = prelu2<FASTP>(v23, p.prelu_out2);
+          o.w[h * 4 + 2 * k] = f2_to_act2(v01.x, v01.y);
+          o.w[h * 4 + 2 * k + 1] = f2_to_act2(v23.x, v23.y);
         }
       }
       if (valid) stg_v8(dst + col0 + cc * 16, o);
     }
-    tc_fence_before();   // TMEM reads ordered before the next item's MMAs (via xp_ready)
+    // (the TMEM reads above are ordered before the next item's MMAs by wg_handover() after its T0)
+    TRUNK_STAMP(14)
   }
 }
 
 // ---------------------------------------------------------------------------------- kernel
-template <int C, bool HAS_SC>
-__global__ void __launch_bounds__(NTHREADS, 1)
+template <int C, bool HAS_SC, int S, int WPS, bool FASTP>
+__global__ void __launch_bounds__(WPS * S * 32, 1)
 trunk_kernel(const TrunkArgs a, const __grid_constant__ CUtensorMap tm_x,
              const __grid_constant__ CUtensorMap tm_sc, const __grid_constant__ CUtensorMap tm_w1,
              const __grid_constant__ CUtensorMap tm_w2, const __grid_constant__ CUtensorMap tm_w3) {
-  using G = Geo<C>;
+  using G = Geo<C, S>;
   extern __shared__ uint8_t smem_raw[];
   const ou_trunk_params& p = a.p;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -496,11 +459,12 @@ trunk_kernel(const TrunkArgs a, const __grid_constant__ CUtensorMap tm_x,
   sm.w_full = at, at += 8;
 #pragma unroll
   for (int s = 0; s < S; s++) {
-    sm.x_full[s] = at, sm.sc_full[s] = at + 8, sm.xp_ready[s] = at + 16, sm.c_ready[s] = at + 24;
+    sm.x_full[s] = at, sm.sc_full[s] = at + 8;
     sm.acc_full[s] = at + 32;
     at += 40;
   }
   sm.tmem_slot = at, at += 16;
+  at = (at + 15u) & ~15u;       // the coefficient vectors are read as float4
 #pragma unroll
   for (int s = 0; s < S; s++) sm.coef1[s] = at, at += 8u * C;
   sm.bias2 = at, at += 4u * C;
@@ -511,8 +475,6 @@ trunk_kernel(const TrunkArgs a, const __grid_constant__ CUtensorMap tm_x,
     for (int s = 0; s < S; s++) {
       mbar_init(sm.x_full[s], 1);
       mbar_init(sm.sc_full[s], 1);
-      mbar_init(sm.xp_ready[s], WPS);
-      mbar_init(sm.c_ready[s], WPS);
       mbar_init(sm.acc_full[s], 1);
     }
     fence_barrier_init();
@@ -521,7 +483,8 @@ trunk_kernel(const TrunkArgs a, const __grid_constant__ CUtensorMap tm_x,
     sts_f1(sm.bias2 + 4u * threadIdx.x, p.b2[threadIdx.x]);
     sts_f1(sm.coef3 + 4u * threadIdx.x, p.scale3 * p.b3[threadIdx.x]);
   }
-  if (warp == 0) tmem_alloc(sm.tmem_slot, 256);
+  constexpr uint32_t TMEM_COLS = S * SLOT_COLS <= 256 ? 256u : 512u;
+  if (warp == 0) tmem_alloc(sm.tmem_slot, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -531,22 +494,29 @@ trunk_kernel(const TrunkArgs a, const __grid_constant__ CUtensorMap tm_x,
   // items blockIdx.x, blockIdx.x + gridDim.x, ... ; the n-th of them runs in slot n % S
   const int n_items = (a.total_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
-  if (warp == 0) {
-    mma_role<C>(a, sm, tmem_base, n_items, &tm_w1, &tm_w2, &tm_w3, lane);
-  } else {
-    const int slot = (warp - 1) / WPS;
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(sm.w_full, G::W_BYTES);
+    for (int q = 0; q < TAPS1; q++) tma_load_3d(sm.w + q * G::W_TAP_BYTES, &tm_w1, 0, 0, q, sm.w_full);
+    for (int q = 0; q < TAPS2; q++)
+      tma_load_3d(sm.w + (TAPS1 + q) * G::W_TAP_BYTES, &tm_w2, 0, 0, q, sm.w_full);
+    for (int q = 0; q < TAPS3; q++)
+      tma_load_3d(sm.w + (TAPS1 + TAPS2 + q) * G::W_TAP_BYTES, &tm_w3, 0, 0, q, sm.w_full);
+  }
+  __syncwarp();
+  {
+    const int slot = warp / WPS;
     const int nprelu = p.has_prelu_out2 ? 2 : (p.has_prelu_out ? 1 : 0);
     if (nprelu == 0)
-      slot_role<C, HAS_SC, 0>(a, sm, tmem_base, slot, n_items, &tm_x, &tm_sc, warp, lane);
+      slot_role<C, S, WPS, HAS_SC, 0, FASTP>(a, sm, tmem_base, slot, n_items, &tm_x, &tm_sc, warp, lane);
     else if (nprelu == 1)
-      slot_role<C, HAS_SC, 1>(a, sm, tmem_base, slot, n_items, &tm_x, &tm_sc, warp, lane);
+      slot_role<C, S, WPS, HAS_SC, 1, FASTP>(a, sm, tmem_base, slot, n_items, &tm_x, &tm_sc, warp, lane);
     else
-      slot_role<C, HAS_SC, 2>(a, sm, tmem_base, slot, n_items, &tm_x, &tm_sc, warp, lane);
+      slot_role<C, S, WPS, HAS_SC, 2, FASTP>(a, sm, tmem_base, slot, n_items, &tm_x, &tm_sc, warp, lane);
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, 256);
+  if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
 // ---------------------------------------------------------------------------------- host side
@@ -588,9 +558,9 @@ static int encode3(CUtensorMap* tm, const void* base, int c, uint64_t d1, uint64
   return OU_OK;
 }
 
-template <int C>
-static int launch_c(const ou_trunk_params* p, cudaStream_t st) {
-  using G = Geo<C>;
+template <int C, int S, int WPS>
+static int launch_cfg(const ou_trunk_params* p, cudaStream_t st) {
+  using G = Geo<C, S>;
   TrunkArgs a;
   a.trace = ou::tc::g_trace;
   a.p = *p;
@@ -618,13 +588,32 @@ static int launch_c(const ou_trunk_params* p, cudaStream_t st) {
   if ((rc = encode3(&tm_w2, p->w2, C, (uint64_t)C, TAPS2, C, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, "w2"))) return rc;
   if ((rc = encode3(&tm_w3, p->w3, C, (uint64_t)C, TAPS3, C, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, "w3"))) return rc;
 
-  auto kern = p->sc ? trunk_kernel<C, true> : trunk_kernel<C, false>;
-  static SmemConfig cfg[2];
-  if ((rc = ensure_smem(kern, (size_t)G::SMEM, cfg[p->sc ? 1 : 0], "ou_conv_trunk"))) return rc;
+  // FASTP: every epilogue PReLU slope in [0, 1] -> PReLU(x) = max(x, a x)
+  auto in01 = [](float a) { return a >= 0.f && a <= 1.f; };
+  const bool fastp = in01(p->prelu_mid1) && in01(p->prelu_mid2) && (!p->has_prelu_out || in01(p->prelu_out)) &&
+                     (!p->has_prelu_out2 || in01(p->prelu_out2));
+  auto kern = p->sc ? (fastp ? trunk_kernel<C, true, S, WPS, true> : trunk_kernel<C, true, S, WPS, false>)
+                    : (fastp ? trunk_kernel<C, false, S, WPS, true> : trunk_kernel<C, false, S, WPS, false>);
+  static SmemConfig cfg[4];
+  if ((rc = ensure_smem(kern, (size_t)G::SMEM, cfg[(p->sc ? 1 : 0) + (fastp ? 2 : 0)], "ou_conv_trunk"))) return rc;
   const int n_sms = num_sms();
   int grid = n_sms < a.total_items ? n_sms : a.total_items;
-  kern<<<grid, NTHREADS, G::SMEM, st>>>(a, tm_x, tm_sc, tm_w1, tm_w2, tm_w3);
+  kern<<<grid, WPS * S * 32, G::SMEM, st>>>(a, tm_x, tm_sc, tm_w1, tm_w2, tm_w3);
   return check_launch("ou_conv_trunk");
+}
+
+// Slot configuration: S = 3 slots x WPS = 4 warps.  Measured dead ends (profiles/README.md, round 2): 5 x 4 at
+// C = 32 (21 warps -> 80 registers, spills: 27 % slower), 2 x 8 and 4 x 4 (17 warps put 5 on one scheduler
+// -> 96 registers); the kernel is bound by instruction issue, more warps in flight do not help.
+template <int C>
+static int launch_c(const ou_trunk_params* p, cudaStream_t st) {
+  if constexpr (C == 32) {
+    // 4 slots fit next to the 22 KB of weights at C = 32 (16 warps -> 128 registers): measured 213 / 237 us
+    // against 233 / 245 us with 3 slots (enc / dec, cfg-2 sizes); OU_TRUNK_S32=3 for A/B runs
+    static const int s32 = [] { const char* e = getenv("OU_TRUNK_S32"); return e ? atoi(e) : 4; }();
+    if (s32 == 4) return launch_cfg<C, 4, 4>(p, st);
+  }
+  return launch_cfg<C, 3, 4>(p, st);
 }
 
 }  // namespace trunk

@@ -80,11 +80,15 @@ __global__ void __launch_bounds__(256) dft_power_kernel(const float* __restrict_
 __global__ void mel_project_kernel(const float* __restrict__ power, const float* __restrict__ fb,
                                    float* __restrict__ mel, float* __restrict__ energy, int n_freq, int n_mels,
                                    int frames) {
-  extern __shared__ float pw[];   // [n_freq]
+  // [n_freq] padded to a multiple of 4 floats + 4 (zero filled): the unrolled dot-product loop below is
+  // compiled to 12-byte shared loads that may start at the last element (compute-sanitizer memcheck,
+  // profiles/r2_sanitize_summary.txt)
+  extern __shared__ float pw[];
   __shared__ float red[32];
   const int m = blockIdx.x, b = blockIdx.y;
   const float* prow = power + ((size_t)b * frames + m) * n_freq;
-  for (int k = threadIdx.x; k < n_freq; k += blockDim.x) pw[k] = prow[k];
+  const int n_pad = ((n_freq + 3) & ~3) + 4;
+  for (int k = threadIdx.x; k < n_pad; k += blockDim.x) pw[k] = k < n_freq ? prow[k] : 0.f;
   __syncthreads();
   float e = 0.f;
   for (int j = threadIdx.x; j < n_mels; j += blockDim.x) {
@@ -188,7 +192,7 @@ extern "C" int ou_mel_power(const float* x, const float* window, const float* fb
   ou::dft_power_kernel<<<grid, 256, 0, st>>>(x, window, dft, power, batch, t, n_fft, hop, pad_left, frames);
   int rc = ou::check_launch("ou_mel_power(dft)");
   if (rc) return rc;
-  ou::mel_project_kernel<<<dim3(frames, batch), 128, (size_t)n_freq * sizeof(float), st>>>(power, fb, mel, energy,
+  ou::mel_project_kernel<<<dim3(frames, batch), 128, (size_t)(((n_freq + 3) & ~3) + 4) * sizeof(float), st>>>(power, fb, mel, energy,
                                                                                            n_freq, n_mels, frames);
   return ou::check_launch("ou_mel_power(project)");
 }

@@ -217,6 +217,36 @@ __device__ __forceinline__ uint4 prelu_act8(uint4 v, uint32_t a_hi2, uint32_t a_
   return v;
 }
 
+// Packed fp32 pairs (Blackwell FFMA2 / FMUL2 / FADD2: one issue slot for two lanes' worth of fp32 math).
+// The epilogues of the tcgen05 kernels are bound by instruction issue, not by the tensor pipe or HBM.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b);
+  unsigned long long rc = *reinterpret_cast<unsigned long long*>(&c), rd;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  return *reinterpret_cast<float2*>(&rd);
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b), rd;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  return *reinterpret_cast<float2*>(&rd);
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b), rd;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  return *reinterpret_cast<float2*>(&rd);
+}
+__device__ __forceinline__ float2 u2_as_f2(uint32_t lo, uint32_t hi) {
+  return make_float2(__uint_as_float(lo), __uint_as_float(hi));
+}
+// PReLU of a pair.  FAST (every slope of the launch in [0, 1], checked on the host): max(x, a x) =
+// FMUL2 + 2 FMNMX (fma pipe + alu pipe) instead of multiply / compare / select per element.
+template <bool FAST>
+__device__ __forceinline__ float2 prelu2(float2 v, float a) {
+  const float2 t = fmul2(v, make_float2(a, a));
+  if (FAST) return make_float2(fmaxf(v.x, t.x), fmaxf(v.y, t.y));
+  return make_float2(v.x >= 0.f ? v.x : t.x, v.y >= 0.f ? v.y : t.y);
+}
+
 // One elected lane of a fully converged warp (the compiler keeps warp-uniform operands in uniform
 // registers across this predicate; `if (lane == 0)` would force a per-instruction R2UR shuffle).
 __device__ __forceinline__ bool elect_one() {

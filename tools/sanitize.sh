@@ -19,7 +19,7 @@ for tool in $TOOLS; do
   extra=""
   [ "$tool" = memcheck ] && extra="--leak-check no"
   [ "$tool" = racecheck ] && extra="--racecheck-report all"
-  OU_GPU_TEST_TIMEOUT=1200 timeout ${SANITIZE_TIMEOUT:-1500} "$CS" --tool "$tool" $extra --target-processes all --print-limit 20 \
+  OU_GPU_TEST_TIMEOUT=1200 timeout ${SANITIZE_TIMEOUT:-1500} "$CS" --tool "$tool" $extra --target-processes all --print-limit 2000 \
       --error-exitcode 86 \
       python -m pytest tests/test_gpu_kernels.py -q -m gpu -p no:cacheprovider -k "$SUBSET" \
       > "$log" 2>&1
@@ -28,4 +28,7 @@ for tool in $TOOLS; do
   summ=$(grep -E "ERROR SUMMARY|RACECHECK SUMMARY" "$log" | tail -1)
   tests=$(grep -E "passed|failed" "$log" | tail -1)
   echo "$tool: rc=$rc  reports=$errs  [$summ]  pytest: $tests" | tee -a gpurun_out/sanitize_summary.txt
+  # where the reports point (kernel + source line), most frequent first
+  grep -E "^=========     (at |Write Thread|Read Thread)" "$log" | sed -E 's/\+0x[0-9a-f]+//; s/[Tt]hread \([0-9,]+\)/thread/; s/\(ou::[A-Za-z]+\)//' \
+      | sort | uniq -c | sort -rn | head -12 | sed 's/^/    /' | tee -a gpurun_out/sanitize_summary.txt
 done

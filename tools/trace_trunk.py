@@ -45,17 +45,12 @@ for name, c, t, sc in (("C64 enc", 64, 64080, False), ("C64 dec", 64, 64080, Tru
     torch.cuda.synchronize()
     L.ou_debug_set_trace(None)
     tr = tr.cpu()
-    sl = tr[:512].reshape(64, 8)
+    sl = tr[:512].reshape(32, 16)[:, :15]
     ok = sl[:, 0] > 0
     sl = sl[ok].double()
-    names = ["wait x", "T0", "wait acc1", "E1", "wait acc2", "E2", "wait acc3", "E3+coef"]
-    d = torch.cat([sl[:, 1:] - sl[:, :-1], (sl[1:, 0:1] - sl[:-1, 7:8]).mean(0, keepdim=True).expand(sl.shape[0], 1)], 1)
+    names = ["wait x", "T0", "bar", "issue1", "wait acc1", "E1", "bar", "issue2", "wait acc2", "E2", "bar", "issue3",
+             "wait acc3", "E3"]
+    d = sl[:, 1:] - sl[:, :-1]
     per_item = float((sl[1:, 0] - sl[:-1, 0]).float().mean())
     print(f"== {name}: {us:.1f} us, {byts / us / 1e3:.0f} GB/s; slot-0 item period {per_item:.0f} cycles")
     print("   " + "  ".join(f"{n}={float(d[:, i].float().mean()):.0f}" for i, n in enumerate(names)))
-    mm = tr[512:]
-    mm = mm[mm > 0]
-    clk, tag = mm // 16, mm % 16
-    gaps = (clk[1:] - clk[:-1]).float()
-    print(f"   MMA warp: mean gap between issues {float(gaps.mean()):.0f} cycles; first 18: "
-          + " ".join(f"s{int(x) // 4}M{int(x) % 4 + 1}+{int(gp)}" for x, gp in zip(tag[1:19], gaps[:18])))
