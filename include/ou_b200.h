@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define OU_ABI_VERSION 1
+#define OU_ABI_VERSION 2
 
 enum {
   OU_OK = 0,
@@ -96,6 +96,8 @@ typedef struct ou_conv_params {
   int32_t has_prelu_in, has_prelu_out, has_prelu_out2;
   float prelu_in, prelu_out, prelu_out2;
   float scale1, scale2;
+  int32_t max_ctas;       /* cap on the persistent grid (0 = one CTA per SM): the host leaves SMs to a
+                             kernel of another stream it wants to run concurrently (GRU overlap)  */
 } ou_conv_params;
 
 int ou_conv1d(const ou_conv_params* p, void* stream);
@@ -131,6 +133,7 @@ typedef struct ou_trunk_params {
   int32_t has_prelu_out, has_prelu_out2;
   float prelu_in, prelu_mid1, prelu_mid2, prelu_out, prelu_out2;
   float scale1, scale3;
+  int32_t max_ctas;         /* cap on the persistent grid (0 = one CTA per SM), as in ou_conv_params */
 } ou_trunk_params;
 
 int ou_conv_trunk(const ou_trunk_params* p, void* stream);

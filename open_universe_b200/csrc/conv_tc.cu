@@ -674,7 +674,7 @@ int plan(const ou_conv_params* p, TcArgs* a) {
     }
   if (!bn || p->cin % 16 || p->cout % 16) return OU_ERR_UNSUPPORTED;
   if (p->add2 && !p->add1) return OU_ERR_UNSUPPORTED;
-  const int g_num_sms = num_sms();
+  const int g_num_sms = p->max_ctas > 0 && p->max_ctas < num_sms() ? p->max_ctas : num_sms();
   a->p = *p;
   a->cb = cl_cb(p->cin);
   a->row_bytes = a->cb * 2;
@@ -778,7 +778,7 @@ int launch(const ou_conv_params* p, cudaStream_t st) {
                       (size_t)6 * a.bn * sizeof(float);
   static SmemConfig cfg;
   if ((rc = ensure_smem(conv1d_tc_kernel, smem, cfg, "ou_conv1d(tc)"))) return rc;
-  int per = num_sms() / a.n_ntiles;
+  int per = (p->max_ctas > 0 && p->max_ctas < num_sms() ? p->max_ctas : num_sms()) / a.n_ntiles;
   if (per < 1) per = 1;
   if (per > a.total_m_tiles) per = a.total_m_tiles;
   a.ctas_per_ntile = per;

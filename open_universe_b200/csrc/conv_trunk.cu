@@ -596,7 +596,7 @@ static int launch_cfg(const ou_trunk_params* p, cudaStream_t st) {
                     : (fastp ? trunk_kernel<C, false, S, WPS, true> : trunk_kernel<C, false, S, WPS, false>);
   static SmemConfig cfg[4];
   if ((rc = ensure_smem(kern, (size_t)G::SMEM, cfg[(p->sc ? 1 : 0) + (fastp ? 2 : 0)], "ou_conv_trunk"))) return rc;
-  const int n_sms = num_sms();
+  const int n_sms = p->max_ctas > 0 && p->max_ctas < num_sms() ? p->max_ctas : num_sms();
   int grid = n_sms < a.total_items ? n_sms : a.total_items;
   kern<<<grid, WPS * S * 32, G::SMEM, st>>>(a, tm_x, tm_sc, tm_w1, tm_w2, tm_w3);
   return check_launch("ou_conv_trunk");

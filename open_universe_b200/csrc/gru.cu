@@ -574,13 +574,23 @@ static int launch_gru_f16_bg(const GruArgs& a, cudaStream_t st, int* max_cluster
   cfg.blockDim = dim3(G::NT);
   cfg.dynamicSmemBytes = 0;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  // Highest launch priority: when the host overlaps this latency-bound recurrence with the convolutions
+  // of another half-batch (engine/runtime.py, two capture streams), its few CTAs must get SMs as soon as
+  // a conv kernel of the other stream retires, not queue behind that stream's next persistent grid.
+  static const int prio = [] {
+    int least = 0, greatest = 0;
+    if (cudaDeviceGetStreamPriorityRange(&least, &greatest) != cudaSuccess) cudaGetLastError();
+    return greatest;
+  }();
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = G::CS;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributePriority;
+  attr[1].val.priority = prio;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   if (max_clusters) {   // query only
     int n = 0;
     if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) {

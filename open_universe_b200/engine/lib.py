@@ -11,7 +11,7 @@ from ctypes import (POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int
 from pathlib import Path
 
 from ..build import LIB as LIB_PATH
-OU_ABI_VERSION = 1
+OU_ABI_VERSION = 2
 
 
 class ConvParams(Structure):
@@ -28,6 +28,7 @@ class ConvParams(Structure):
         ("has_prelu_in", c_int32), ("has_prelu_out", c_int32), ("has_prelu_out2", c_int32),
         ("prelu_in", c_float), ("prelu_out", c_float), ("prelu_out2", c_float),
         ("scale1", c_float), ("scale2", c_float),
+        ("max_ctas", c_int32),
     ]
 
 
@@ -43,6 +44,7 @@ class TrunkParams(Structure):
         ("prelu_in", c_float), ("prelu_mid1", c_float), ("prelu_mid2", c_float),
         ("prelu_out", c_float), ("prelu_out2", c_float),
         ("scale1", c_float), ("scale3", c_float),
+        ("max_ctas", c_int32),
     ]
 
 

@@ -188,9 +188,10 @@ def prepare_ops(prog, device, shared=None, tag=""):
 PROFILE = None
 
 
-def launch_conv(op, bufs, batch, gamma=None, beta=None, film_bstride=0, naive=False):
+def launch_conv(op, bufs, batch, gamma=None, beta=None, film_bstride=0, naive=False, max_ctas=0):
     fc, pk = op.fc, op.packed
     prm = lib.ConvParams()
+    prm.max_ctas = max_ctas
     prm.x = bufs[op.src].data_ptr()
     prm.w = pk["w"].data_ptr()
     prm.w_tc = pk["w_tc"].data_ptr() if pk["w_tc"] is not None else None
@@ -224,10 +225,11 @@ def launch_conv(op, bufs, batch, gamma=None, beta=None, film_bstride=0, naive=Fa
 USE_TRUNK = os.environ.get("OU_TRUNK", "1") != "0"
 
 
-def launch_trunk(op, bufs, batch, film=None, film_bstride=0):
+def launch_trunk(op, bufs, batch, film=None, film_bstride=0, max_ctas=0):
     """One ``ou_conv_trunk`` launch for the three ConvOps of a TrunkOp."""
     c1, c2, c3 = op.parts
     prm = lib.TrunkParams()
+    prm.max_ctas = max_ctas
     prm.x = bufs[c1.src].data_ptr()
     prm.w1, prm.w2, prm.w3 = (c.packed["w_tc"].data_ptr() for c in op.parts)
     prm.b1, prm.b2, prm.b3 = (c.packed["bias"].data_ptr() for c in op.parts)
@@ -259,12 +261,14 @@ class Executor:
         prepare_ops(prog, device, shared, tag)
         self.bufs = alloc_buffers(prog, device, skip=external)
         self.naive = False   # tests: route ConvOps through the fp32 CUDA-core reference kernel
+        self.max_ctas = 0    # cap on the persistent conv grids (0 = all SMs), see PipelinedScoreRunner
 
     def run(self, film=None, film_bstride=0, in_scale=None, coef=None, noise=None, xout=None,
-            net_out=None):
+            net_out=None, ops=None):
+        """Launch the program's ops in order (``ops``: a contiguous part of ``self.prog.ops``)."""
         L = lib.load()
         bufs, B = self.bufs, self.batch
-        ops = self.prog.ops
+        ops = self.prog.ops if ops is None else ops
         if self.naive or not USE_TRUNK:
             ops = P.flat_ops(ops)
         for op in ops:
@@ -272,13 +276,13 @@ class Executor:
                 e0 = torch.cuda.Event(enable_timing=True)
                 e0.record()
             if isinstance(op, P.TrunkOp):
-                launch_trunk(op, bufs, B, film, film_bstride)
+                launch_trunk(op, bufs, B, film, film_bstride, self.max_ctas)
             elif isinstance(op, P.ConvOp):
                 gamma = beta = None
                 if op.film_off is not None:
                     base = film.data_ptr() + 4 * op.film_off
                     gamma, beta = base, base + 4 * op.fc.cout
-                launch_conv(op, bufs, B, gamma, beta, film_bstride, self.naive)
+                launch_conv(op, bufs, B, gamma, beta, film_bstride, self.naive, self.max_ctas)
             elif isinstance(op, P.InputConvOp):
                 c, k = op.packed["w"].shape
                 lib.check(L.ou_input_conv(_ptr(bufs[op.src]), _ptr(op.packed["w"]),
@@ -484,13 +488,88 @@ class ScoreRunner:
         self.proj_exe.run()
 
     def step(self, x, film_row, per_clip_film, in_scale=None, coef=None, noise=None, xout=None,
-             net_out=None):
-        """One network evaluation.  x: (B,1,T) fp32.  film_row: first row of the FiLM table to use
-        (one row shared by all clips, or B consecutive rows if per_clip_film)."""
+             net_out=None, ops=None):
+        """One network evaluation (or the part ``ops`` of it).  x: (B,1,T) fp32.  film_row: first row of
+        the FiLM table to use (one row shared by all clips, or B consecutive rows if per_clip_film)."""
         self.exe.bufs["x"] = x
         film = self.film[film_row:]
         self.exe.run(film=film, film_bstride=self.film_cols if per_clip_film else 0,
-                     in_scale=in_scale, coef=coef, noise=noise, xout=xout, net_out=net_out)
+                     in_scale=in_scale, coef=coef, noise=noise, xout=xout, net_out=net_out, ops=ops)
+
+    def phases(self):
+        """(ops up to and including the GRU input projection, the recurrence, the rest) -- the recurrence is
+        a latency-bound kernel on a few SMs that ``PipelinedScoreRunner`` hides behind the other half-batch's
+        convolutions; None when the network has no recurrent bottleneck."""
+        ops = self.prog.ops
+        idx = [i for i, op in enumerate(ops) if isinstance(op, P.GruOp)]
+        if len(idx) != 1:
+            return None
+        i = idx[0]
+        return ops[:i], ops[i:i + 1], ops[i + 1:]
+
+
+# OU_PIPELINE=0: one full-batch op stream per step (round-1 behaviour) instead of two half-batch streams
+PIPELINE = os.environ.get("OU_PIPELINE", "1") != "0"
+
+
+class PipelinedScoreRunner:
+    """The score network for a batch split in two halves that run as two op streams on two CUDA streams
+    (SURVEY section 8(f) item 1).  Batch rows are independent end to end, so are the halves -- over the
+    WHOLE sampler loop, not just one step.  The bottleneck BiGRU is a serial recurrence (801 steps x
+    ~0.8 us) that keeps 8 SMs per (direction, 8 clips) busy whatever the batch: run alone it idles most
+    of the GPU for ~15 % of every step.  Here half B's encoder is ordered after half A's (one event per
+    step), which keeps the halves half a step apart: A's recurrence runs while B's encoder convolutions
+    use the other SMs, B's while A's decoder does.  The persistent conv / trunk grids are capped at
+    (SMs - CTAs of the other half's recurrence) so that both fit side by side (``max_ctas`` of the C
+    ABI), and ``ou_gru_bidir`` launches at the highest priority."""
+
+    def __init__(self, net, batch, t, device, shared=None):
+        self.batch, self.t, self.device = batch, t, device
+        b0 = (batch + 1) // 2
+        self.rows = [(0, b0), (b0, batch)]
+        self.halves = [ScoreRunner(net, hi - lo, t, device, shared) for lo, hi in self.rows]
+        self.film_cols = self.halves[0].film_cols
+        self.film = None
+        n_sms = torch.cuda.get_device_properties(device).multi_processor_count
+        for h, other in ((0, 1), (1, 0)):
+            gru_ctas = 2 * 8 * -(-self.halves[other].batch // 8)      # clusters of 8 CTAs per (direction, 8 clips)
+            self.halves[h].exe.max_ctas = max(n_sms - gru_ctas, n_sms // 2)
+            if os.environ.get("OU_PIPE_CAP"):        # A/B knob: explicit cap (0 = none)
+                self.halves[h].exe.max_ctas = int(os.environ["OU_PIPE_CAP"])
+        self.side = torch.cuda.Stream(device=device)
+        self.cond_lengths = self.halves[0].cond_lengths
+        self.cond_channels = self.halves[0].cond_channels
+
+    def set_sigmas(self, net_sigma):
+        self.film = self.halves[0].set_sigmas(net_sigma)
+        self.halves[1].film = self.film          # same table (one row per step), same device pointer
+        return self.film
+
+    def set_cond(self, cond_blocked):
+        for h, (lo, hi) in zip(self.halves, self.rows):
+            h.set_cond([c[lo:hi] for c in cond_blocked])
+
+    def loop_step(self, n, x, in_scale, coef, noise):
+        """Step ``n`` of the sampler for both halves; must be called with ``self.side`` already forked from
+        the current stream (``SamplerLoop._loop``)."""
+        main, side = torch.cuda.current_stream(), self.side
+        a, b = self.halves
+        (lo_a, hi_a), (lo_b, hi_b) = self.rows
+
+        def part(h, lo, hi, ops):
+            h.step(x[lo:hi], n, False, in_scale=in_scale[lo:hi], coef=coef[lo:hi],
+                   noise=None if noise is None else noise[lo:hi], xout=x[lo:hi], ops=ops)
+
+        enc_a, gru_a, dec_a = a.phases()
+        part(a, lo_a, hi_a, enc_a)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        with torch.cuda.stream(side):
+            if os.environ.get("OU_PIPE_STAGGER", "1") != "0":
+                side.wait_event(ev)              # B's encoder after A's: the halves stay half a step apart
+            part(b, lo_b, hi_b, None)
+        part(a, lo_a, hi_a, gru_a)
+        part(a, lo_a, hi_a, dec_a)
 
 
 # OU_GRAPH=0 launches the sampler loop kernel by kernel from Python instead of replaying a CUDA graph
@@ -523,6 +602,14 @@ class SamplerLoop:
 
     def _loop(self):
         sr, N = self.sr, self.n_steps
+        if isinstance(sr, PipelinedScoreRunner):
+            main = torch.cuda.current_stream()
+            sr.side.wait_stream(main)            # fork (inside a capture: the side stream joins it)
+            for n in range(self.n_start, N):
+                sr.loop_step(n, self.x, self.in_scale[n], self.coef[n],
+                             self.noise[n] if n < N - 1 else None)
+            main.wait_stream(sr.side)            # join
+            return
         for n in range(self.n_start, N):   # warm start skips the first steps (universe.py:326-334)
             sr.step(self.x, n, False, in_scale=self.in_scale[n], coef=self.coef[n],
                     noise=self.noise[n] if n < N - 1 else None, xout=self.x)
@@ -535,8 +622,13 @@ class SamplerLoop:
         side = torch.cuda.Stream(device=self.sr.device)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            self.sr.step(self.x, 0, False, in_scale=self.in_scale[0], coef=self.coef[0],
-                         noise=None, xout=self.x)
+            if isinstance(self.sr, PipelinedScoreRunner):
+                self.sr.side.wait_stream(side)
+                self.sr.loop_step(0, self.x, self.in_scale[0], self.coef[0], None)
+                side.wait_stream(self.sr.side)
+            else:
+                self.sr.step(self.x, 0, False, in_scale=self.in_scale[0], coef=self.coef[0],
+                             noise=None, xout=self.x)
         torch.cuda.current_stream().wait_stream(side)
         g = torch.cuda.CUDAGraph()
         n0 = lib.launch_count()
@@ -575,8 +667,15 @@ def get_sampler_loop(sr, n_steps, n_start=0):
     return loop
 
 
-def get_score_runner(net, batch, t, device):
+def get_score_runner(net, batch, t, device, pipelined=False):
+    """``pipelined``: the sampler loop's runner -- two half-batch op streams (``PipelinedScoreRunner``) when
+    the batch can be split and the network has a recurrent bottleneck; single evaluations
+    (``score_forward``, the EDM wrapper) and bench.py's kernel-by-kernel timing pass use the plain one."""
     device = torch.device(device)
+    profiling = PROFILE is not None and not os.environ.get("OU_PIPE_PROFILE")   # tools/pipe_timeline.py
+    if pipelined and PIPELINE and not profiling and batch >= 2 and getattr(net.encoder, "seq_model", "") == "gru":
+        return _get_runner(net, ("score2", batch, t, str(device)),
+                           lambda shared: PipelinedScoreRunner(net, batch, t, device, shared))
     return _get_runner(net, ("score", batch, t, str(device)),
                        lambda shared: ScoreRunner(net, batch, t, device, shared))
 

@@ -318,7 +318,7 @@ class Universe(torch.nn.Module):
                 x = self._oracle_score_sampler(mixn, tgt, sig, sigma_b, n_steps, epsilon, warm_start,
                                                fake_score_snr, rng)
             else:
-                sr = runtime.get_score_runner(self.get_score_model(), B, t_pad, dev)
+                sr = runtime.get_score_runner(self.get_score_model(), B, t_pad, dev, pipelined=True)
                 sr.set_sigmas(net_sigma)
                 sr.set_cond(cond)
                 # the N-step loop (universe.py:334-343) replays a CUDA graph over persistent
