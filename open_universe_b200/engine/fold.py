@@ -40,7 +40,12 @@ class FoldedConv:
 
 
 def effective_weight(mod):
-    """Weight of a (possibly old-style weight-normed) Conv1d / ConvTranspose1d / Linear."""
+    """Weight of a (possibly old-style weight-normed, possibly LoRA-adapted) Conv1d /
+    ConvTranspose1d / Linear.  A LoRA adapter (``open_universe_b200.lora``; reference lora/lora.py:53-56,
+    134-137, 213-215) contributes  W + alpha / rank * A B  -- merged here, at load time, so that the
+    adapted network runs through exactly the same kernels."""
+    if hasattr(mod, "lora_merged_weight"):
+        return mod.lora_merged_weight().detach().double()
     if hasattr(mod, "weight_g"):
         v = mod.weight_v.detach().double()
         g = mod.weight_g.detach().double()
@@ -49,8 +54,19 @@ def effective_weight(mod):
     return mod.weight.detach().double()
 
 
+def inner(mod):
+    """The Conv1d / ConvTranspose1d / Linear behind a LoRA adapter (or ``mod`` itself)."""
+    return mod.lora_inner() if hasattr(mod, "lora_inner") else mod
+
+
+def bias_of(mod):
+    """fp32 bias (or None) of a possibly LoRA-adapted layer."""
+    b = getattr(inner(mod), "bias", None)
+    return None if b is None else b.detach().float()
+
+
 def _bias(mod, n, like):
-    b = getattr(mod, "bias", None)
+    b = getattr(inner(mod), "bias", None)
     if b is None:
         return torch.zeros(n, dtype=torch.float64, device=like.device)
     return b.detach().double()

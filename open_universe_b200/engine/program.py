@@ -317,12 +317,12 @@ def lower_score_network(net, batch, t):
     if net.precoding is not None:
         raise NotImplementedError("precoding is not used by any shipped config")
     prog = Program(batch)
-    c0 = net.input_conv.out_channels
+    c0 = fold.inner(net.input_conv).out_channels
     prog.buf("x", "f32_bt", 1, t)
-    w_in = net.input_conv.weight.detach().float()[:, 0, :].contiguous()
+    w_in = fold.effective_weight(net.input_conv).float()[:, 0, :].contiguous()
     prog.buf("enc.in", "blocked", c0, t)
     prog.ops.append(InputConvOp("input_conv", "x", "enc.in", w_in,
-                                net.input_conv.bias.detach().float().contiguous(), t,
+                                fold.bias_of(net.input_conv).contiguous(), t,
                                 use_in_scale=True))
     enc, dec = net.encoder, net.decoder
     h, tl = "enc.in", t
@@ -362,10 +362,11 @@ def lower_score_network(net, batch, t):
                                            input_cond=f"sc{lvl}", res=skips[lvl],
                                            length=lengths[lvl], out_prelus=po)
     oc = net.output_conv
-    if oc.conv.out_channels != 1:
+    if fold.inner(oc.conv).out_channels != 1:
         raise NotImplementedError("output_channels != 1")
     w_out = fold.effective_weight(oc.conv)[0].float().contiguous()      # (C, k)
-    b_out = float(oc.conv.bias.detach()[0].item()) if oc.conv.bias is not None else 0.0
+    b_out = fold.bias_of(oc.conv)
+    b_out = float(b_out[0].item()) if b_out is not None else 0.0
     prog.ops.append(OutputOp("output_conv", h, w_out, b_out, tl, t))
     prog.meta["lengths"] = lengths
     prog.meta["cond_channels"] = [b.n_channels for b in dec.up_modules]
@@ -403,11 +404,11 @@ def lower_conditioner(net, batch, t, need_signal_tail=True):
     m0, _ = add_conv(prog, "mel.conv", "mel", "mel.c", fcm, frames)
     x_mel, _, _, _ = lower_conv_block(prog, mel.conv_block, "mel.block", m0, frames)
 
-    c0 = net.input_conv.out_channels
+    c0 = fold.inner(net.input_conv).out_channels
     w_in = fold.effective_weight(net.input_conv)[:, 0, :].float().contiguous()
     prog.buf("enc.in", "blocked", c0, t)
     prog.ops.append(InputConvOp("input_conv", "x", "enc.in", w_in,
-                                net.input_conv.bias.detach().float().contiguous(), t))
+                                fold.bias_of(net.input_conv).contiguous(), t))
     enc = net.encoder
     h, tl = "enc.in", t
     lengths = []

@@ -392,8 +392,8 @@ def embedding_spec(sb, device):
     """Device-resident parameters of a SigmaBlock / SimpleTimeEmbedding (sigma_block.py:36-78)."""
     if hasattr(sb, "freq"):
         return ("rff", sb.freq.detach().float().to(device).contiguous(), [
-            (lyr.lin.weight.detach().float().to(device).contiguous(),
-             lyr.lin.bias.detach().float().to(device).contiguous(), fold.prelu_slope(lyr.prelu))
+            (fold.effective_weight(lyr.lin).float().to(device).contiguous(),
+             fold.bias_of(lyr.lin).to(device).contiguous(), fold.prelu_slope(lyr.prelu))
             for lyr in (sb.layer1, sb.layer2, sb.layer3)])
     return ("simple", float(sb.weight.detach().reshape(-1)[0].item()),
             float(sb.bias.detach().reshape(-1)[0].item()))
@@ -450,7 +450,7 @@ class ScoreRunner:
         for lin, off, cout in self.prog.film_layers:
             assert off == sum(w.shape[0] for w in ws)
             ws.append(fold.effective_weight(lin).float())
-            bs.append(lin.bias.detach().float())
+            bs.append(fold.bias_of(lin))
         self.film_w = torch.cat(ws).to(device).contiguous()
         self.film_b = torch.cat(bs).to(device).contiguous()
         self.film_cols = self.prog.film_cols
@@ -508,8 +508,18 @@ class ScoreRunner:
         return ops[:i], ops[i:i + 1], ops[i + 1:]
 
 
-# OU_PIPELINE=0: one full-batch op stream per step (round-1 behaviour) instead of two half-batch streams
-PIPELINE = os.environ.get("OU_PIPELINE", "1") != "0"
+# Two half-batch op streams per step (PipelinedScoreRunner) pay when the recurrence is a large share of a
+# step, i.e. at small per-GPU batches: measured on B200 +8 % at B = 4 (cfg-4 share of a GPU), +2 % at
+# B = 32 x 8 s (cfg-2), -4 % at B = 64 x 4 s (cfg-3: twice the launches for a recurrence half as long).
+# OU_PIPELINE = auto (default: batch <= PIPELINE_MAX_BATCH) | 1 (always) | 0 (never, round-1 behaviour)
+PIPELINE = os.environ.get("OU_PIPELINE", "auto")
+PIPELINE_MAX_BATCH = 32
+
+
+def _pipeline_wanted(batch):
+    if PIPELINE == "0":
+        return False
+    return batch >= 2 and (PIPELINE == "1" or batch <= PIPELINE_MAX_BATCH)
 
 
 class PipelinedScoreRunner:
@@ -673,7 +683,7 @@ def get_score_runner(net, batch, t, device, pipelined=False):
     (``score_forward``, the EDM wrapper) and bench.py's kernel-by-kernel timing pass use the plain one."""
     device = torch.device(device)
     profiling = PROFILE is not None and not os.environ.get("OU_PIPE_PROFILE")   # tools/pipe_timeline.py
-    if pipelined and PIPELINE and not profiling and batch >= 2 and getattr(net.encoder, "seq_model", "") == "gru":
+    if pipelined and _pipeline_wanted(batch) and not profiling and getattr(net.encoder, "seq_model", "") == "gru":
         return _get_runner(net, ("score2", batch, t, str(device)),
                            lambda shared: PipelinedScoreRunner(net, batch, t, device, shared))
     return _get_runner(net, ("score", batch, t, str(device)),
@@ -838,11 +848,12 @@ def alias_free_snake(mod, x, conv=None, blocked=False, t=None):
     w = bias = None
     k = 1
     if conv is not None:
-        if conv.out_channels != 1 or conv.in_channels != c:
+        if fold.inner(conv).out_channels != 1 or fold.inner(conv).in_channels != c:
             raise ValueError("the fused conv must map all channels to one")
         w = fold.effective_weight(conv)[0].float().to(dev).contiguous()   # (C, k)
         k = w.shape[1]
-        bias = float(conv.bias.detach()[0].item()) if conv.bias is not None else 0.0
+        bias = fold.bias_of(conv)
+        bias = float(bias[0].item()) if bias is not None else 0.0
         out = torch.empty(b, 1, tt, dtype=torch.float32, device=dev)
     else:
         out = torch.empty(b, c, tt, dtype=torch.float32, device=dev)

@@ -152,11 +152,12 @@ def run_mel(op, bufs, quant=False):
 
 def film_table(prog, g):
     """g: (rows, noise_cond_dim) sigma embedding -> (rows, film_cols) FiLM table."""
+    from open_universe_b200.engine import fold
     from open_universe_b200.engine.fold import effective_weight
     cols = []
     for lin, off, cout in prog.film_layers:
         w = effective_weight(lin).float()
-        cols.append(g @ w.t() + lin.bias.detach().float())
+        cols.append(g @ w.t() + fold.bias_of(lin))
     return torch.cat(cols, dim=1) if cols else None
 
 

@@ -464,6 +464,33 @@ class UniverseOracle:
         gain = level / (mix_padded - mean).std(dim=(1, 2), keepdim=True).clamp(min=1e-5)
         return (target_padded - mean) * gain
 
+    def partial_diffusion(self, mix, n_steps, epsilon, t_final, noise):
+        """UniverseLoRA.partial_diffusion (networks/universe/lora.py:231-296): ``n_steps`` sampler steps from
+        t = 1 down to a per-clip final time ``t_final`` (B,), no padding, no post-processing.
+        mix (B, 1, T); ``noise``: the n_steps unit-variance tensors in draw order."""
+        d = self.cfg["diffusion"]
+        ratio = float(d["sigma_max"]) / float(d["sigma_min"])
+        delta_t = (1.0 - t_final) / (n_steps - 1)
+        mix = self.normalize(mix)
+        gamma = ratio ** -delta_t
+        eta = 1 - gamma**epsilon
+        beta = torch.sqrt(1 - gamma ** (2 * (epsilon - 1.0)))
+        time = mix.new_ones(mix.shape[0])
+        std = lambda t: float(d["sigma_min"]) * ratio ** t   # noqa: E731  (universe.py:380-386)
+        sigma = std(time)
+        cond, _, _ = self.condition(mix, x_wav=mix)
+        it = iter(noise)
+        x = next(it).to(mix) * sigma[:, None, None]
+        for _ in range(n_steps - 1):
+            score = self.score(x, sigma, cond)
+            time = time - delta_t
+            sigma_next = std(time)
+            z = next(it).to(mix) * sigma_next[:, None, None]
+            x = x + sigma[:, None, None] ** 2 * eta[:, None, None] * score + beta[:, None, None] * z
+            sigma = sigma_next
+        score = self.score(x, sigma, cond)
+        return x + sigma[:, None, None] ** 2 * score
+
     def enhance(self, mix, n_steps=None, epsilon=None, noise=None, rng=None, keep_rms=False,
                 use_aux_signal=False, ensemble=None, ensemble_stat="median", warm_start=None,
                 target=None, fake_score_snr=None):

@@ -51,6 +51,17 @@ NET_CASES = [
 ]
 
 
+# UniverseLoRA.forward (networks/universe/lora.py:298-392): LoRA adapters (rank 8) on every Conv1d /
+# ConvTranspose1d / Linear of both networks with non-zero factors; full sampler and partial diffusion
+# (lora.py:231-296: per-clip random final time, no padding, no post-processing)
+LORA_CASES = [
+    dict(name="upp16k_lora_full", model="upp16k", shape=(2, 4000), n_steps=3, seed=51, partial=False),
+    dict(name="upp16k_lora_partial", model="upp16k", shape=(2, 4800), n_steps=4, seed=52, partial=True),
+]
+LORA_RANK = 8
+LORA_SEED = 9
+
+
 def noise_rows(case):
     """Rows of the diffusion-noise tensors of an enhance case: batch x ensemble."""
     shape = tuple(case["shape"])

@@ -66,6 +66,22 @@ def det_state_dict(manifest, seed=0):
     return out
 
 
+def det_lora_factors(named_shapes, seed=0):
+    """Deterministic values for the LoRA factors ({key: shape} of the ``lora_*`` parameters): both factors
+    non-zero (the reference initialises one of them to zero, i.e. a no-op adapter) and small enough that
+    the merged weights stay in the regime of the base weights (delta ~ 10 % of W)."""
+    out = {}
+    for key in sorted(named_shapes):
+        shape = tuple(named_shapes[key])
+        r = _rng(seed, key)
+        if key.endswith(("lora_weight_a", "lora_linear_a")):          # (out, rank)
+            arr = r.standard_normal(shape) * 0.3 / np.sqrt(shape[1])
+        else:                                                          # (rank, in [* k])
+            arr = r.standard_normal(shape) * 0.3 / np.sqrt(shape[1])
+        out[key] = torch.from_numpy(arr.astype(np.float32))
+    return out
+
+
 def det_audio(shape, seed, level=0.05):
     """White-noise 'noisy speech' (synthetic white-noise inputs)."""
     r = np.random.default_rng([seed, 1])

@@ -21,8 +21,9 @@ HERE = Path(__file__).resolve().parent
 sys.path.insert(0, str(HERE))
 
 import ref_shim  # noqa: E402
-from cases import ENHANCE_CASES, MODELS, NET_CASES, WEIGHT_SEED, case_kwargs, noise_rows  # noqa: E402
-from detweights import (det_audio, det_noise, det_state_dict,  # noqa: E402
+from cases import (ENHANCE_CASES, LORA_CASES, LORA_RANK, LORA_SEED, MODELS, NET_CASES, WEIGHT_SEED,  # noqa: E402
+                   case_kwargs, noise_rows)
+from detweights import (det_audio, det_lora_factors, det_noise, det_state_dict,  # noqa: E402
                         is_constructor_buffer, subsample)
 
 torch.set_num_threads(8)
@@ -111,8 +112,50 @@ def run_net_case(case):
           "cond shapes", [tuple(c.shape) for c in cond])
 
 
+def run_lora_case(case):
+    """Reference UniverseLoRA (lora.py) around a freshly built base model with the deterministic weights."""
+    import importlib
+    get_model(case["model"])                     # writes the manifests
+    _models.pop(case["model"])                   # UniverseLoRA rewrites its base model: use a private copy
+    base, _ = get_model(case["model"])
+    _models.pop(case["model"])
+    ref_shim.install()
+    lora_mod = importlib.import_module("open_universe.networks.universe.lora")
+    n_steps = case["n_steps"]
+    m = lora_mod.UniverseLoRA(
+        model=base, fs=base.fs, losses=ref_shim.to_attr({}), training=ref_shim.to_attr({"ema_decay": 0.0}),
+        validation=ref_shim.to_attr({"enh_losses": {}}), optimizer=None, scheduler=None, grad_clipper=None,
+        diffusion=ref_shim.to_attr({"n_steps": n_steps, "epsilon": 1.3}), lora_rank=LORA_RANK,
+        use_partial_diffusion=case["partial"])
+    m.eval()
+    shapes = {k: list(v.shape) for k, v in m.state_dict().items()}
+    lora_keys = {k: v for k, v in shapes.items() if ".lora_" in k}
+    (HERE / f"{case['model']}_lora_manifest.json").write_text(
+        json.dumps({"manifest": shapes, "state_dict_order": list(shapes)}, indent=0, sort_keys=True))
+    missing, unexpected = m.load_state_dict(det_lora_factors(lora_keys, LORA_SEED), strict=False)
+    assert not unexpected
+    shape = tuple(case["shape"])
+    mix = det_audio(shape, case["seed"])
+    t = shape[-1]
+    t_len = t if case["partial"] else t + (base.tot_ds - t % base.tot_ds)
+    noise = det_noise(n_steps, (shape[0], 1, t_len), case["seed"])
+    ref_shim.set_injected_noise(noise)
+    lora_mod.randn = importlib.import_module("open_universe.networks.universe.universe").randn
+    torch.manual_seed(case["seed"])          # t_final = zeros(B).uniform_(0, 1) comes from the global generator
+    with torch.no_grad():
+        y = m(mix, n_steps=n_steps)
+    y = y.detach()       # partial_diffusion re-enables grad for its last steps (lora.py:272, 290)
+    np.savez(HERE / f"{case['name']}.npz", y=y.numpy())
+    print(case["name"], "rms", float(y.square().mean().sqrt()), "shape", tuple(y.shape))
+
+
 if __name__ == "__main__":
     only = set(sys.argv[1:])
+    for c in LORA_CASES:
+        if not only or c["name"] in only:
+            run_lora_case(c)
+    if only and only <= {c["name"] for c in LORA_CASES}:
+        sys.exit(0)
     for c in NET_CASES:
         if not only or c["name"] in only:
             run_net_case(c)
