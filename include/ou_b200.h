@@ -264,6 +264,26 @@ int ou_alias_free_snake(const void* x, int x_blocked, const float* alpha, const 
  * clock64() per warp role / tile / event into it (tools/trace_conv.py).  NULL disables. */
 int ou_debug_set_trace(void* device_buffer);
 
+/* ------------------------------------------------------------------------------------------
+ * Around the path.
+ *
+ * ou_resample_poly: polyphase windowed-sinc sample-rate conversion -- replaces the
+ *   torchaudio.functional.resample calls of the reference CLI (bin/enhance.py:77-80,188-190).
+ *   out[b][n*up + p] = sum_{j<klen} kern[p][j] * x[b][n*down + j - width], x zero outside [0, t_in);
+ *   kern fp32 [up][klen] is built on the host with torchaudio's published formula
+ *   (open_universe_b200/utils/resample.py); rates already divided by their gcd.
+ * ou_lsd: log-spectral distance -- replaces metrics/lsd.py:26-147 (log_spectral_distance with
+ *   center=True reflect padding, power = 2, normalized = "window", onesided):
+ *   out[b] = ( mean_{bins, frames} | L(input) - L(s_b * target) |^p )^(1/p),  L = 10 log10(P + eps) if db
+ *   else ln(P + eps); s_b = <input, target> / (<input, input> + eps) if scale_invariant else 1.
+ *   partial: fp32 [batch][frames] scratch; scale: fp32 [batch] scratch (scale_invariant only).
+ * ------------------------------------------------------------------------------------------ */
+int ou_resample_poly(const float* x, const float* kern, float* out, int batch, int t_in, int t_out,
+                     int down, int up, int width, int klen, void* stream);
+int ou_lsd(const float* input, const float* target, const float* window, float* partial, float* scale,
+           float* out, int batch, int t, int n_fft, int hop, int frames, float p, int db, float eps,
+           float window_sumsq, int scale_invariant, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -65,9 +65,11 @@ def save_audio(path, audio, fs):
 
 
 def resample(audio, fs, target_fs):
+    """Sample-rate conversion on the GPU (upstream: torchaudio.functional.resample, enhance.py:77-80): the
+    polyphase windowed-sinc kernel ``ou_resample_poly`` with torchaudio's default filter design."""
     if fs != target_fs:
-        import torchaudio
-        audio = torchaudio.functional.resample(audio, fs, target_fs)
+        from ..utils.resample import resample as gpu_resample
+        audio = gpu_resample(audio, fs, target_fs)
     return audio
 
 

@@ -82,6 +82,10 @@ SIGNATURES = {
     "ou_alias_free_snake": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int,
                                     c_void_p, c_int, c_void_p, c_float, c_int, c_void_p, c_int,
                                     c_int, c_int, c_void_p]),
+    "ou_resample_poly": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                 c_int, c_void_p]),
+    "ou_lsd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                       c_int, c_int, c_float, c_int, c_float, c_float, c_int, c_void_p]),
     "ou_debug_set_trace": (c_int, [c_void_p]),
 }
 
