@@ -253,12 +253,17 @@ def lower_conv_block(prog, blk, pfx, src, t_in, *, film_linear=None, input_cond=
     fc3 = fold.fold_prelu_conv(blk.conv3)
     film_off = prog.film(film_linear, c) if film_linear is not None else None
     cond_out = None
-    if raw_cond_out:
+    if raw_cond_out and film_off is None and input_cond is None:
         # the conditioner decoder exports conv1's raw output (condition.py:264-270): keep it raw
         # and let conv2 apply its PReLU on load
         cond_out, _ = add_conv(prog, pfx + ".conv1", h, pfx + ".cond", fc1, t)
         c1 = cond_out
     else:
+        if raw_cond_out:
+            # module-level ConvBlock.forward with FiLM / conditioning input AND the raw conv1 output
+            # requested (blocks.py:385-396): conv1 runs twice, once raw for ``cond_out`` and once with the
+            # fused epilogue for conv2 (only the layer-level API takes this path, never the networks)
+            cond_out, _ = add_conv(prog, pfx + ".conv1raw", h, pfx + ".cond", fc1, t)
         a2 = fc2.prelu_in
         fc2 = FoldedConv(fc2.w, fc2.bias, fc2.cin, fc2.cout, 1, 1, fc2.taps, fc2.tap_off, None)
         c1, _ = add_conv(prog, pfx + ".conv1", h, pfx + ".c1", fc1, t, add1=input_cond,
