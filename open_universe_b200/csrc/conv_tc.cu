@@ -40,8 +40,8 @@ namespace ou {
 namespace tc {
 
 constexpr int BM = 128;
-constexpr int XF_WARP0 = 2, EPI_WARP0 = 6, N_EPI_WARPS = 8;
-constexpr int NTHREADS = (EPI_WARP0 + N_EPI_WARPS) * 32;   // 448
+constexpr int XF_WARP0 = 2, EPI_WARP0 = 6, N_EPI_WARPS = 12;
+constexpr int NTHREADS = (EPI_WARP0 + N_EPI_WARPS) * 32;   // 576
 constexpr int MAX_A_STAGES = 8, MAX_B_STAGES = 16;
 
 struct TcArgs {
@@ -77,6 +77,8 @@ struct Ctx {
   uint32_t tmem_full, tmem_empty;            // [2]
   uint32_t coef;                             // fp32 [2 buffers][c0 | c1 | c2][bn]
   const float* coef_ptr;                     // the same array as a generic pointer (plain C++ loads)
+  const int* coltab_ptr;                     // int2 [16]: per 16-column group (output offset or -1, phase)
+  uint32_t coltab;
   uint32_t tmem_base;
   int nt, n0, mt0, mt_stride;
 };
@@ -324,7 +326,6 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& a, const Ctx& c, int
   const int cbo_shift = cbo == 64 ? 6 : (cbo == 32 ? 5 : 4);
   const size_t blk_stride = (size_t)t_out * cbo;
   const int n0 = c.n0;
-  const int n0_ph = n0 / cout, n0_co = n0 - n0_ph * cout;
   const act_t* add1 = (const act_t*)p.add1;
   const act_t* add2 = (const act_t*)p.add2;
   act_t* outp = (act_t*)p.out;
@@ -332,6 +333,19 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& a, const Ctx& c, int
   const float slope1 = p.prelu_out, slope2 = p.prelu_out2;
   const bool has_film = FILM;
   const float c0s = s1 * s2;     // column scale without FiLM
+
+  // column part of the output addressing, once per kernel (the first coefficient barrier publishes it):
+  // columns [n0 + 16 g, +16) = channels co.. of depth-to-space phase ph -> channel block, position in it
+  if (et < (bn >> 4)) {
+    const int n = n0 + 16 * et;
+    int off = -1, ph = 0;
+    if (n < n_total && !F32TM) {
+      ph = n / cout;
+      const int co = n - ph * cout;
+      off = (int)((size_t)(co >> cbo_shift) * blk_stride + (size_t)ph * cbo + (co & (cbo - 1)));
+    }
+    asm volatile("st.shared.v2.s32 [%0], {%1, %2};" ::"r"(c.coltab + 8u * et), "r"(off), "r"(ph) : "memory");
+  }
 
   int acc = 0;
   uint32_t acc_phase = 0;
@@ -365,42 +379,37 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& a, const Ctx& c, int
 
     const size_t clip_base = (size_t)b * cout * t_out;
     const int m_sub = a.m_sub;
-    // element offset of the 8-channel output vector at (sub-tile, tile column nl), or -1
-    auto out_offset = [&](int sub, int nl) -> long {
-      const int jj = m0 + sub * BM + row;
-      int co = n0_co + nl, ph = n0_ph;
-      while (co >= cout) co -= cout, ph++;
-      const int t = jj * up + ph;
-      if (jj >= p.rows || n0 + nl >= n_total || t >= t_out) return -1;
-      return (long)(clip_base + (size_t)(co >> cbo_shift) * blk_stride + (size_t)t * cbo + (co & (cbo - 1)));
-    };
     // Work units of this thread: (sub-tile, 16 columns) = one 32-byte output vector (16 consecutive
-    // channels of one time step); unit u = widx + k * nw is this warp's k-th.  Residual vectors are
-    // prefetched D units ahead (the first D while the MMAs of this tile still run) so that their HBM
-    // latency never sits on the epilogue's critical path.
-    constexpr int D = NADD == 1 ? 3 : (NADD == 2 ? 2 : 1);
+    // channels of one time step); unit u = widx + k * nw is this warp's k-th.  The column part of the
+    // output address (channel block, depth-to-space phase) comes from the per-kernel table `coltab`
+    // (int2 per 16-column group: element offset inside the clip or -1, phase); the row part is
+    // (m0 + sub * 128 + row) * up * cbo.  Residual vectors are prefetched D units ahead (the first D while
+    // the MMAs of this tile still run) so that their HBM latency never sits on the critical path.
+    constexpr int D = NADD == 1 ? 4 : (NADD == 2 ? 2 : 1);
     const int unit_shift = bn == 256 ? 4 : (bn == 128 ? 3 : (bn == 64 ? 2 : 1));   // log2(bn / 16)
     const int n_units = m_sub << unit_shift;
     const int nk = widx < n_units ? (n_units - widx + nw - 1) / nw : 0;
+    const int row_stride = up * cbo;                      // elements per GEMM row in the output layout
+    const long row_off0 = (long)(m0 + row) * row_stride;  // sub-tile 0
+    // element offset of unit u's 16-channel vector inside the output tensor, or -1
+    auto unit_offset = [&](int u) -> long {
+      const int sub = u >> unit_shift, g = u - (sub << unit_shift);
+      const int2 ct = *reinterpret_cast<const int2*>(c.coltab_ptr + 2 * g);
+      const int jj = m0 + sub * BM + row;
+      if (ct.x < 0 || jj >= p.rows || jj * up + ct.y >= t_out) return -1;
+      return (long)clip_base + row_off0 + (long)sub * (BM * row_stride) + ct.x;
+    };
     U8 pre1[D], pre2[D];
+    long poff[D];
     auto prefetch = [&](int d, int k) {
-      const int u = widx + k * nw;
-      const int sub = u >> unit_shift;
-      const int col = (u - (sub << unit_shift)) << 4;
-#pragma unroll
-      for (int i = 0; i < 8; i++) pre1[d].w[i] = 0u, pre2[d].w[i] = 0u;
-      if (NADD > 0 && k < nk) {
-        const long off = out_offset(sub, col);
-        if (off >= 0) {
-          pre1[d] = ldg_nc_v8(add1 + off);
-          if (NADD > 1) pre2[d] = ldg_nc_v8(add2 + off);
-        }
+      poff[d] = k < nk ? unit_offset(widx + k * nw) : -1;
+      if (NADD > 0 && poff[d] >= 0) {
+        pre1[d] = ldg_nc_v8(add1 + poff[d]);
+        if (NADD > 1) pre2[d] = ldg_nc_v8(add2 + poff[d]);
       }
     };
-    if (NADD > 0) {
 #pragma unroll
-      for (int d = 0; d < D; d++) prefetch(d, d);
-    }
+    for (int d = 0; d < D; d++) prefetch(d, d);
 
     mbar_wait(c.tmem_full + 8u * acc, acc_phase);
     tc_fence_after();
@@ -419,15 +428,9 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& a, const Ctx& c, int
         const int u = widx + k * nw;
         const int sub = u >> unit_shift;
         const int col = (u - (sub << unit_shift)) << 4;
-        const int j = m0 + sub * BM + row;
         uint32_t r[16];
-#define EPI_DETAIL(ev)                                                                                  \
-  if (a.trace != nullptr && blockIdx.x == 0 && ti == 8 && row == 0 && widx == 0 && k < 8)              \
-    a.trace[1024 + k * 4 + (ev)] = clock64();
-        EPI_DETAIL(0)
         tmem_ld16(taddr0 + (uint32_t)(sub * bn + col), r);
         tmem_ld_wait();
-        EPI_DETAIL(1)
         if (k == nk - 1) {
           // accumulators fully read by this warp: hand the TMEM buffer back before the store phase
           tc_fence_before();
@@ -435,55 +438,55 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& a, const Ctx& c, int
           if (lane == 0) mbar_arrive(c.tmem_empty + 8u * acc);
           if (row == 0 && widx == 0) trace_ev(a, 3, ti, 2);
         }
-        const U8 cur1 = pre1[d], cur2 = pre2[d];
-        if (NADD > 0) prefetch(d, k + D);
-        EPI_DETAIL(2)
-        if (j >= p.rows || n0 + col >= n_total) continue;
         if (F32TM) {
-          float4* dst = reinterpret_cast<float4*>(p.out_f32_tm + ((size_t)b * p.rows + j) * n_total + n0 + col);
+          const int j = m0 + sub * BM + row;
+          if (j < p.rows && n0 + col < n_total) {
+            float4* dst = reinterpret_cast<float4*>(p.out_f32_tm + ((size_t)b * p.rows + j) * n_total + n0 + col);
 #pragma unroll
-          for (int i = 0; i < 4; i++) {
-            const float4 x1 = lds_f4(coef + 4u * (bn + col + 4 * i));
-            dst[i] = make_float4(__uint_as_float(r[4 * i]) + x1.x, __uint_as_float(r[4 * i + 1]) + x1.y,
-                                 __uint_as_float(r[4 * i + 2]) + x1.z, __uint_as_float(r[4 * i + 3]) + x1.w);
+            for (int i = 0; i < 4; i++) {
+              const float4 x1 = lds_f4(coef + 4u * (bn + col + 4 * i));
+              dst[i] = make_float4(__uint_as_float(r[4 * i]) + x1.x, __uint_as_float(r[4 * i + 1]) + x1.y,
+                                   __uint_as_float(r[4 * i + 2]) + x1.z, __uint_as_float(r[4 * i + 3]) + x1.w);
+            }
           }
           continue;
         }
-        const long off = out_offset(sub, col);
-        if (off < 0) continue;
-        // coefficient vectors as plain shared-memory loads: the compiler is free to hoist them over the
-        // arithmetic of the previous group (volatile asm accessors would serialise every load).
-        // Arithmetic on packed fp32 pairs (FFMA2 / FADD2 / FMUL2): these layers are bound by the issue
-        // rate of the epilogue warps, not by the tensor pipe or HBM.
-        const float4* k0 = reinterpret_cast<const float4*>(coefp + col);
-        const float4* k1 = reinterpret_cast<const float4*>(coefp + bn + col);
-        const float4* k2 = reinterpret_cast<const float4*>(coefp + 2 * bn + col);
-        U8 o;
+        const long off = poff[d];
+        if (off >= 0) {
+          // coefficient vectors as plain shared-memory loads: the compiler is free to hoist them over the
+          // arithmetic of the previous group (volatile asm accessors would serialise every load).
+          // Arithmetic on packed fp32 pairs (FFMA2 / FADD2 / FMUL2).
+          const float4* k0 = reinterpret_cast<const float4*>(coefp + col);
+          const float4* k1 = reinterpret_cast<const float4*>(coefp + bn + col);
+          const float4* k2 = reinterpret_cast<const float4*>(coefp + 2 * bn + col);
+          U8 o;
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-          const float4 x1 = k1[i];
-          float4 x0 = make_float4(c0s, c0s, c0s, c0s);
-          if (FILM) x0 = k0[i];
-          float2 a01 = u2_as_f2(r[4 * i], r[4 * i + 1]), a23 = u2_as_f2(r[4 * i + 2], r[4 * i + 3]);
-          if (NADD > 0) {
-            a01 = fadd2(a01, act2_to_f2(cur1.w[2 * i]));
-            a23 = fadd2(a23, act2_to_f2(cur1.w[2 * i + 1]));
+          for (int i = 0; i < 4; i++) {
+            const float4 x1 = k1[i];
+            float4 x0 = make_float4(c0s, c0s, c0s, c0s);
+            if (FILM) x0 = k0[i];
+            float2 a01 = u2_as_f2(r[4 * i], r[4 * i + 1]), a23 = u2_as_f2(r[4 * i + 2], r[4 * i + 3]);
+            if (NADD > 0) {
+              a01 = fadd2(a01, act2_to_f2(pre1[d].w[2 * i]));
+              a23 = fadd2(a23, act2_to_f2(pre1[d].w[2 * i + 1]));
+            }
+            a01 = ffma2(make_float2(x0.x, x0.y), a01, make_float2(x1.x, x1.y));
+            a23 = ffma2(make_float2(x0.z, x0.w), a23, make_float2(x1.z, x1.w));
+            if (NADD > 1) {
+              float4 x2 = make_float4(s2, s2, s2, s2);
+              if (FILM) x2 = k2[i];
+              a01 = ffma2(make_float2(x2.x, x2.y), act2_to_f2(pre2[d].w[2 * i]), a01);
+              a23 = ffma2(make_float2(x2.z, x2.w), act2_to_f2(pre2[d].w[2 * i + 1]), a23);
+            }
+            if (NPRELU > 0) a01 = prelu2<false>(a01, slope1), a23 = prelu2<false>(a23, slope1);
+            if (NPRELU > 1) a01 = prelu2<false>(a01, slope2), a23 = prelu2<false>(a23, slope2);
+            o.w[2 * i] = f2_to_act2(a01.x, a01.y);
+            o.w[2 * i + 1] = f2_to_act2(a23.x, a23.y);
           }
-          a01 = ffma2(make_float2(x0.x, x0.y), a01, make_float2(x1.x, x1.y));
-          a23 = ffma2(make_float2(x0.z, x0.w), a23, make_float2(x1.z, x1.w));
-          if (NADD > 1) {
-            float4 x2 = make_float4(s2, s2, s2, s2);
-            if (FILM) x2 = k2[i];
-            a01 = ffma2(make_float2(x2.x, x2.y), act2_to_f2(cur2.w[2 * i]), a01);
-            a23 = ffma2(make_float2(x2.z, x2.w), act2_to_f2(cur2.w[2 * i + 1]), a23);
-          }
-          if (NPRELU > 0) a01 = prelu2<false>(a01, slope1), a23 = prelu2<false>(a23, slope1);
-          if (NPRELU > 1) a01 = prelu2<false>(a01, slope2), a23 = prelu2<false>(a23, slope2);
-          o.w[2 * i] = f2_to_act2(a01.x, a01.y);
-          o.w[2 * i + 1] = f2_to_act2(a23.x, a23.y);
+          stg_v8(outp + off, o);
         }
-        stg_v8(outp + off, o);
-        EPI_DETAIL(3)
+        // the slot's residual registers are free again: fetch the vectors of unit k + D into them
+        prefetch(d, k + D);
       }
     }
     if (row == 0 && widx == 0) trace_ev(a, 3, ti, 3);
@@ -516,6 +519,8 @@ conv1d_tc_kernel(const TcArgs a, const __grid_constant__ CUtensorMap tm_a,
   const uint32_t tmem_slot = c.tmem_empty + 16u;
   c.coef = tmem_slot + 16u;
   c.coef_ptr = reinterpret_cast<const float*>(smem_raw + (c.coef - raw));
+  c.coltab = c.coef + (uint32_t)(6 * a.bn) * 4u;
+  c.coltab_ptr = reinterpret_cast<const int*>(smem_raw + (c.coltab - raw));
 
   const bool use_xf = p.has_prelu_in != 0;
 
@@ -600,8 +605,8 @@ conv1d_tc_kernel(const TcArgs a, const __grid_constant__ CUtensorMap tm_a,
   } else {
     // epilogue: warps 6-13 always; warps 2-5 as a third warp per TMEM lane quarter when they have no
     // input PReLU to apply
-    const int nw = use_xf ? 2 : 3;
-    const int widx = warp >= EPI_WARP0 ? (warp - EPI_WARP0) >> 2 : 2;
+    const int nw = use_xf ? N_EPI_WARPS / 4 : N_EPI_WARPS / 4 + 1;
+    const int widx = warp >= EPI_WARP0 ? (warp - EPI_WARP0) >> 2 : N_EPI_WARPS / 4;
     const int nadd = p.add2 ? 2 : (p.add1 ? 1 : 0);
     const int nprelu = p.has_prelu_out2 ? 2 : (p.has_prelu_out ? 1 : 0);
     if (p.out_f32_tm) {
@@ -687,7 +692,7 @@ int plan(const ou_conv_params* p, TcArgs* a) {
   a->b_tx_bytes = (uint32_t)(bn * a->row_bytes);
   a->a_sub_bytes = (a->a_tx_bytes + 1023u) & ~1023u;
   a->b_stage_bytes = (a->b_tx_bytes + 1023u) & ~1023u;
-  const int budget = 232448 - 2048 - 6 * bn * 4;   // 227 KB minus alignment slack, barriers, coefficients
+  const int budget = 232448 - 2048 - 6 * bn * 4 - 128;   // 227 KB minus alignment slack, barriers, coefficients, column table
   const int nb_all = p->taps * a->n_kblocks;
   // Sub-tiles of 128 rows per scheduling unit.  A unit costs a fixed round of barrier hand-overs
   // between the five warp roles (~2 000 clk measured) whatever its size, which dominates layers whose
@@ -775,7 +780,7 @@ int launch(const ou_conv_params* p, cudaStream_t st) {
   }
   const size_t smem = 1024 + (size_t)a.a_stages * a.a_stage_bytes + (size_t)a.b_stages * a.b_stage_bytes +
                       (3 * MAX_A_STAGES + 2 * MAX_B_STAGES + 4) * sizeof(uint64_t) + 16 +
-                      (size_t)6 * a.bn * sizeof(float);
+                      (size_t)6 * a.bn * sizeof(float) + 128;
   static SmemConfig cfg;
   if ((rc = ensure_smem(conv1d_tc_kernel, smem, cfg, "ou_conv1d(tc)"))) return rc;
   int per = (p->max_ctas > 0 && p->max_ctas < num_sms() ? p->max_ctas : num_sms()) / a.n_ntiles;

@@ -396,6 +396,50 @@ class Universe(torch.nn.Module):
             x = x + sigma[:, n, None, None] ** 2 * eta * sc + beta * z
         return x + sigma[:, -1, None, None] ** 2 * score(x, sigma[:, -1])
 
+    # ------------------------------------------------------------------ validation (enhancement half)
+    def on_validation_epoch_start(self):
+        """universe.py:588-604: counters and the de-randomised generator of the validation loop."""
+        self.n_batches_est_done = 0
+        val = self.val_kwargs or {}
+        self.num_tb_samples = val.get("num_tb_samples", 0)
+        dev = next(self.parameters()).device
+        self.rng = torch.Generator(device=dev)
+        self.rng.manual_seed(682479040)
+
+    def on_validation_epoch_end(self):
+        self.rng = None
+
+    def validation_step(self, batch, batch_idx, dataset_i=0):
+        """The enhancement half of the reference's validation step (universe.py:651-660, 704-719):
+        ``est = enhance(mix, rng=self.rng)`` on the un-normalised batch, limited to
+        ``validation.max_enh_batches`` batches per epoch, then every configured ``enh_losses`` metric on
+        (est, target).  The log-spectral distance runs as a CUDA kernel (``metrics.LogSpectralDistance``,
+        always reported as ``"lsd"``); the score-matching loss bins of the first half (universe.py:606-650)
+        need the training forward (MDN losses, autograd) and are not built.  Returns {name: value} -- there
+        is no Lightning logger here -- or None once the batch budget is used up."""
+        if getattr(self, "rng", None) is None:
+            self.on_validation_epoch_start()
+        mix, target = batch[:2]
+        val = self.val_kwargs or {}
+        max_batches = val.get("max_enh_batches", None)
+        if max_batches is not None and self.n_batches_est_done >= max_batches:
+            return None
+        self.n_batches_est_done += 1
+        with torch.no_grad():
+            est = self.enhance(mix, rng=self.rng)
+            from ...metrics import LogSpectralDistance
+            if getattr(self, "_lsd_metric", None) is None:
+                self._lsd_metric = LogSpectralDistance().to(est.device)
+            out = {"lsd": self._lsd_metric(est, target.reshape(est.shape))}
+            for name, loss in (getattr(self, "enh_losses", None) or {}).items():
+                metric = loss(est, target)
+                if not isinstance(metric, dict):
+                    metric = {"": metric}
+                for sub, value in metric.items():
+                    out[name + sub] = value
+        out["est"] = est
+        return out
+
     # ------------------------------------------------------------------ EMA weight swap
     def train(self, mode=True, no_ema=False):
         """eval() copies the EMA shadow weights into the live parameters, train() restores them

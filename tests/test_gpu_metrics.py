@@ -80,3 +80,24 @@ def test_lsd_matches_torchaudio_spectrogram_and_module():
     want = (torch.norm(a - b, p=2, dim=(-2, -1)) / (b.shape[-1] * b.shape[-2]) ** 0.5).mean()
     got = LogSpectralDistance().to(DEV)(x.to(DEV), y.to(DEV)).cpu()
     assert torch.allclose(got, want, rtol=2e-4)
+
+
+def test_validation_step_enhancement_half():
+    """Universe.validation_step: de-randomised generator (seed 682479040, universe.py:602-604), enhance()
+    on the raw batch, LSD kernel on (est, target), batch budget ``validation.max_enh_batches``."""
+    from open_universe_b200.config import builtin_config, instantiate
+    torch.manual_seed(0)
+    m = instantiate(builtin_config("universepp_16k").model, _recursive_=False)
+    m.eval(no_ema=True)
+    m = m.to(DEV)
+    mix, target = det_audio((2, 4000), 21).to(DEV), det_audio((2, 4000), 22).to(DEV)
+    m.on_validation_epoch_start()
+    out = m.validation_step((mix, target), 0)
+    want = m.enhance(mix, rng=torch.Generator(device=DEV).manual_seed(682479040))
+    assert torch.equal(out["est"], want)
+    ref = torch_lsd(want.cpu(), target.cpu(), eps=1e-5).mean()
+    assert torch.allclose(out["lsd"].cpu(), ref, rtol=2e-4)
+    m.val_kwargs["max_enh_batches"] = 1
+    assert m.validation_step((mix, target), 1) is None
+    m.on_validation_epoch_end()
+    assert m.rng is None
