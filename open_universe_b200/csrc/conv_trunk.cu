@@ -85,7 +85,9 @@ struct Geo {
   static constexpr uint32_t SWZ_MASK = ROWB == 128 ? 7u : 3u;
   static constexpr uint32_t W_BYTES = NTAPS * W_TAP_BYTES;
   static constexpr uint32_t TAIL_BYTES = 8u * (1 + 5 * S) + 32u + 4u * (S * 2 * C + 2 * C);   // barriers, TMEM slot, coefficients
-  static constexpr size_t SMEM = 1024 + W_BYTES + (size_t)S * 2 * BUF_BYTES + TAIL_BYTES;
+  // no alignment slack: the dynamic shared window of a kernel without static shared memory starts 1024-byte
+  // aligned (checked at run time) -- with it, 4 slots do not fit next to the 90 KB of weights at C = 64
+  static constexpr size_t SMEM = W_BYTES + (size_t)S * 2 * BUF_BYTES + TAIL_BYTES;
 };
 
 // byte offset `off` inside a 1024-aligned buffer -> address in the hardware swizzle (16-byte chunk
@@ -444,12 +446,13 @@ trunk_kernel(const TrunkArgs a, const __grid_constant__ CUtensorMap tm_x,
              const __grid_constant__ CUtensorMap tm_sc, const __grid_constant__ CUtensorMap tm_w1,
              const __grid_constant__ CUtensorMap tm_w2, const __grid_constant__ CUtensorMap tm_w3) {
   using G = Geo<C, S>;
-  extern __shared__ uint8_t smem_raw[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   const ou_trunk_params& p = a.p;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   Smem sm;
-  uint32_t at = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint32_t at = smem_u32(smem_raw);
+  if ((at & 1023u) != 0u) __trap();   // the swizzled tiles need 1024-byte aligned bases
   sm.w = at, at += G::W_BYTES;
 #pragma unroll
   for (int s = 0; s < S; s++) {
@@ -607,6 +610,10 @@ static int launch_cfg(const ou_trunk_params* p, cudaStream_t st) {
 // -> 96 registers); the kernel is bound by instruction issue, more warps in flight do not help.
 template <int C>
 static int launch_c(const ou_trunk_params* p, cudaStream_t st) {
+  if constexpr (C == 64) {
+    static const int s64 = [] { const char* e = getenv("OU_TRUNK_S64"); return e ? atoi(e) : 3; }();
+    if (s64 == 4) return launch_cfg<C, 4, 4>(p, st);
+  }
   if constexpr (C == 32) {
     // 4 slots fit next to the 22 KB of weights at C = 32 (16 warps -> 128 registers): measured 213 / 237 us
     // against 233 / 245 us with 3 slots (enc / dec, cfg-2 sizes); OU_TRUNK_S32=3 for A/B runs
