@@ -284,6 +284,45 @@ int ou_lsd(const float* input, const float* target, const float* window, float* 
            float* out, int batch, int t, int n_fft, int hop, int frames, float p, int db, float eps,
            float window_sumsq, int scale_invariant, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Plan level: ONE call per network evaluation.
+ *
+ * A plan is a recorded list of the launches of ScoreNetwork.forward (score.py:277-297) for a fixed
+ * (batch, length) with every weight / activation pointer resolved; the host lowers the network once
+ * (engine/program.py), records the ops in launch order with ou_plan_add_*, and replays them with
+ * ou_plan_run.  What changes from one evaluation to the next comes in ou_step_args: the signal, the
+ * FiLM row(s) of this noise level (gamma of an op = film + film_off, beta behind it), the EDM input
+ * scale, the affine update coefficients of ou_output_sde, the noise and the outputs
+ * (universe.py:197-209, 334-343).  ou_plan_run(first, count) replays a contiguous part of the list
+ * (count < 0: to the end) -- the pipelined sampler runs encoder / recurrence / decoder of two
+ * half-batch plans on two streams.  The plan owns no device memory; the caller keeps every buffer
+ * alive.  Same return-code contract as the per-kernel entry points.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct ou_plan ou_plan;
+typedef struct ou_step_args {
+  const float* x;         /* fp32 (B, 1, T) signal: input conv and EDM / SDE update               */
+  const float* film;      /* fp32 FiLM row(s) of this evaluation, or NULL                          */
+  int32_t film_bstride;   /* floats between the rows of consecutive clips (0: one row for all)     */
+  const float* in_scale;  /* fp32 (B,) EDM input scale, or NULL                                    */
+  const float* coef;      /* fp32 (B, 3) update coefficients (ca, cb, cc), or NULL                 */
+  const float* noise;     /* fp32 (B, 1, T), or NULL                                               */
+  float* xout;            /* fp32 (B, 1, T) updated signal (may alias x), or NULL                  */
+  float* net_out;         /* fp32 (B, 1, T) raw network output, or NULL                            */
+} ou_step_args;
+
+int ou_plan_create(ou_plan** plan);
+int ou_plan_destroy(ou_plan* plan);
+int ou_plan_size(const ou_plan* plan);
+int ou_plan_add_conv(ou_plan* plan, const ou_conv_params* p, int32_t film_off /* -1: no FiLM */);
+int ou_plan_add_trunk(ou_plan* plan, const ou_trunk_params* p, int32_t film_off);
+int ou_plan_add_input_conv(ou_plan* plan, const float* w, const float* bias, void* out, int batch, int t,
+                           int cout, int k, int use_in_scale);
+int ou_plan_add_output_sde(ou_plan* plan, const void* src, const float* w, float bias, int batch, int cin,
+                           int k, int t_src, int t_sig);
+int ou_plan_add_gru(ou_plan* plan, const float* gx, const float* w_hh, const float* b_hh, const void* add,
+                    float scale, void* out, int batch, int t, int hidden);
+int ou_plan_run(const ou_plan* plan, const ou_step_args* args, int first, int count, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

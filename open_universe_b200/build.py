@@ -16,7 +16,7 @@ CSRC = Path(__file__).resolve().parent / "csrc"
 # runs; the product default is fp16 storage (csrc/common.cuh)
 BF16_VARIANT = os.environ.get("OU_ACT_BF16", "0") not in ("", "0")
 LIB = CSRC / ("libou_b200_bf16.so" if BF16_VARIANT else "libou_b200.so")
-SOURCES = ["api.cu", "conv.cu", "conv_tc.cu", "conv_trunk.cu", "gru.cu", "signal.cu", "mel.cu", "snake.cu", "metrics.cu"]
+SOURCES = ["api.cu", "conv.cu", "conv_tc.cu", "conv_trunk.cu", "gru.cu", "signal.cu", "mel.cu", "snake.cu", "metrics.cu", "plan.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 

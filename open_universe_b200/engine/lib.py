@@ -48,6 +48,11 @@ class TrunkParams(Structure):
     ]
 
 
+class StepArgs(Structure):
+    _fields_ = [("x", c_void_p), ("film", c_void_p), ("film_bstride", c_int32), ("in_scale", c_void_p),
+                ("coef", c_void_p), ("noise", c_void_p), ("xout", c_void_p), ("net_out", c_void_p)]
+
+
 # name -> (restype, argtypes); every symbol of include/ou_b200.h
 SIGNATURES = {
     "ou_abi_version": (c_int, []),
@@ -86,6 +91,18 @@ SIGNATURES = {
                                  c_int, c_void_p]),
     "ou_lsd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                        c_int, c_int, c_float, c_int, c_float, c_float, c_int, c_void_p]),
+    "ou_plan_create": (c_int, [POINTER(c_void_p)]),
+    "ou_plan_destroy": (c_int, [c_void_p]),
+    "ou_plan_size": (c_int, [c_void_p]),
+    "ou_plan_add_conv": (c_int, [c_void_p, POINTER(ConvParams), c_int32]),
+    "ou_plan_add_trunk": (c_int, [c_void_p, POINTER(TrunkParams), c_int32]),
+    "ou_plan_add_input_conv": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                       c_int]),
+    "ou_plan_add_output_sde": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_int, c_int,
+                                       c_int]),
+    "ou_plan_add_gru": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int,
+                                c_int, c_int]),
+    "ou_plan_run": (c_int, [c_void_p, POINTER(StepArgs), c_int, c_int, c_void_p]),
     "ou_debug_set_trace": (c_int, [c_void_p]),
 }
 

@@ -188,7 +188,8 @@ def prepare_ops(prog, device, shared=None, tag=""):
 PROFILE = None
 
 
-def launch_conv(op, bufs, batch, gamma=None, beta=None, film_bstride=0, naive=False, max_ctas=0):
+def conv_params(op, bufs, batch, gamma=None, beta=None, film_bstride=0, max_ctas=0):
+    """``ou_conv_params`` of a ConvOp bound to device buffers."""
     fc, pk = op.fc, op.packed
     prm = lib.ConvParams()
     prm.max_ctas = max_ctas
@@ -217,6 +218,11 @@ def launch_conv(op, bufs, batch, gamma=None, beta=None, film_bstride=0, naive=Fa
     prm.has_prelu_out2 = op.prelu_out2 is not None
     prm.prelu_out2 = op.prelu_out2 or 0.0
     prm.scale1, prm.scale2 = op.scale1, op.scale2
+    return prm
+
+
+def launch_conv(op, bufs, batch, gamma=None, beta=None, film_bstride=0, naive=False, max_ctas=0):
+    prm = conv_params(op, bufs, batch, gamma, beta, film_bstride, max_ctas)
     fn = lib.load().ou_conv1d_naive if naive else lib.load().ou_conv1d
     lib.check(fn(byref(prm), _stream()))
 
@@ -225,8 +231,8 @@ def launch_conv(op, bufs, batch, gamma=None, beta=None, film_bstride=0, naive=Fa
 USE_TRUNK = os.environ.get("OU_TRUNK", "1") != "0"
 
 
-def launch_trunk(op, bufs, batch, film=None, film_bstride=0, max_ctas=0):
-    """One ``ou_conv_trunk`` launch for the three ConvOps of a TrunkOp."""
+def trunk_params(op, bufs, batch, film=None, film_bstride=0, max_ctas=0):
+    """``ou_trunk_params`` of a TrunkOp bound to device buffers."""
     c1, c2, c3 = op.parts
     prm = lib.TrunkParams()
     prm.max_ctas = max_ctas
@@ -235,7 +241,7 @@ def launch_trunk(op, bufs, batch, film=None, film_bstride=0, max_ctas=0):
     prm.b1, prm.b2, prm.b3 = (c.packed["bias"].data_ptr() for c in op.parts)
     prm.sc = bufs[c1.add1].data_ptr() if c1.add1 else None
     prm.gamma = prm.beta = None
-    if c1.film_off is not None:
+    if c1.film_off is not None and film is not None:
         base = film.data_ptr() + 4 * c1.film_off
         prm.gamma, prm.beta = base, base + 4 * c1.fc.cout
     prm.film_bstride = film_bstride
@@ -248,6 +254,12 @@ def launch_trunk(op, bufs, batch, film=None, film_bstride=0, max_ctas=0):
     prm.has_prelu_out2 = c3.prelu_out2 is not None
     prm.prelu_out2 = c3.prelu_out2 or 0.0
     prm.scale1, prm.scale3 = c1.scale1, c3.scale1
+    return prm
+
+
+def launch_trunk(op, bufs, batch, film=None, film_bstride=0, max_ctas=0):
+    """One ``ou_conv_trunk`` launch for the three ConvOps of a TrunkOp."""
+    prm = trunk_params(op, bufs, batch, film, film_bstride, max_ctas)
     lib.check(lib.load().ou_conv_trunk(byref(prm), _stream()))
 
 
@@ -487,13 +499,69 @@ class ScoreRunner:
             self.proj_exe.bufs[f"cond{lvl}"] = c
         self.proj_exe.run()
 
+    def _build_plan(self):
+        """Record the evaluation as an ``ou_plan`` (include/ou_b200.h, plan level): every op with its device
+        pointers resolved, so that ``step`` is ONE foreign call instead of one per launch."""
+        L = lib.load()
+        exe, bufs, B = self.exe, self.exe.bufs, self.batch
+        handle = c_void_p()
+        lib.check(L.ou_plan_create(byref(handle)))
+        self._plan, self._plan_ctas = handle, exe.max_ctas
+        for op in exe.prog.ops:
+            off = -1
+            if isinstance(op, P.TrunkOp):
+                off = op.parts[0].film_off
+                prm = trunk_params(op, bufs, B, max_ctas=exe.max_ctas)
+                lib.check(L.ou_plan_add_trunk(handle, byref(prm), -1 if off is None else off))
+            elif isinstance(op, P.ConvOp):
+                prm = conv_params(op, bufs, B, max_ctas=exe.max_ctas)
+                lib.check(L.ou_plan_add_conv(handle, byref(prm), -1 if op.film_off is None else op.film_off))
+            elif isinstance(op, P.InputConvOp):
+                c, k = op.packed["w"].shape
+                lib.check(L.ou_plan_add_input_conv(handle, _ptr(op.packed["w"]), _ptr(op.packed["bias"]),
+                                                   _ptr(bufs[op.dst]), B, op.t, c, k, 1 if op.use_in_scale else 0))
+            elif isinstance(op, P.OutputOp):
+                c, k = op.packed["w"].shape
+                lib.check(L.ou_plan_add_output_sde(handle, _ptr(bufs[op.src]), _ptr(op.packed["w"]), op.bias, B,
+                                                   c, k, op.t, op.t_out))
+            elif isinstance(op, P.GruOp):
+                lib.check(L.ou_plan_add_gru(handle, _ptr(bufs[op.src]), _ptr(op.packed["w_hh"]),
+                                            _ptr(op.packed["b_hh"]), _ptr(bufs[op.add] if op.add else None),
+                                            op.scale, _ptr(bufs[op.dst]), B, op.t, op.hidden))
+            else:
+                raise TypeError(op)
+        assert L.ou_plan_size(handle) == len(exe.prog.ops)
+
+    def __del__(self):
+        plan = self.__dict__.get("_plan")
+        if plan is not None:
+            try:
+                lib.load().ou_plan_destroy(plan)
+            except Exception:
+                pass
+
     def step(self, x, film_row, per_clip_film, in_scale=None, coef=None, noise=None, xout=None,
-             net_out=None, ops=None):
-        """One network evaluation (or the part ``ops`` of it).  x: (B,1,T) fp32.  film_row: first row of
-        the FiLM table to use (one row shared by all clips, or B consecutive rows if per_clip_film)."""
-        self.exe.bufs["x"] = x
+             net_out=None, ops=None, op_range=None):
+        """One network evaluation (or the part ``ops`` / ``op_range`` = (first, count) of it).  x: (B,1,T)
+        fp32.  film_row: first row of the FiLM table to use (one row shared by all clips, or B consecutive
+        rows if per_clip_film)."""
         film = self.film[film_row:]
-        self.exe.run(film=film, film_bstride=self.film_cols if per_clip_film else 0,
+        bstride = self.film_cols if per_clip_film else 0
+        if USE_PLAN and PROFILE is None and USE_TRUNK and not self.exe.naive and (ops is None or op_range is not None):
+            if self.__dict__.get("_plan") is None or self._plan_ctas != self.exe.max_ctas:
+                self._build_plan()
+            args = lib.StepArgs()
+            args.x, args.film, args.film_bstride = x.data_ptr(), film.data_ptr(), bstride
+            args.in_scale = in_scale.data_ptr() if in_scale is not None else None
+            args.coef = coef.data_ptr() if coef is not None else None
+            args.noise = noise.data_ptr() if noise is not None else None
+            args.xout = xout.data_ptr() if xout is not None else None
+            args.net_out = net_out.data_ptr() if net_out is not None else None
+            first, count = op_range if op_range is not None else (0, -1)
+            lib.check(lib.load().ou_plan_run(self._plan, byref(args), first, count, _stream()))
+            return
+        self.exe.bufs["x"] = x
+        self.exe.run(film=film, film_bstride=bstride,
                      in_scale=in_scale, coef=coef, noise=noise, xout=xout, net_out=net_out, ops=ops)
 
     def phases(self):
@@ -506,6 +574,11 @@ class ScoreRunner:
             return None
         i = idx[0]
         return ops[:i], ops[i:i + 1], ops[i + 1:]
+
+    def phase_ranges(self):
+        """(first, count) of the three phases in the plan's op numbering."""
+        enc, gru, dec = self.phases()
+        return (0, len(enc)), (len(enc), 1), (len(enc) + 1, len(dec))
 
 
 # Two half-batch op streams per step (PipelinedScoreRunner) pay when the recurrence is a large share of a
@@ -566,21 +639,25 @@ class PipelinedScoreRunner:
         a, b = self.halves
         (lo_a, hi_a), (lo_b, hi_b) = self.rows
 
-        def part(h, lo, hi, ops):
+        def part(h, lo, hi, ops, rng=None):
             h.step(x[lo:hi], n, False, in_scale=in_scale[lo:hi], coef=coef[lo:hi],
-                   noise=None if noise is None else noise[lo:hi], xout=x[lo:hi], ops=ops)
+                   noise=None if noise is None else noise[lo:hi], xout=x[lo:hi], ops=ops, op_range=rng)
 
         enc_a, gru_a, dec_a = a.phases()
-        part(a, lo_a, hi_a, enc_a)
+        r_enc, r_gru, r_dec = a.phase_ranges()
+        part(a, lo_a, hi_a, enc_a, r_enc)
         ev = torch.cuda.Event()
         ev.record(main)
         with torch.cuda.stream(side):
             if os.environ.get("OU_PIPE_STAGGER", "1") != "0":
                 side.wait_event(ev)              # B's encoder after A's: the halves stay half a step apart
             part(b, lo_b, hi_b, None)
-        part(a, lo_a, hi_a, gru_a)
-        part(a, lo_a, hi_a, dec_a)
+        part(a, lo_a, hi_a, gru_a, r_gru)
+        part(a, lo_a, hi_a, dec_a, r_dec)
 
+
+# OU_PLAN=0: one ctypes call per launch (Executor.run) instead of one ``ou_plan_run`` per evaluation
+USE_PLAN = os.environ.get("OU_PLAN", "1") != "0"
 
 # OU_GRAPH=0 launches the sampler loop kernel by kernel from Python instead of replaying a CUDA graph
 USE_GRAPH = os.environ.get("OU_GRAPH", "1") != "0"

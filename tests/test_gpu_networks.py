@@ -282,3 +282,30 @@ def test_enhance_edge_cases_vs_oracle(name, shape, level, monkeypatch):
     a = abs_rms(got, want)
     print(name, "abs rms err", a, "out rms", float(want.square().mean().sqrt()))
     assert a < 1e-3, a
+
+
+def test_plan_replay_equals_per_launch_execution():
+    """ScoreNetwork.forward through ONE ou_plan_run call == the same ops launched one by one from Python
+    (Executor.run), bit for bit; also a partial replay (first, count) of the recorded list."""
+    from open_universe_b200.engine import runtime as R
+    m = our_model("upp16k")
+    net = m.get_score_model()
+    B, T = 2, 4800
+    x = det_noise(1, (B, 1, T), 3)[0].to(DEV) * 0.3
+    sigma = torch.tensor([0.3, 1.7], device=DEV)
+    cond = [torch.randn(B, c, t, device=DEV, generator=torch.Generator(device=DEV).manual_seed(i))
+            for i, (c, t) in enumerate([(512, 30), (256, 150), (128, 600), (64, 2400), (32, 4800)])]
+    n0 = R.lib.launch_count()
+    y_plan = net(x, sigma, cond)
+    n_plan = R.lib.launch_count() - n0
+    old = R.USE_PLAN
+    R.USE_PLAN = False
+    try:
+        y_ops = net(x, sigma, cond)
+    finally:
+        R.USE_PLAN = old
+    assert torch.equal(y_plan, y_ops)
+    r = R.get_score_runner(net, B, T, x.device)
+    assert r.__dict__.get("_plan") is not None and n_plan >= len(r.exe.prog.ops)
+    (e0, ne), (g0, ng), (d0, nd) = r.phase_ranges()
+    assert e0 == 0 and g0 == ne and d0 == ne + 1 and ne + ng + nd == len(r.exe.prog.ops)

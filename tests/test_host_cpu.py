@@ -251,3 +251,22 @@ def test_runner_cache_is_bounded_and_shares_packed_weights():
         mod.w.add_(1.0)                                       # weights changed: everything is rebuilt
     runtime._get_runner(mod, ("score", 1, n + 2, "cpu"), make("rebuilt"))
     assert "rebuilt" in made and len(runtime._cache(mod)["runners"]) == 1
+
+
+def test_plan_abi_records_ops_without_a_gpu():
+    """Plan-level C ABI (include/ou_b200.h): create / add / size / destroy are host-only bookkeeping."""
+    from ctypes import byref, c_void_p
+    from open_universe_b200.engine import lib
+    L = lib.load()
+    plan = c_void_p()
+    assert L.ou_plan_create(byref(plan)) == 0 and plan.value
+    prm = lib.ConvParams()
+    assert L.ou_plan_add_conv(plan, byref(prm), -1) == 0
+    tp = lib.TrunkParams()
+    assert L.ou_plan_add_trunk(plan, byref(tp), 0) == 0
+    assert L.ou_plan_size(plan) == 2
+    args = lib.StepArgs()
+    assert L.ou_plan_run(plan, byref(args), 5, -1, None) == -1          # first op out of range -> OU_ERR_INVALID
+    assert "out of range" in lib.last_error()
+    assert L.ou_plan_run(plan, byref(args), 2, -1, None) == 0           # empty range: nothing launched
+    assert L.ou_plan_destroy(plan) == 0
