@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define OU_ABI_VERSION 2
+#define OU_ABI_VERSION 3
 
 enum {
   OU_OK = 0,
@@ -134,6 +134,18 @@ typedef struct ou_trunk_params {
   float prelu_in, prelu_mid1, prelu_mid2, prelu_out, prelu_out2;
   float scale1, scale3;
   int32_t max_ctas;         /* cap on the persistent grid (0 = one CTA per SM), as in ou_conv_params */
+  /* Optional tail (ABI v3, channels = 64 only): the NEXT decoder block's transposed rate-change conv
+   * (blocks.py:360-376: PReLU -> ConvTranspose1d(C -> C/2, k = stride = 2) -> low-pass -> bias -> pad to
+   * length -> (h + res)/sqrt2, folded to 3 taps at the low rate) runs on the block output while it is
+   * still in shared memory; `out` is then not written (may be NULL):
+   *   up_out[b][co][2 j + ph] = (sum_q W_up[ph*C/2 + co][q][:] . PReLU(v, up_prelu_in)[:, j + q - 1]
+   *                              + up_bias[ph*C/2 + co] + up_skip[b][co][2 j + ph]) * up_scale          */
+  const void* up_w;         /* ou_conv_params.w_tc packing [3][1][C][C] of the folded up conv, or NULL   */
+  const float* up_bias;     /* fp32 [C] or NULL                                                         */
+  const void* up_skip;      /* blocked act (B, C/2, up_t_out) or NULL                                   */
+  void* up_out;             /* blocked act (B, C/2, up_t_out)                                           */
+  int32_t up_t_out;         /* <= 2 t                                                                   */
+  float up_scale, up_prelu_in;
 } ou_trunk_params;
 
 int ou_conv_trunk(const ou_trunk_params* p, void* stream);

@@ -72,7 +72,7 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
   return ok != 0;
 }
 
-template <int C, int S = 3>
+template <int C, int S = 3, bool UP = false>
 struct Geo {
   static constexpr int W = 64 / C;                     // 128-row sub-tiles per item
   static constexpr int ROWB = C * 2;                   // bytes per activation row
@@ -83,8 +83,10 @@ struct Geo {
   static constexpr uint32_t BUF_BYTES = ((uint32_t)(XPAD * ROWB) + 1023u) & ~1023u;
   static constexpr uint32_t W_TAP_BYTES = (uint32_t)(C * ROWB);
   static constexpr uint32_t SWZ_MASK = ROWB == 128 ? 7u : 3u;
-  static constexpr uint32_t W_BYTES = NTAPS * W_TAP_BYTES;
-  static constexpr uint32_t TAIL_BYTES = 8u * (1 + 5 * S) + 32u + 4u * (S * 2 * C + 2 * C);   // barriers, TMEM slot, coefficients
+  static constexpr int TAPS_UP = UP ? 3 : 0;                   // the fused up conv of the next block (tail)
+  static constexpr int ITEM_VALID = UP ? VALID - 2 : VALID;    // rows an item contributes to the final output
+  static constexpr uint32_t W_BYTES = (NTAPS + TAPS_UP) * W_TAP_BYTES;
+  static constexpr uint32_t TAIL_BYTES = 8u * (1 + 5 * S) + 32u + 4u * (S * 2 * C + 3 * C);   // barriers, TMEM slot, coefficients
   // no alignment slack: the dynamic shared window of a kernel without static shared memory starts 1024-byte
   // aligned (checked at run time) -- with it, 4 slots do not fit next to the 90 KB of weights at C = 64
   static constexpr size_t SMEM = W_BYTES + (size_t)S * 2 * BUF_BYTES + TAIL_BYTES;
@@ -105,6 +107,7 @@ struct Smem {
   uint32_t tmem_slot;
   uint32_t coef1[MAXS];           // fp32 [c0 | c1][C] of the slot's current clip (conv1 epilogue)
   uint32_t bias2, coef3;         // fp32 [C]: conv2 bias; s3 * conv3 bias
+  uint32_t coef_up;              // fp32 [C]: up_scale * up conv bias (tail)
 };
 
 // ---------------------------------------------------------------------------------- MMA issue
@@ -131,11 +134,11 @@ __device__ __forceinline__ void issue_stage(uint32_t a_buf, uint32_t w_buf, uint
 }
 
 // ---------------------------------------------------------------------------------- slot warpgroup
-template <int C, int S, int WPS, bool HAS_SC, int NPRELU, bool FASTP>
+template <int C, int S, int WPS, bool HAS_SC, int NPRELU, bool FASTP, bool UP>
 __device__ __forceinline__ void slot_role(const TrunkArgs& a, const Smem& sm, uint32_t tmem_base, int slot,
                                           int n_items, const CUtensorMap* tm_x, const CUtensorMap* tm_sc,
                                           int warp, int lane) {
-  using G = Geo<C, S>;
+  using G = Geo<C, S, UP>;
   const ou_trunk_params& p = a.p;
   const int quarter = warp & 3;                 // TMEM lane quarter this warp may read
   const int wis = warp % WPS;                   // warp index inside the slot's warpgroup
@@ -173,7 +176,8 @@ __device__ __forceinline__ void slot_role(const TrunkArgs& a, const Smem& sm, ui
   auto item_pos = [&](int n, int& b, int& t0) {
     const int item = (int)blockIdx.x + (int)gridDim.x * n;
     b = item / a.items_per_clip;
-    t0 = (item - b * a.items_per_clip) * G::VALID;
+    // with the up tail, output row r of an item is low-rate index t0 + 1 + r (one row of halo on each side)
+    t0 = (item - b * a.items_per_clip) * G::ITEM_VALID - (UP ? 1 : 0);
   };
   auto load_x = [&](int n) {
     int b, t0;
@@ -240,26 +244,25 @@ __device__ __forceinline__ void slot_role(const TrunkArgs& a, const Smem& sm, ui
     ph_x ^= 1;
     TRUNK_STAMP(1)
     {
-      uint4 halo[CHH];
 #pragma unroll
       for (int sub = 0; sub < G::W; sub++)
 #pragma unroll
         for (int c = 0; c < CHH; c++)
           res[sub][c] = lds_u4(swz<C>(X, (uint32_t)((sub * 128 + row + 4) * G::ROWB + (ch0 + c) * 16)));
-      if (row < 4) {
-#pragma unroll
-        for (int c = 0; c < CHH; c++) halo[c] = lds_u4(swz<C>(X, (uint32_t)(row * G::ROWB + (ch0 + c) * 16)));
-      }
 #pragma unroll
       for (int sub = 0; sub < G::W; sub++)
 #pragma unroll
         for (int c = 0; c < CHH; c++)
           sts_u4(swz<C>(X, (uint32_t)((sub * 128 + row + 4) * G::ROWB + (ch0 + c) * 16)),
                  prelu_act8(res[sub][c], a_in_hi, a_in_lo));
+      // the 4 halo rows in front of the tile, by the first 4 threads, chunk by chunk (their registers are
+      // not worth keeping live next to the residual rows: that spilled in the variants with a tail)
       if (row < 4) {
 #pragma unroll
-        for (int c = 0; c < CHH; c++)
-          sts_u4(swz<C>(X, (uint32_t)(row * G::ROWB + (ch0 + c) * 16)), prelu_act8(halo[c], a_in_hi, a_in_lo));
+        for (int c = 0; c < CHH; c++) {
+          const uint32_t ha = swz<C>(X, (uint32_t)(row * G::ROWB + (ch0 + c) * 16));
+          sts_u4(ha, prelu_act8(lds_u4(ha), a_in_hi, a_in_lo));
+        }
       }
     }
     TRUNK_STAMP(2)
@@ -398,7 +401,7 @@ __device__ __forceinline__ void slot_role(const TrunkArgs& a, const Smem& sm, ui
     ph_acc ^= 1;
     tc_fence_after();
     TRUNK_STAMP(13)
-    if (HAS_SC && leader && has_next) load_sc(n + S);   // conv3's MMAs are done with Cb
+    if (!UP && HAS_SC && leader && has_next) load_sc(n + S);   // conv3's MMAs are done with Cb
     tmem_ld16(q_taddr(0), rbuf[0]);
     const float2 s3v = make_float2(s3, s3);
 #pragma unroll
@@ -406,7 +409,7 @@ __device__ __forceinline__ void slot_role(const TrunkArgs& a, const Smem& sm, ui
       const int sub = q / QS, cc = q % QS;
       const int i = sub * 128 + row;
       const int t = t0 + i;
-      const bool valid = i < G::VALID && t < T;
+      const bool valid = i < G::VALID && t < T && t >= 0;
       act_t* dst = outp + ((size_t)b * T + t) * C;
       float4 kk[4];
 #pragma unroll
@@ -428,11 +431,82 @@ __device__ __forceinline__ void slot_role(const TrunkArgs& a, const Smem& sm, ui
                              make_float2(c1.z, c1.w));
           if (NPRELU > 0) v01 = prelu2<FASTP>(v01, p.prelu_out), v23 = prelu2<FASTP>(v23, p.prelu_out);
           if (NPRELU > 1) v01 = prelu2<FASTP>(v01, p.prelu_out2), v23 = prelu2<FASTP>(v23, p.prelu_out2);
+          if (UP) {
+            // the block output is rounded to the storage type exactly as if it went through HBM, then the
+            // up conv's input PReLU is applied (same rounding points as the separate launches)
+            const float2 r01 = act2_to_f2(f2_to_act2(v01.x, v01.y)), r23 = act2_to_f2(f2_to_act2(v23.x, v23.y));
+            v01 = prelu2<false>(r01, p.up_prelu_in), v23 = prelu2<false>(r23, p.up_prelu_in);
+          }
           o.w[h * 4 + 2 * k] = f2_to_act2(v01.x, v01.y);
           o.w[h * 4 + 2 * k + 1] = f2_to_act2(v23.x, v23.y);
         }
       }
-      if (valid) stg_v8(dst + col0 + cc * 16, o);
+      if (UP) {
+        // operand rows of the up conv (zero outside the clip: its "same" padding)
+        const uint32_t d0 = swz<C>(Cb, (uint32_t)(i * G::ROWB + (ch0 + 2 * cc) * 16));
+        const uint32_t d1 = swz<C>(Cb, (uint32_t)(i * G::ROWB + (ch0 + 2 * cc + 1) * 16));
+        sts_u4(d0, valid ? make_uint4(o.w[0], o.w[1], o.w[2], o.w[3]) : zero4);
+        sts_u4(d1, valid ? make_uint4(o.w[4], o.w[5], o.w[6], o.w[7]) : zero4);
+      } else if (valid) {
+        stg_v8(dst + col0 + cc * 16, o);
+      }
+    }
+    if (UP) {
+      // ---- stage 4 (tail): the next block's transposed up conv + skip add on the tile just computed:
+      // out[2 (t0 + 1 + r) + ph][co] = ((sum_q W_q[(ph, co)] . v[t0 + r + q]) + b_up + skip) * up_scale
+      wg_handover();
+      if (issuer_warp) {
+        tc_fence_after();
+        issue_stage<C, 3>(Cb, sm.w + (TAPS1 + TAPS2 + TAPS3) * G::W_TAP_BYTES, d_tmem, bar_acc, idesc, hi64);
+      }
+      static_assert(!UP || (G::W == 1 && WPS == 4), "the up tail is built for C = 64 (one sub-tile, thread = row)");
+      const int low = t0 + 1 + row;                    // low-rate index of this thread's output row
+      const bool row_ok = row < G::ITEM_VALID && low >= 0 && low < T;
+      // the thread's 64 output values are 2 consecutive time steps x 32 channels = 128 contiguous bytes of
+      // the [t][C/2] output (and skip) layout: chunk q = elements [16 q, 16 q + 16), phase q / 2
+      const size_t ubase = ((size_t)b * p.up_t_out + 2 * low) * (C / 2);
+      const bool ok0 = row_ok && 2 * low < p.up_t_out, ok1 = row_ok && 2 * low + 1 < p.up_t_out;
+      act_t* up_out = (act_t*)p.up_out + ubase;
+      const act_t* up_skip = p.up_skip ? (const act_t*)p.up_skip + ubase : nullptr;
+      U8 sk[4];
+      if (up_skip != nullptr) {
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+          if (q < 2 ? ok0 : ok1) sk[q] = ldg_nc_v8(up_skip + 16 * q);
+      }
+      mbar_wait(bar_acc, ph_acc);
+      ph_acc ^= 1;
+      tc_fence_after();
+      if (HAS_SC && leader && has_next) load_sc(n + S);   // the tail's MMAs are done with Cb
+      tmem_ld16(q_taddr(0), rbuf[0]);
+      const float2 usv = make_float2(p.up_scale, p.up_scale);
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const bool ok = q < 2 ? ok0 : ok1;
+        float4 kk[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) kk[j] = lds_f4(sm.coef_up + 4u * (q * 16 + j * 4));
+        tmem_ld_wait();
+        if (q + 1 < 4) tmem_ld16(q_taddr(q + 1), rbuf[(q + 1) & 1]);
+        const uint32_t(&r)[16] = rbuf[q & 1];
+        if (ok) {
+          U8 o;
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            float2 a01 = u2_as_f2(r[4 * k], r[4 * k + 1]), a23 = u2_as_f2(r[4 * k + 2], r[4 * k + 3]);
+            if (up_skip != nullptr) {
+              a01 = fadd2(a01, act2_to_f2(sk[q].w[2 * k]));
+              a23 = fadd2(a23, act2_to_f2(sk[q].w[2 * k + 1]));
+            }
+            a01 = ffma2(a01, usv, make_float2(kk[k].x, kk[k].y));
+            a23 = ffma2(a23, usv, make_float2(kk[k].z, kk[k].w));
+            o.w[2 * k] = f2_to_act2(a01.x, a01.y);
+            o.w[2 * k + 1] = f2_to_act2(a23.x, a23.y);
+          }
+          stg_v8(up_out + 16 * q, o);
+        }
+      }
+      TRUNK_STAMP(15)
     }
     // (the TMEM reads above are ordered before the next item's MMAs by wg_handover() after its T0)
     TRUNK_STAMP(14)
@@ -440,12 +514,13 @@ __device__ __forceinline__ void slot_role(const TrunkArgs& a, const Smem& sm, ui
 }
 
 // ---------------------------------------------------------------------------------- kernel
-template <int C, bool HAS_SC, int S, int WPS, bool FASTP>
+template <int C, bool HAS_SC, int S, int WPS, bool FASTP, bool UP>
 __global__ void __launch_bounds__(WPS * S * 32, 1)
 trunk_kernel(const TrunkArgs a, const __grid_constant__ CUtensorMap tm_x,
              const __grid_constant__ CUtensorMap tm_sc, const __grid_constant__ CUtensorMap tm_w1,
-             const __grid_constant__ CUtensorMap tm_w2, const __grid_constant__ CUtensorMap tm_w3) {
-  using G = Geo<C, S>;
+             const __grid_constant__ CUtensorMap tm_w2, const __grid_constant__ CUtensorMap tm_w3,
+             const __grid_constant__ CUtensorMap tm_wup) {
+  using G = Geo<C, S, UP>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const ou_trunk_params& p = a.p;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -471,7 +546,8 @@ trunk_kernel(const TrunkArgs a, const __grid_constant__ CUtensorMap tm_x,
 #pragma unroll
   for (int s = 0; s < S; s++) sm.coef1[s] = at, at += 8u * C;
   sm.bias2 = at, at += 4u * C;
-  sm.coef3 = at;
+  sm.coef3 = at, at += 4u * C;
+  sm.coef_up = at;
 
   if (threadIdx.x == 0) {
     mbar_init(sm.w_full, 1);
@@ -485,6 +561,7 @@ trunk_kernel(const TrunkArgs a, const __grid_constant__ CUtensorMap tm_x,
   if (threadIdx.x < C) {
     sts_f1(sm.bias2 + 4u * threadIdx.x, p.b2[threadIdx.x]);
     sts_f1(sm.coef3 + 4u * threadIdx.x, p.scale3 * p.b3[threadIdx.x]);
+    if (UP) sts_f1(sm.coef_up + 4u * threadIdx.x, p.up_scale * (p.up_bias ? p.up_bias[threadIdx.x] : 0.f));
   }
   constexpr uint32_t TMEM_COLS = S * SLOT_COLS <= 256 ? 256u : 512u;
   if (warp == 0) tmem_alloc(sm.tmem_slot, TMEM_COLS);
@@ -504,17 +581,19 @@ trunk_kernel(const TrunkArgs a, const __grid_constant__ CUtensorMap tm_x,
       tma_load_3d(sm.w + (TAPS1 + q) * G::W_TAP_BYTES, &tm_w2, 0, 0, q, sm.w_full);
     for (int q = 0; q < TAPS3; q++)
       tma_load_3d(sm.w + (TAPS1 + TAPS2 + q) * G::W_TAP_BYTES, &tm_w3, 0, 0, q, sm.w_full);
+    for (int q = 0; q < G::TAPS_UP; q++)
+      tma_load_3d(sm.w + (NTAPS + q) * G::W_TAP_BYTES, &tm_wup, 0, 0, q, sm.w_full);
   }
   __syncwarp();
   {
     const int slot = warp / WPS;
     const int nprelu = p.has_prelu_out2 ? 2 : (p.has_prelu_out ? 1 : 0);
     if (nprelu == 0)
-      slot_role<C, S, WPS, HAS_SC, 0, FASTP>(a, sm, tmem_base, slot, n_items, &tm_x, &tm_sc, warp, lane);
+      slot_role<C, S, WPS, HAS_SC, 0, FASTP, UP>(a, sm, tmem_base, slot, n_items, &tm_x, &tm_sc, warp, lane);
     else if (nprelu == 1)
-      slot_role<C, S, WPS, HAS_SC, 1, FASTP>(a, sm, tmem_base, slot, n_items, &tm_x, &tm_sc, warp, lane);
+      slot_role<C, S, WPS, HAS_SC, 1, FASTP, UP>(a, sm, tmem_base, slot, n_items, &tm_x, &tm_sc, warp, lane);
     else
-      slot_role<C, S, WPS, HAS_SC, 2, FASTP>(a, sm, tmem_base, slot, n_items, &tm_x, &tm_sc, warp, lane);
+      slot_role<C, S, WPS, HAS_SC, 2, FASTP, UP>(a, sm, tmem_base, slot, n_items, &tm_x, &tm_sc, warp, lane);
   }
 
   tc_fence_before();
@@ -561,13 +640,13 @@ static int encode3(CUtensorMap* tm, const void* base, int c, uint64_t d1, uint64
   return OU_OK;
 }
 
-template <int C, int S, int WPS>
+template <int C, int S, int WPS, bool UP = false>
 static int launch_cfg(const ou_trunk_params* p, cudaStream_t st) {
-  using G = Geo<C, S>;
+  using G = Geo<C, S, UP>;
   TrunkArgs a;
   a.trace = ou::tc::g_trace;
   a.p = *p;
-  a.items_per_clip = ceil_div(p->t, G::VALID);
+  a.items_per_clip = ceil_div(p->t, G::ITEM_VALID);
   a.total_items = a.items_per_clip * p->batch;
   // X rows per item: 128W + 8, fetched as equal boxes of <= 256 rows whose byte size keeps every
   // box start on a swizzle-pattern boundary (multiple of 8 rows)
@@ -579,7 +658,7 @@ static int launch_cfg(const ou_trunk_params* p, cudaStream_t st) {
   const uint32_t layout = G::ROWB == 128 ? 2u : 4u;
   a.desc_hi = ((sbo >> 4) & 0x3FFFu) | (1u << (46 - 32)) | (layout << (61 - 32));
 
-  CUtensorMap tm_x, tm_sc, tm_w1, tm_w2, tm_w3;
+  CUtensorMap tm_x, tm_sc, tm_w1, tm_w2, tm_w3, tm_wup;
   int rc;
   if ((rc = encode3(&tm_x, p->x, C, (uint64_t)p->t, (uint64_t)p->batch, (uint32_t)a.x_box_rows,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, "x")))
@@ -590,18 +669,20 @@ static int launch_cfg(const ou_trunk_params* p, cudaStream_t st) {
   if ((rc = encode3(&tm_w1, p->w1, C, (uint64_t)C, TAPS1, C, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, "w1"))) return rc;
   if ((rc = encode3(&tm_w2, p->w2, C, (uint64_t)C, TAPS2, C, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, "w2"))) return rc;
   if ((rc = encode3(&tm_w3, p->w3, C, (uint64_t)C, TAPS3, C, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, "w3"))) return rc;
+  if ((rc = encode3(&tm_wup, UP ? p->up_w : p->w3, C, (uint64_t)C, 3, C, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, "w_up")))
+    return rc;
 
   // FASTP: every epilogue PReLU slope in [0, 1] -> PReLU(x) = max(x, a x)
   auto in01 = [](float a) { return a >= 0.f && a <= 1.f; };
   const bool fastp = in01(p->prelu_mid1) && in01(p->prelu_mid2) && (!p->has_prelu_out || in01(p->prelu_out)) &&
                      (!p->has_prelu_out2 || in01(p->prelu_out2));
-  auto kern = p->sc ? (fastp ? trunk_kernel<C, true, S, WPS, true> : trunk_kernel<C, true, S, WPS, false>)
-                    : (fastp ? trunk_kernel<C, false, S, WPS, true> : trunk_kernel<C, false, S, WPS, false>);
+  auto kern = p->sc ? (fastp ? trunk_kernel<C, true, S, WPS, true, UP> : trunk_kernel<C, true, S, WPS, false, UP>)
+                    : (fastp ? trunk_kernel<C, false, S, WPS, true, UP> : trunk_kernel<C, false, S, WPS, false, UP>);
   static SmemConfig cfg[4];
   if ((rc = ensure_smem(kern, (size_t)G::SMEM, cfg[(p->sc ? 1 : 0) + (fastp ? 2 : 0)], "ou_conv_trunk"))) return rc;
   const int n_sms = p->max_ctas > 0 && p->max_ctas < num_sms() ? p->max_ctas : num_sms();
   int grid = n_sms < a.total_items ? n_sms : a.total_items;
-  kern<<<grid, WPS * S * 32, G::SMEM, st>>>(a, tm_x, tm_sc, tm_w1, tm_w2, tm_w3);
+  kern<<<grid, WPS * S * 32, G::SMEM, st>>>(a, tm_x, tm_sc, tm_w1, tm_w2, tm_w3, tm_wup);
   return check_launch("ou_conv_trunk");
 }
 
@@ -611,7 +692,11 @@ static int launch_cfg(const ou_trunk_params* p, cudaStream_t st) {
 template <int C>
 static int launch_c(const ou_trunk_params* p, cudaStream_t st) {
   if constexpr (C == 64) {
-    static const int s64 = [] { const char* e = getenv("OU_TRUNK_S64"); return e ? atoi(e) : 3; }();
+    if (p->up_w != nullptr) return launch_cfg<C, 3, 4, true>(p, st);   // fused up-conv tail
+    // 4 slots fit exactly (no alignment slack) next to the 90 KB of weights; since the halo rows are
+    // transformed chunk by chunk the kernel does not spill at 128 registers: 234 / 262 us against 250 / 265 us
+    // with 3 slots (enc / dec, cfg-2 sizes); OU_TRUNK_S64=3 for A/B runs
+    static const int s64 = [] { const char* e = getenv("OU_TRUNK_S64"); return e ? atoi(e) : 4; }();
     if (s64 == 4) return launch_cfg<C, 4, 4>(p, st);
   }
   if constexpr (C == 32) {
@@ -628,8 +713,12 @@ static int launch_c(const ou_trunk_params* p, cudaStream_t st) {
 
 extern "C" int ou_conv_trunk(const ou_trunk_params* p, void* stream) {
   OU_REQUIRE(p != nullptr, "ou_conv_trunk: null params");
-  OU_REQUIRE(p->x && p->w1 && p->w2 && p->w3 && p->b1 && p->b2 && p->b3 && p->out,
+  OU_REQUIRE(p->x && p->w1 && p->w2 && p->w3 && p->b1 && p->b2 && p->b3 && (p->out || p->up_w),
              "ou_conv_trunk: null pointer");
+  OU_REQUIRE(p->up_w == nullptr || (p->channels == 64 && p->up_out != nullptr && p->up_t_out > 0 &&
+                                    p->up_t_out <= 2 * p->t && !p->has_prelu_out && !p->has_prelu_out2),
+             "ou_conv_trunk: the fused up-conv tail needs C = 64, an output buffer of at most 2 t samples and no "
+             "output PReLU on the block");
   OU_REQUIRE(p->batch > 0 && p->t > 0, "ou_conv_trunk: empty problem");
   OU_REQUIRE((p->gamma == nullptr) == (p->beta == nullptr), "ou_conv_trunk: gamma / beta must come together");
   if ((p->channels != 32 && p->channels != 64) || p->taps1 != ou::trunk::TAPS1 || p->taps2 != ou::trunk::TAPS2 ||

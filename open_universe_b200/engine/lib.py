@@ -11,7 +11,7 @@ from ctypes import (POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int
 from pathlib import Path
 
 from ..build import LIB as LIB_PATH
-OU_ABI_VERSION = 2
+OU_ABI_VERSION = 3
 
 
 class ConvParams(Structure):
@@ -45,6 +45,8 @@ class TrunkParams(Structure):
         ("prelu_out", c_float), ("prelu_out2", c_float),
         ("scale1", c_float), ("scale3", c_float),
         ("max_ctas", c_int32),
+        ("up_w", c_void_p), ("up_bias", c_void_p), ("up_skip", c_void_p), ("up_out", c_void_p),
+        ("up_t_out", c_int32), ("up_scale", c_float), ("up_prelu_in", c_float),
     ]
 
 

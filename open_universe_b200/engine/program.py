@@ -73,14 +73,20 @@ class TrunkOp:
     name: str
     parts: List[ConvOp]
     packed: Optional[dict] = None
+    # the next decoder block's transposed up conv (+ skip add) fused behind conv3 (C = 64 only): the block
+    # output stays in shared memory, ``parts[2].dst`` is not written by the fused launch
+    tail: Optional[ConvOp] = None
+
+    def all_parts(self):
+        return self.parts + ([self.tail] if self.tail is not None else [])
 
     @property
     def flops_exec(self):
-        return sum(p.flops_exec for p in self.parts)
+        return sum(p.flops_exec for p in self.all_parts())
 
     @property
     def flops_algo(self):
-        return sum(p.flops_algo for p in self.parts)
+        return sum(p.flops_algo for p in self.all_parts())
 
 
 TRUNK_CHANNELS = (32, 64)
@@ -106,6 +112,37 @@ def fuse_trunk(prog, name, n_parts=3):
         return False
     del prog.ops[-n_parts:]
     prog.ops.append(TrunkOp(name, [c1, c2, c3]))
+    return True
+
+
+# OU_TRUNK_TAIL=0 keeps the up convs as separate ou_conv1d launches (A/B runs)
+import os as _os
+TRUNK_TAIL = _os.environ.get("OU_TRUNK_TAIL", "1") != "0"
+
+
+def fuse_up_tail(prog):
+    """If the last op is a x2 transposed up conv reading the output of the 64-channel TrunkOp right before
+    it (decoder: dec.k.trunk -> dec.k+1.up), fold it into that trunk launch as its tail."""
+    if not TRUNK_TAIL or len(prog.ops) < 2:
+        return False
+    up, tr = prog.ops[-1], prog.ops[-2]
+    if not (isinstance(up, ConvOp) and isinstance(tr, TrunkOp) and tr.tail is None):
+        return False
+    c3 = tr.parts[2]
+    fc = up.fc
+    ok = (c3.fc.cin == 64 and up.src == c3.dst and c3.prelu_out is None and c3.prelu_out2 is None
+          and fc.cin == 64 and fc.n == 64 and fc.up == 2 and fc.s == 1 and fc.taps == 3 and fc.tap_off == -1
+          and fc.prelu_in is not None and up.add2 is None and up.film_off is None and up.prelu_out is None
+          and up.prelu_out2 is None and up.dst_kind == "blocked" and up.t_in == c3.t_out
+          and up.t_out <= 2 * up.t_in and up.rows <= up.t_in
+          # nothing else may read the block output
+          and not any(c3.dst in (getattr(o, "src", None), getattr(o, "add1", None), getattr(o, "add2", None),
+                                 getattr(o, "add", None))
+                      for o in flat_ops(prog.ops[:-2])))
+    if not ok:
+        return False
+    tr.tail = up
+    del prog.ops[-1]
     return True
 
 
@@ -204,7 +241,7 @@ def flat_ops(ops):
     """Op list with every TrunkOp expanded into its three ConvOps."""
     out = []
     for op in ops:
-        out.extend(op.parts if isinstance(op, TrunkOp) else [op])
+        out.extend(op.all_parts() if isinstance(op, TrunkOp) else [op])
     return out
 
 
@@ -245,6 +282,7 @@ def lower_conv_block(prog, blk, pfx, src, t_in, *, film_linear=None, input_cond=
             raise ValueError("target length is more than one frame longer than the upsampled input")
         h, t = add_conv(prog, pfx + ".up", src, pfx + ".h", fc, t_in, t_up,
                         add1=res, scale1=SQRT_HALF if res is not None else 1.0)
+        fuse_up_tail(prog)
     elif res is not None:
         raise RuntimeError("lowering expects the residual of a rate-preserving block to be "
                            "pre-added by the producer (GRU epilogue)")
@@ -483,7 +521,11 @@ def op_bytes(op, batch, elem=2):
     if isinstance(op, TrunkOp):
         c1 = op.parts[0]
         c, t = c1.fc.cin, c1.t_in
-        w = sum(p.fc.w.numel() for p in op.parts) * elem
+        w = sum(p.fc.w.numel() for p in op.all_parts()) * elem
+        if op.tail is not None:      # x (+ sc) in; the up conv's skip in and output out; the block output stays on chip
+            up = op.tail
+            return (elem * batch * c * t * (1 + (c1.add1 is not None))
+                    + elem * batch * up.fc.cout * up.t_out * (1 + (up.add1 is not None)) + w)
         return elem * batch * c * t * (2 + (c1.add1 is not None)) + w
     if isinstance(op, ConvOp):
         fc = op.fc

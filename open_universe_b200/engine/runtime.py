@@ -254,6 +254,12 @@ def trunk_params(op, bufs, batch, film=None, film_bstride=0, max_ctas=0):
     prm.has_prelu_out2 = c3.prelu_out2 is not None
     prm.prelu_out2 = c3.prelu_out2 or 0.0
     prm.scale1, prm.scale3 = c1.scale1, c3.scale1
+    if op.tail is not None:
+        up = op.tail
+        prm.up_w, prm.up_bias = up.packed["w_tc"].data_ptr(), up.packed["bias"].data_ptr()
+        prm.up_skip = bufs[up.add1].data_ptr() if up.add1 else None
+        prm.up_out = bufs[up.dst].data_ptr()
+        prm.up_t_out, prm.up_scale, prm.up_prelu_in = up.t_out, up.scale1, up.fc.prelu_in
     return prm
 
 

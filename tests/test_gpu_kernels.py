@@ -368,3 +368,67 @@ def test_conv_resident_weights_with_more_k_blocks_than_a_stages():
     exe.run()
     torch.cuda.synchronize()
     assert rel_rms(R.unpack_blocked(exe.bufs["out"]).cpu(), bufs["out"]) < 3e-3
+
+
+TAIL_CASES = [
+    dict(t=1000, B=2, sc=True, film=True, skip=True, t_up=2000),
+    dict(t=123, B=1, sc=False, film=False, skip=True, t_up=245),       # one partial item, odd target length
+    dict(t=122 * 3, B=2, sc=True, film=False, skip=False, t_up=122 * 6),  # exact multiple of the item, no skip
+    dict(t=122 * 2 + 1, B=1, sc=True, film=True, skip=True, t_up=2 * (122 * 2 + 1)),
+    dict(t=64080, B=3, sc=True, film=True, skip=True, t_up=128160),     # many items per CTA
+]
+
+
+@pytest.mark.parametrize("c", TAIL_CASES, ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items()))
+def test_conv_trunk_with_up_tail_vs_emulator(c):
+    """ou_conv_trunk with the next block's transposed up conv (+ skip add) fused behind conv3 (C = 64):
+    against the emulator and against the four separate launches."""
+    g = torch.Generator().manual_seed(987)
+    B, C, t, t_up = c["B"], 64, c["t"], c["t_up"]
+    prog = P.Program(B)
+    prog.buf("in", "blocked", C, t)
+    inputs = {"in": bf(torch.randn(B, C, t, generator=g))}
+    if c["sc"]:
+        prog.buf("sc", "blocked", C, t)
+        inputs["sc"] = bf(torch.randn(B, C, t, generator=g))
+    if c["skip"]:
+        prog.buf("skip", "blocked", C // 2, t_up)
+        inputs["skip"] = bf(torch.randn(B, C // 2, t_up, generator=g))
+    P.add_conv(prog, "conv1", "in", "c1", rand_fc(g, C, C, taps=5, tap_off=-2, prelu_in=0.2), t,
+               add1="sc" if c["sc"] else None, scale1=0.7071 if c["sc"] else 1.0,
+               film_off=0 if c["film"] else None, prelu_out=0.15)
+    P.add_conv(prog, "conv2", "c1", "c2", rand_fc(g, C, C, taps=3, tap_off=-1), t, prelu_out=0.3)
+    P.add_conv(prog, "conv3", "c2", "v", rand_fc(g, C, C, taps=3, tap_off=-1), t, add1="in", scale1=0.7071)
+    assert P.fuse_trunk(prog, "trunk")
+    P.add_conv(prog, "up", "v", "h", rand_fc(g, C, C // 2, up=2, taps=3, tap_off=-1, prelu_in=0.25), t, t_up,
+               add1="skip" if c["skip"] else None, scale1=0.7071 if c["skip"] else 1.0)
+    assert P.fuse_up_tail(prog) and len(prog.ops) == 1 and prog.ops[0].tail is not None
+    film = torch.randn(B, 2 * C, generator=g) if c["film"] else None
+    bufs, _, _ = E.run_program(prog, inputs, film=film, quant=True)
+    want = bufs["h"]
+
+    exe = R.Executor(prog, DEV, external=list(inputs))
+    for k, v in inputs.items():
+        exe.bufs[k] = R.pack_blocked(v.to(DEV))
+    film_d = film.to(DEV).contiguous() if film is not None else None
+    exe.bufs["h"].fill_(7.0)
+    n0 = lib.launch_count()
+    exe.run(film=film_d, film_bstride=2 * C)
+    assert lib.launch_count() - n0 == 1
+    got = R.unpack_blocked(exe.bufs["h"]).cpu()
+    R.USE_TRUNK = False
+    try:
+        exe.bufs["h"].zero_()
+        n0 = lib.launch_count()
+        exe.run(film=film_d, film_bstride=2 * C)
+        assert lib.launch_count() - n0 == 4
+        split = R.unpack_blocked(exe.bufs["h"]).cpu()
+    finally:
+        R.USE_TRUNK = True
+    assert got.shape == want.shape and torch.isfinite(got).all()
+    err, err_split = rel_rms(got, want), rel_rms(got, split)
+    if err >= 3e-3 or err_split >= 3e-3:
+        d = (got - want).abs()
+        bad = (d > 0.05 * want.abs().max()).float()
+        raise AssertionError(f"rel_rms={err:.4f} vs split {err_split:.4f} bad_fraction={bad.mean():.5f} "
+                             f"bad rows (time) {bad.amax(dim=(0, 1)).nonzero().flatten()[:24].tolist()}")
