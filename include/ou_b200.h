@@ -146,6 +146,18 @@ typedef struct ou_trunk_params {
   void* up_out;             /* blocked act (B, C/2, up_t_out)                                           */
   int32_t up_t_out;         /* <= 2 t                                                                   */
   float up_scale, up_prelu_in;
+  /* Optional output tail (ABI v3, channels = 32 only): the network's output conv (score.py:288,294: C -> 1,
+   * k = 3, 'same') on the block output + EDM mix + reverse-SDE update, exactly ou_output_sde:
+   *   net[t] = out_bias + sum_{k<3} sum_c out_w[k][c] * v[c][t + k - 1];  out_net[b][t] = net (if not NULL)
+   *   out_xout[b][t] = ca*out_x[b][t] + cb*net + cc*out_noise[b][t], (ca, cb, cc) = out_coef[b] (if not NULL)
+   * `out` is then not written (may be NULL).                                                            */
+  const float* out_w;       /* fp32 [3][C] tap-major, or NULL                                           */
+  float out_bias;
+  const float* out_coef;    /* fp32 (B, 3) or NULL                                                      */
+  const float* out_x;       /* fp32 (B, t)                                                              */
+  const float* out_noise;   /* fp32 (B, t) or NULL                                                      */
+  float* out_xout;          /* fp32 (B, t)                                                              */
+  float* out_net;           /* fp32 (B, t) or NULL                                                      */
 } ou_trunk_params;
 
 int ou_conv_trunk(const ou_trunk_params* p, void* stream);

@@ -72,8 +72,10 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
   return ok != 0;
 }
 
-template <int C, int S = 3, bool UP = false>
+// TAIL: 0 none; 1 the next block's x2 up conv (C = 64); 2 the network's output conv + EDM / SDE update (C = 32)
+template <int C, int S = 3, int TAIL = 0>
 struct Geo {
+  static constexpr bool UP = TAIL == 1, OUTC = TAIL == 2;
   static constexpr int W = 64 / C;                     // 128-row sub-tiles per item
   static constexpr int ROWB = C * 2;                   // bytes per activation row
   static constexpr int CH = C / 8;                     // 16-byte chunks per row
@@ -84,9 +86,9 @@ struct Geo {
   static constexpr uint32_t W_TAP_BYTES = (uint32_t)(C * ROWB);
   static constexpr uint32_t SWZ_MASK = ROWB == 128 ? 7u : 3u;
   static constexpr int TAPS_UP = UP ? 3 : 0;                   // the fused up conv of the next block (tail)
-  static constexpr int ITEM_VALID = UP ? VALID - 2 : VALID;    // rows an item contributes to the final output
+  static constexpr int ITEM_VALID = TAIL ? VALID - 2 : VALID;  // rows an item contributes to the final output
   static constexpr uint32_t W_BYTES = (NTAPS + TAPS_UP) * W_TAP_BYTES;
-  static constexpr uint32_t TAIL_BYTES = 8u * (1 + 5 * S) + 32u + 4u * (S * 2 * C + 3 * C);   // barriers, TMEM slot, coefficients
+  static constexpr uint32_t TAIL_BYTES = 8u * (1 + 5 * S) + 32u + 4u * (S * 2 * C + (OUTC ? 5 : 3) * C);   // barriers, TMEM slot, coefficients
   // no alignment slack: the dynamic shared window of a kernel without static shared memory starts 1024-byte
   // aligned (checked at run time) -- with it, 4 slots do not fit next to the 90 KB of weights at C = 64
   static constexpr size_t SMEM = W_BYTES + (size_t)S * 2 * BUF_BYTES + TAIL_BYTES;
@@ -134,11 +136,12 @@ __device__ __forceinline__ void issue_stage(uint32_t a_buf, uint32_t w_buf, uint
 }
 
 // ---------------------------------------------------------------------------------- slot warpgroup
-template <int C, int S, int WPS, bool HAS_SC, int NPRELU, bool FASTP, bool UP>
+template <int C, int S, int WPS, bool HAS_SC, int NPRELU, bool FASTP, int TAIL>
 __device__ __forceinline__ void slot_role(const TrunkArgs& a, const Smem& sm, uint32_t tmem_base, int slot,
                                           int n_items, const CUtensorMap* tm_x, const CUtensorMap* tm_sc,
                                           int warp, int lane) {
-  using G = Geo<C, S, UP>;
+  using G = Geo<C, S, TAIL>;
+  constexpr bool UP = TAIL == 1, OUTC = TAIL == 2;
   const ou_trunk_params& p = a.p;
   const int quarter = warp & 3;                 // TMEM lane quarter this warp may read
   const int wis = warp % WPS;                   // warp index inside the slot's warpgroup
@@ -177,7 +180,7 @@ __device__ __forceinline__ void slot_role(const TrunkArgs& a, const Smem& sm, ui
     const int item = (int)blockIdx.x + (int)gridDim.x * n;
     b = item / a.items_per_clip;
     // with the up tail, output row r of an item is low-rate index t0 + 1 + r (one row of halo on each side)
-    t0 = (item - b * a.items_per_clip) * G::ITEM_VALID - (UP ? 1 : 0);
+    t0 = (item - b * a.items_per_clip) * G::ITEM_VALID - (TAIL ? 1 : 0);
   };
   auto load_x = [&](int n) {
     int b, t0;
@@ -401,7 +404,7 @@ __device__ __forceinline__ void slot_role(const TrunkArgs& a, const Smem& sm, ui
     ph_acc ^= 1;
     tc_fence_after();
     TRUNK_STAMP(13)
-    if (!UP && HAS_SC && leader && has_next) load_sc(n + S);   // conv3's MMAs are done with Cb
+    if (!TAIL && HAS_SC && leader && has_next) load_sc(n + S);   // conv3's MMAs are done with Cb
     tmem_ld16(q_taddr(0), rbuf[0]);
     const float2 s3v = make_float2(s3, s3);
 #pragma unroll
@@ -441,8 +444,8 @@ __device__ __forceinline__ void slot_role(const TrunkArgs& a, const Smem& sm, ui
           o.w[h * 4 + 2 * k + 1] = f2_to_act2(v23.x, v23.y);
         }
       }
-      if (UP) {
-        // operand rows of the up conv (zero outside the clip: its "same" padding)
+      if (TAIL) {
+        // operand rows of the tail conv (zero outside the clip: its "same" padding)
         const uint32_t d0 = swz<C>(Cb, (uint32_t)(i * G::ROWB + (ch0 + 2 * cc) * 16));
         const uint32_t d1 = swz<C>(Cb, (uint32_t)(i * G::ROWB + (ch0 + 2 * cc + 1) * 16));
         sts_u4(d0, valid ? make_uint4(o.w[0], o.w[1], o.w[2], o.w[3]) : zero4);
@@ -508,19 +511,68 @@ __device__ __forceinline__ void slot_role(const TrunkArgs& a, const Smem& sm, ui
       }
       TRUNK_STAMP(15)
     }
+    if (OUTC) {
+      // ---- tail: the network's output conv (C -> 1, k = 3) on the block output just written to Cb, fused with
+      // the EDM mix and the reverse-SDE update (ou_output_sde): thread = output time step t0 + 1 + r
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + slot), "n"(WPS * 32) : "memory");
+      static_assert(!OUTC || (C == 32 && WPS == 4), "the output tail is built for C = 32");
+      const float ca = p.out_coef ? p.out_coef[b * 3] : 0.f, cbv = p.out_coef ? p.out_coef[b * 3 + 1] : 0.f;
+      const float ccv = p.out_coef ? p.out_coef[b * 3 + 2] : 0.f;
+      // a thread owns rows `row` and `row + 128` of the item: each weight vector is fetched once for both
+      float2 acc[G::W];
+      float xv[G::W], zv[G::W];
+#pragma unroll
+      for (int sub = 0; sub < G::W; sub++) {
+        const int r = sub * 128 + row, tt = t0 + 1 + r;
+        acc[sub] = make_float2(0.f, 0.f), xv[sub] = zv[sub] = 0.f;
+        if (r < G::ITEM_VALID && tt >= 0 && tt < T && p.out_coef) {
+          xv[sub] = __ldg(p.out_x + (size_t)b * T + tt);
+          if (p.out_noise) zv[sub] = __ldg(p.out_noise + (size_t)b * T + tt);
+        }
+      }
+#pragma unroll 1
+      for (int k = 0; k < 3; k++) {
+#pragma unroll
+        for (int c = 0; c < G::CH; c++) {
+          const float4 w0 = lds_f4(sm.coef_up + 4u * (k * C + c * 8)), w1 = lds_f4(sm.coef_up + 4u * (k * C + c * 8 + 4));
+#pragma unroll
+          for (int sub = 0; sub < G::W; sub++) {
+            const uint4 v = lds_u4(swz<C>(Cb, (uint32_t)((sub * 128 + row + k) * G::ROWB + c * 16)));
+            acc[sub] = ffma2(make_float2(w0.x, w0.y), act2_to_f2(v.x), acc[sub]);
+            acc[sub] = ffma2(make_float2(w0.z, w0.w), act2_to_f2(v.y), acc[sub]);
+            acc[sub] = ffma2(make_float2(w1.x, w1.y), act2_to_f2(v.z), acc[sub]);
+            acc[sub] = ffma2(make_float2(w1.z, w1.w), act2_to_f2(v.w), acc[sub]);
+          }
+        }
+      }
+#pragma unroll
+      for (int sub = 0; sub < G::W; sub++) {
+        const int r = sub * 128 + row, tt = t0 + 1 + r;
+        const float net = p.out_bias + (acc[sub].x + acc[sub].y);
+        if (r < G::ITEM_VALID && tt >= 0 && tt < T) {
+          const size_t o = (size_t)b * T + tt;
+          if (p.out_net) p.out_net[o] = net;
+          if (p.out_coef) p.out_xout[o] = fmaf(ccv, zv[sub], fmaf(cbv, net, ca * xv[sub]));
+        }
+      }
+      // every thread is done reading Cb: the next item's conditioning rows may land
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + slot), "n"(WPS * 32) : "memory");
+      if (HAS_SC && leader && has_next) load_sc(n + S);
+    }
     // (the TMEM reads above are ordered before the next item's MMAs by wg_handover() after its T0)
     TRUNK_STAMP(14)
   }
 }
 
 // ---------------------------------------------------------------------------------- kernel
-template <int C, bool HAS_SC, int S, int WPS, bool FASTP, bool UP>
+template <int C, bool HAS_SC, int S, int WPS, bool FASTP, int TAIL>
 __global__ void __launch_bounds__(WPS * S * 32, 1)
 trunk_kernel(const TrunkArgs a, const __grid_constant__ CUtensorMap tm_x,
              const __grid_constant__ CUtensorMap tm_sc, const __grid_constant__ CUtensorMap tm_w1,
              const __grid_constant__ CUtensorMap tm_w2, const __grid_constant__ CUtensorMap tm_w3,
              const __grid_constant__ CUtensorMap tm_wup) {
-  using G = Geo<C, S, UP>;
+  using G = Geo<C, S, TAIL>;
+  constexpr bool UP = TAIL == 1, OUTC = TAIL == 2;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const ou_trunk_params& p = a.p;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -563,6 +615,8 @@ trunk_kernel(const TrunkArgs a, const __grid_constant__ CUtensorMap tm_x,
     sts_f1(sm.coef3 + 4u * threadIdx.x, p.scale3 * p.b3[threadIdx.x]);
     if (UP) sts_f1(sm.coef_up + 4u * threadIdx.x, p.up_scale * (p.up_bias ? p.up_bias[threadIdx.x] : 0.f));
   }
+  // output tail: the C x 3 fp32 weights of the output conv, tap-major [k][C]
+  if (OUTC && threadIdx.x < 3 * C) sts_f1(sm.coef_up + 4u * threadIdx.x, p.out_w[threadIdx.x]);
   constexpr uint32_t TMEM_COLS = S * SLOT_COLS <= 256 ? 256u : 512u;
   if (warp == 0) tmem_alloc(sm.tmem_slot, TMEM_COLS);
   tc_fence_before();
@@ -589,11 +643,11 @@ trunk_kernel(const TrunkArgs a, const __grid_constant__ CUtensorMap tm_x,
     const int slot = warp / WPS;
     const int nprelu = p.has_prelu_out2 ? 2 : (p.has_prelu_out ? 1 : 0);
     if (nprelu == 0)
-      slot_role<C, S, WPS, HAS_SC, 0, FASTP, UP>(a, sm, tmem_base, slot, n_items, &tm_x, &tm_sc, warp, lane);
+      slot_role<C, S, WPS, HAS_SC, 0, FASTP, TAIL>(a, sm, tmem_base, slot, n_items, &tm_x, &tm_sc, warp, lane);
     else if (nprelu == 1)
-      slot_role<C, S, WPS, HAS_SC, 1, FASTP, UP>(a, sm, tmem_base, slot, n_items, &tm_x, &tm_sc, warp, lane);
+      slot_role<C, S, WPS, HAS_SC, 1, FASTP, TAIL>(a, sm, tmem_base, slot, n_items, &tm_x, &tm_sc, warp, lane);
     else
-      slot_role<C, S, WPS, HAS_SC, 2, FASTP, UP>(a, sm, tmem_base, slot, n_items, &tm_x, &tm_sc, warp, lane);
+      slot_role<C, S, WPS, HAS_SC, 2, FASTP, TAIL>(a, sm, tmem_base, slot, n_items, &tm_x, &tm_sc, warp, lane);
   }
 
   tc_fence_before();
@@ -640,9 +694,11 @@ static int encode3(CUtensorMap* tm, const void* base, int c, uint64_t d1, uint64
   return OU_OK;
 }
 
-template <int C, int S, int WPS, bool UP = false>
+template <int C, int S, int WPS, int TAIL = 0>
 static int launch_cfg(const ou_trunk_params* p, cudaStream_t st) {
-  using G = Geo<C, S, UP>;
+  using G = Geo<C, S, TAIL>;
+  constexpr bool UP = TAIL == 1;
+  static_assert(G::SMEM <= 232448, "trunk_kernel: shared-memory budget exceeds the 227 KB a CTA may opt into");
   TrunkArgs a;
   a.trace = ou::tc::g_trace;
   a.p = *p;
@@ -676,8 +732,8 @@ static int launch_cfg(const ou_trunk_params* p, cudaStream_t st) {
   auto in01 = [](float a) { return a >= 0.f && a <= 1.f; };
   const bool fastp = in01(p->prelu_mid1) && in01(p->prelu_mid2) && (!p->has_prelu_out || in01(p->prelu_out)) &&
                      (!p->has_prelu_out2 || in01(p->prelu_out2));
-  auto kern = p->sc ? (fastp ? trunk_kernel<C, true, S, WPS, true, UP> : trunk_kernel<C, true, S, WPS, false, UP>)
-                    : (fastp ? trunk_kernel<C, false, S, WPS, true, UP> : trunk_kernel<C, false, S, WPS, false, UP>);
+  auto kern = p->sc ? (fastp ? trunk_kernel<C, true, S, WPS, true, TAIL> : trunk_kernel<C, true, S, WPS, false, TAIL>)
+                    : (fastp ? trunk_kernel<C, false, S, WPS, true, TAIL> : trunk_kernel<C, false, S, WPS, false, TAIL>);
   static SmemConfig cfg[4];
   if ((rc = ensure_smem(kern, (size_t)G::SMEM, cfg[(p->sc ? 1 : 0) + (fastp ? 2 : 0)], "ou_conv_trunk"))) return rc;
   const int n_sms = p->max_ctas > 0 && p->max_ctas < num_sms() ? p->max_ctas : num_sms();
@@ -692,7 +748,7 @@ static int launch_cfg(const ou_trunk_params* p, cudaStream_t st) {
 template <int C>
 static int launch_c(const ou_trunk_params* p, cudaStream_t st) {
   if constexpr (C == 64) {
-    if (p->up_w != nullptr) return launch_cfg<C, 3, 4, true>(p, st);   // fused up-conv tail
+    if (p->up_w != nullptr) return launch_cfg<C, 3, 4, 1>(p, st);   // fused up-conv tail
     // 4 slots fit exactly (no alignment slack) next to the 90 KB of weights; since the halo rows are
     // transformed chunk by chunk the kernel does not spill at 128 registers: 234 / 262 us against 250 / 265 us
     // with 3 slots (enc / dec, cfg-2 sizes); OU_TRUNK_S64=3 for A/B runs
@@ -700,6 +756,7 @@ static int launch_c(const ou_trunk_params* p, cudaStream_t st) {
     if (s64 == 4) return launch_cfg<C, 4, 4>(p, st);
   }
   if constexpr (C == 32) {
+    if (p->out_w != nullptr) return launch_cfg<C, 4, 4, 2>(p, st);   // fused output conv + SDE update
     // 4 slots fit next to the 22 KB of weights at C = 32 (16 warps -> 128 registers): measured 213 / 237 us
     // against 233 / 245 us with 3 slots (enc / dec, cfg-2 sizes); OU_TRUNK_S32=3 for A/B runs
     static const int s32 = [] { const char* e = getenv("OU_TRUNK_S32"); return e ? atoi(e) : 4; }();
@@ -713,8 +770,11 @@ static int launch_c(const ou_trunk_params* p, cudaStream_t st) {
 
 extern "C" int ou_conv_trunk(const ou_trunk_params* p, void* stream) {
   OU_REQUIRE(p != nullptr, "ou_conv_trunk: null params");
-  OU_REQUIRE(p->x && p->w1 && p->w2 && p->w3 && p->b1 && p->b2 && p->b3 && (p->out || p->up_w),
+  OU_REQUIRE(p->x && p->w1 && p->w2 && p->w3 && p->b1 && p->b2 && p->b3 && (p->out || p->up_w || p->out_w),
              "ou_conv_trunk: null pointer");
+  OU_REQUIRE(p->out_w == nullptr || (p->channels == 32 && p->up_w == nullptr && (p->out_net || p->out_coef) &&
+                                     (!p->out_coef || (p->out_x && p->out_xout))),
+             "ou_conv_trunk: the fused output conv needs C = 32, no up tail, and net_out or (coef, x, xout)");
   OU_REQUIRE(p->up_w == nullptr || (p->channels == 64 && p->up_out != nullptr && p->up_t_out > 0 &&
                                     p->up_t_out <= 2 * p->t && !p->has_prelu_out && !p->has_prelu_out2),
              "ou_conv_trunk: the fused up-conv tail needs C = 64, an output buffer of at most 2 t samples and no "

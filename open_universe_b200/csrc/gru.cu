@@ -313,6 +313,11 @@ struct G16 {
   static constexpr int NT = NW * 32;
   static constexpr int KS = H / 16;      // k16 steps
   static constexpr int CELLS = (H / 8) * 10;   // 16-byte cells per h buffer
+  // input ring (per warp): XD stages of [8 clip slots][XCLIP floats: gates r, z, n x 8 units, padded so that the
+  // four clip pairs of a quarter warp hit distinct banks] + [8 clip slots][8 units] of the 16-bit residual
+  static constexpr int XD = 4;
+  static constexpr int XCLIP = 28;
+  static constexpr int XSTAGE = 8 * XCLIP * 4 + 8 * 16;   // bytes: 1 024
   static_assert(H % 64 == 0 && HS % 8 == 0 && KS % 2 == 0, "bad GRU shape");
 };
 
@@ -343,6 +348,19 @@ __device__ __forceinline__ void st_async_u4(uint32_t remote_addr, uint4 v, uint3
                ::"r"(remote_addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(remote_bar)
                : "memory");
 }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned short lds_u16(uint32_t addr) {
+  unsigned short v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr) : "memory");
+  return v;
+}
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
   uint32_t r;
   asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
@@ -357,6 +375,7 @@ __global__ void __launch_bounds__(G16<H>::NT) gru_cluster_f16_kernel(const GruAr
   using G = G16<H>;
   constexpr int CS = G::CS, HS = G::HS, KS = G::KS;
   __shared__ __align__(16) uint4 h_buf[2][G::CELLS];
+  __shared__ __align__(16) uint8_t x_ring[G::NW][G::XD][G::XSTAGE];
   __shared__ __align__(8) unsigned long long h_full[2];
 
   cg::cluster_group cluster = cg::this_cluster();
@@ -404,74 +423,95 @@ __global__ void __launch_bounds__(G16<H>::NT) gru_cluster_f16_kernel(const GruAr
   bool valid[2];
   float bhr = 0.f, bhz = 0.f, bhn = 0.f;
   float hprev[2] = {0.f, 0.f};
-  const float* gxp[2] = {nullptr, nullptr};
-  size_t out_base[2] = {0, 0};
   {
     const float* bh = a.b_hh + (size_t)dir * 3 * H;
     bhr = bh[hu], bhz = bh[H + hu], bhn = bh[2 * H + hu];
   }
+  const bool has_add = a.add != nullptr;
+  const int ocb = cl_cb(2 * H);
+  const int t_first = dir ? T - 1 : 0;
+  // output element of this lane's (unit, clip) pairs at the first time step, advanced by one row per step
+  act_t* outp[2] = {a.out, a.out};
+  const ptrdiff_t out_step = dir ? -(ptrdiff_t)ocb : (ptrdiff_t)ocb;
 #pragma unroll
   for (int e = 0; e < 2; e++) {
     const int clip = b0 + 2 * t4 + e;
     valid[e] = slot_ok && clip < a.batch;
-    if (valid[e]) {
-      gxp[e] = a.gx + (size_t)clip * T * 6 * H + (size_t)dir * 3 * H + hu;
-      out_base[e] = cl_off(clip, dir * H + hu, 0, 2 * H, T, cl_cb(2 * H));
-    }
+    if (valid[e]) outp[e] = a.out + cl_off(clip, dir * H + hu, t_first, 2 * H, T, ocb);
   }
-  const bool has_add = a.add != nullptr;
-  const unsigned short* addp = reinterpret_cast<const unsigned short*>(a.add);
-  const int ocb = cl_cb(2 * H);
   // push target of this lane: CTA g; cells (octet, clip 2*t4) and (octet, clip 2*t4 + 1) of its h_buf[0]
   const uint32_t dst_h = mapa_u32((uint32_t)__cvta_generic_to_shared(&h_buf[0][octet * 10 + 2 * t4]), (uint32_t)g);
   const uint32_t dst_bar = mapa_u32(bar0, (uint32_t)g);
-  cluster.sync();
 
-  // input pre-activations (and the residual) come from HBM / L2: fetched two steps ahead and kept as
-  // raw bits until used, so that no dependent instruction stalls the in-order warp on a load.  The
-  // loop is deliberately NOT unrolled (rotating register sets instead of the moves at its end): the
-  // 3x larger body measured 12 % slower -- the recurrence is a serial chain and pays for every
-  // instruction-cache line it touches.
-  float x0[2][3], x1[2][3];
-  unsigned short ad0[2], ad1[2];
+  // Input pre-activations (and the residual) stream from HBM / L2 through a per-warp ring of XD stages in
+  // shared memory, filled with 16-byte cp.async XD - 1 steps ahead: per step and warp 8 clips x 3 gates x 8
+  // units of fp32 gx (48 chunks) + 8 clips x 8 units of the 16-bit residual (8 chunks) = 56 chunks, at most
+  // two per lane, each lane advancing its own source pointer by one time step.  (The previous version loaded
+  // them into registers two steps ahead: with the loop not unrolled that takes register moves which wait on the
+  // loads, per-step address arithmetic and four branches -- 499 of the 1 434 cycles of a step.)
+  const uint32_t ring = (uint32_t)__cvta_generic_to_shared(&x_ring[warp][0][0]);
+  const char* src[2] = {nullptr, nullptr};
+  ptrdiff_t src_step[2] = {0, 0};
+  uint32_t dst_off[2] = {0, 0};
 #pragma unroll
-  for (int e = 0; e < 2; e++) {
-    x0[e][0] = x0[e][1] = x0[e][2] = x1[e][0] = x1[e][1] = x1[e][2] = 0.f;
-    ad0[e] = ad1[e] = 0;
-    if (valid[e]) {
-      const int ta = dir ? T - 1 : 0;
-      const float* gp = gxp[e] + (size_t)ta * 6 * H;
-      x0[e][0] = __ldg(gp), x0[e][1] = __ldg(gp + H), x0[e][2] = __ldg(gp + 2 * H);
-      if (has_add) ad0[e] = __ldg(addp + out_base[e] + (size_t)ta * ocb);
-      if (T > 1) {
-        const int tb = dir ? T - 2 : 1;
-        gp = gxp[e] + (size_t)tb * 6 * H;
-        x1[e][0] = __ldg(gp), x1[e][1] = __ldg(gp + H), x1[e][2] = __ldg(gp + 2 * H);
-        if (has_add) ad1[e] = __ldg(addp + out_base[e] + (size_t)tb * ocb);
+  for (int j = 0; j < 2; j++) {
+    const int c = lane + 32 * j;                    // chunk of the warp's stage
+    if (c < 48) {
+      const int cs = c / 6, gate = (c % 6) >> 1, half = c & 1, clip = b0 + cs;
+      if (cs < BG && clip < a.batch) {
+        src[j] = reinterpret_cast<const char*>(a.gx + ((size_t)clip * T + t_first) * 6 * H + (size_t)dir * 3 * H +
+                                               gate * H + rank * HS + 8 * warp + 4 * half);
+        src_step[j] = (dir ? -1 : 1) * (ptrdiff_t)(6 * H * sizeof(float));
+        dst_off[j] = (uint32_t)((cs * G::XCLIP + gate * 8 + half * 4) * 4);
+      }
+    } else if (c < 56 && has_add) {
+      const int cs = c - 48, clip = b0 + cs;
+      if (cs < BG && clip < a.batch) {
+        src[j] = reinterpret_cast<const char*>(a.add + cl_off(clip, dir * H + rank * HS + 8 * warp, t_first, 2 * H, T, ocb));
+        src_step[j] = out_step * (ptrdiff_t)sizeof(act_t);
+        dst_off[j] = (uint32_t)(8 * G::XCLIP * 4 + cs * 16);
       }
     }
   }
-  for (int step = 0; step < T; step++) {
-    const int t = dir ? (T - 1 - step) : step;
-    const int cur = step & 1;
-    float x2[2][3];
-    unsigned short ad2[2];
+  const bool has_src0 = src[0] != nullptr, has_src1 = src[1] != nullptr;
+  auto prefetch = [&](int stage, bool in_range) {
+    if (has_src0 && in_range) cp_async16(ring + (uint32_t)stage * G::XSTAGE + dst_off[0], src[0]);
+    if (has_src1 && in_range) cp_async16(ring + (uint32_t)stage * G::XSTAGE + dst_off[1], src[1]);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    src[0] += src_step[0], src[1] += src_step[1];
+  };
+  // the ring of a warp is private to it: zero it (unused clip slots are read, never loaded) before the fill
+  for (int i = lane; i < G::XD * G::XSTAGE / 16; i += 32)
+    reinterpret_cast<uint4*>(&x_ring[warp][0][0])[i] = make_uint4(0, 0, 0, 0);
+  __syncwarp();
+  cluster.sync();
 #pragma unroll
-    for (int e = 0; e < 2; e++) {
-      x2[e][0] = x2[e][1] = x2[e][2] = 0.f;
-      ad2[e] = 0;
-      if (valid[e] && step + 2 < T) {
-        const int tn = dir ? t - 2 : t + 2;
-        const float* gp = gxp[e] + (size_t)tn * 6 * H;
-        x2[e][0] = __ldg(gp), x2[e][1] = __ldg(gp + H), x2[e][2] = __ldg(gp + 2 * H);
-        if (has_add) ad2[e] = __ldg(addp + out_base[e] + (size_t)tn * ocb);
-      }
-    }
+  for (int j = 0; j < G::XD - 1; j++) prefetch(j, j < T);
+  // this lane's values inside a stage: gates r, z, n of unit g for clips 2*t4 and 2*t4 + 1; residual likewise
+  const uint32_t rd_x = ring + (uint32_t)((2 * t4 * G::XCLIP + g) * 4);
+  const uint32_t rd_a = ring + (uint32_t)(8 * G::XCLIP * 4 + 2 * t4 * 16 + g * 2);
+
+  for (int step = 0; step < T; step++) {
+    const int cur = step & 1;
+    prefetch((step + G::XD - 1) % G::XD, step + G::XD - 1 < T);
     // arm the barrier that collects h_t (H units x BG clips x 2 B), then wait for h_{t-1}
     if (tid == 0 && step + 1 < T)
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8u * (cur ^ 1)),
                    "r"((uint32_t)(H * BG * 2))
                    : "memory");
+    asm volatile("cp.async.wait_group %0;" ::"n"(G::XD - 1) : "memory");
+    __syncwarp();
+    float x0[2][3];
+    unsigned short ad0[2];
+    {
+      const uint32_t so = (uint32_t)(step % G::XD) * G::XSTAGE;
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+#pragma unroll
+        for (int q = 0; q < 3; q++) x0[e][q] = lds_f32(rd_x + so + (uint32_t)((e * G::XCLIP + q * 8) * 4));
+        ad0[e] = lds_u16(rd_a + so + (uint32_t)(e * 16));
+      }
+    }
     GRU_STAMP(0)
     gru_mbar_wait(bar0 + 8u * cur, (uint32_t)((step >> 1) & 1));
     GRU_STAMP(1)
@@ -550,13 +590,8 @@ __global__ void __launch_bounds__(G16<H>::NT) gru_cluster_f16_kernel(const GruAr
     GRU_STAMP(4)
 #pragma unroll
     for (int e = 0; e < 2; e++) {
-      if (valid[e]) {
-        const float addv = act_bits_to_f(ad0[e]);
-        a.out[out_base[e] + (size_t)t * ocb] = f_to_act((hnew[e] + addv) * a.scale);
-      }
-#pragma unroll
-      for (int q = 0; q < 3; q++) x0[e][q] = x1[e][q], x1[e][q] = x2[e][q];
-      ad0[e] = ad1[e], ad1[e] = ad2[e];
+      if (valid[e]) *outp[e] = f_to_act((hnew[e] + act_bits_to_f(ad0[e])) * a.scale);
+      outp[e] += out_step;
     }
     GRU_STAMP(5)
   }

@@ -123,6 +123,10 @@ extern "C" int ou_plan_run(const ou_plan* plan, const ou_step_args* args, int fi
           p.beta = p.gamma + p.channels;
           p.film_bstride = args->film_bstride;
         }
+        if (p.out_w != nullptr) {   // fused output conv + EDM / SDE update: per-evaluation arguments
+          p.out_coef = args->coef, p.out_x = args->x, p.out_noise = args->noise;
+          p.out_xout = args->xout, p.out_net = args->net_out;
+        }
         rc = ou_conv_trunk(&p, stream);
         break;
       }

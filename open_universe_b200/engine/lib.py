@@ -47,6 +47,8 @@ class TrunkParams(Structure):
         ("max_ctas", c_int32),
         ("up_w", c_void_p), ("up_bias", c_void_p), ("up_skip", c_void_p), ("up_out", c_void_p),
         ("up_t_out", c_int32), ("up_scale", c_float), ("up_prelu_in", c_float),
+        ("out_w", c_void_p), ("out_bias", c_float), ("out_coef", c_void_p), ("out_x", c_void_p),
+        ("out_noise", c_void_p), ("out_xout", c_void_p), ("out_net", c_void_p),
     ]
 
 
@@ -97,7 +99,7 @@ SIGNATURES = {
     "ou_plan_destroy": (c_int, [c_void_p]),
     "ou_plan_size": (c_int, [c_void_p]),
     "ou_plan_add_conv": (c_int, [c_void_p, POINTER(ConvParams), c_int32]),
-    "ou_plan_add_trunk": (c_int, [c_void_p, POINTER(TrunkParams), c_int32]),
+    "ou_plan_add_trunk": (c_int, [c_void_p, POINTER(TrunkParams), c_int32]),   # out tail: fed from ou_step_args
     "ou_plan_add_input_conv": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                        c_int]),
     "ou_plan_add_output_sde": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_int, c_int,

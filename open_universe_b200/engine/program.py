@@ -76,17 +76,23 @@ class TrunkOp:
     # the next decoder block's transposed up conv (+ skip add) fused behind conv3 (C = 64 only): the block
     # output stays in shared memory, ``parts[2].dst`` is not written by the fused launch
     tail: Optional[ConvOp] = None
+    # the network's output conv + EDM / SDE update fused behind conv3 (C = 32 only, ``OutputOp``)
+    tail_out: Optional[object] = None
 
     def all_parts(self):
+        return (self.parts + ([self.tail] if self.tail is not None else [])
+                + ([self.tail_out] if self.tail_out is not None else []))
+
+    def conv_parts(self):
         return self.parts + ([self.tail] if self.tail is not None else [])
 
     @property
     def flops_exec(self):
-        return sum(p.flops_exec for p in self.all_parts())
+        return sum(p.flops_exec for p in self.conv_parts())
 
     @property
     def flops_algo(self):
-        return sum(p.flops_algo for p in self.all_parts())
+        return sum(p.flops_algo for p in self.conv_parts())
 
 
 TRUNK_CHANNELS = (32, 64)
@@ -118,6 +124,8 @@ def fuse_trunk(prog, name, n_parts=3):
 # OU_TRUNK_TAIL=0 keeps the up convs as separate ou_conv1d launches (A/B runs)
 import os as _os
 TRUNK_TAIL = _os.environ.get("OU_TRUNK_TAIL", "1") != "0"
+# OU_TRUNK_OUT_TAIL=0 keeps the output conv + SDE update as a separate ou_output_sde launch (A/B runs)
+TRUNK_OUT_TAIL = _os.environ.get("OU_TRUNK_OUT_TAIL", "1") != "0"
 
 
 def fuse_up_tail(prog):
@@ -142,6 +150,22 @@ def fuse_up_tail(prog):
     if not ok:
         return False
     tr.tail = up
+    del prog.ops[-1]
+    return True
+
+
+def fuse_out_tail(prog):
+    """If the last op is the network's OutputOp reading the output of the 32-channel TrunkOp right before it
+    (dec.last.trunk -> output_conv), fold it into that trunk launch."""
+    if not (TRUNK_TAIL and TRUNK_OUT_TAIL) or len(prog.ops) < 2:
+        return False
+    out, tr = prog.ops[-1], prog.ops[-2]
+    if not (isinstance(out, OutputOp) and isinstance(tr, TrunkOp) and tr.tail is None and tr.tail_out is None):
+        return False
+    c3 = tr.parts[2]
+    if not (c3.fc.cin == 32 and out.src == c3.dst and out.w.shape == (32, 3) and out.t == out.t_out == c3.t_out):
+        return False
+    tr.tail_out = out
     del prog.ops[-1]
     return True
 
@@ -411,6 +435,7 @@ def lower_score_network(net, batch, t):
     b_out = fold.bias_of(oc.conv)
     b_out = float(b_out[0].item()) if b_out is not None else 0.0
     prog.ops.append(OutputOp("output_conv", h, w_out, b_out, tl, t))
+    fuse_out_tail(prog)
     prog.meta["lengths"] = lengths
     prog.meta["cond_channels"] = [b.n_channels for b in dec.up_modules]
     return prog
@@ -521,7 +546,9 @@ def op_bytes(op, batch, elem=2):
     if isinstance(op, TrunkOp):
         c1 = op.parts[0]
         c, t = c1.fc.cin, c1.t_in
-        w = sum(p.fc.w.numel() for p in op.all_parts()) * elem
+        w = sum(p.fc.w.numel() for p in op.conv_parts()) * elem
+        if op.tail_out is not None:  # x (+ sc) in; signal x, noise in and x out (fp32); the block output stays on chip
+            return elem * batch * c * t * (1 + (c1.add1 is not None)) + 3 * 4 * batch * t + w
         if op.tail is not None:      # x (+ sc) in; the up conv's skip in and output out; the block output stays on chip
             up = op.tail
             return (elem * batch * c * t * (1 + (c1.add1 is not None))
@@ -550,7 +577,9 @@ def op_bytes(op, batch, elem=2):
 
 def op_flops(op, batch):
     """Algorithmic FLOPs of one launch (reference graph as written, see ``add_conv``)."""
-    if isinstance(op, (ConvOp, TrunkOp)):
+    if isinstance(op, TrunkOp):
+        return op.flops_algo + (op_flops(op.tail_out, batch) if op.tail_out is not None else 0.0)
+    if isinstance(op, ConvOp):
         return op.flops_algo
     if isinstance(op, (InputConvOp, OutputOp)):
         return 2.0 * batch * op.t * op.w.numel()

@@ -165,7 +165,8 @@ def prepare_ops(prog, device, shared=None, tag=""):
             op.packed = packed_for(op, lambda: {"w": op.w.to(device).contiguous(),
                                                 "bias": op.bias.to(device).contiguous()})
         elif isinstance(op, P.OutputOp):
-            op.packed = packed_for(op, lambda: {"w": op.w.to(device).contiguous()})
+            op.packed = packed_for(op, lambda: {"w": op.w.to(device).contiguous(),
+                                                "w_kc": op.w.t().contiguous().to(device)})   # tap-major [k][C]
         elif isinstance(op, P.GruOp):
             op.packed = packed_for(op, lambda: {"w_hh": op.w_hh.to(device).contiguous(),
                                                 "b_hh": op.b_hh.to(device).contiguous()})
@@ -231,8 +232,10 @@ def launch_conv(op, bufs, batch, gamma=None, beta=None, film_bstride=0, naive=Fa
 USE_TRUNK = os.environ.get("OU_TRUNK", "1") != "0"
 
 
-def trunk_params(op, bufs, batch, film=None, film_bstride=0, max_ctas=0):
-    """``ou_trunk_params`` of a TrunkOp bound to device buffers."""
+def trunk_params(op, bufs, batch, film=None, film_bstride=0, max_ctas=0, coef=None, noise=None, xout=None,
+                 net_out=None):
+    """``ou_trunk_params`` of a TrunkOp bound to device buffers (``coef`` ... ``net_out``: the per-evaluation
+    arguments of a fused output tail, as for the OutputOp)."""
     c1, c2, c3 = op.parts
     prm = lib.TrunkParams()
     prm.max_ctas = max_ctas
@@ -260,12 +263,18 @@ def trunk_params(op, bufs, batch, film=None, film_bstride=0, max_ctas=0):
         prm.up_skip = bufs[up.add1].data_ptr() if up.add1 else None
         prm.up_out = bufs[up.dst].data_ptr()
         prm.up_t_out, prm.up_scale, prm.up_prelu_in = up.t_out, up.scale1, up.fc.prelu_in
+    if op.tail_out is not None:
+        oc = op.tail_out
+        prm.out_w, prm.out_bias = oc.packed["w_kc"].data_ptr(), oc.bias
+        prm.out_coef, prm.out_x = _ptr(coef), _ptr(bufs.get("x"))
+        prm.out_noise, prm.out_xout, prm.out_net = _ptr(noise), _ptr(xout), _ptr(net_out)
     return prm
 
 
-def launch_trunk(op, bufs, batch, film=None, film_bstride=0, max_ctas=0):
-    """One ``ou_conv_trunk`` launch for the three ConvOps of a TrunkOp."""
-    prm = trunk_params(op, bufs, batch, film, film_bstride, max_ctas)
+def launch_trunk(op, bufs, batch, film=None, film_bstride=0, max_ctas=0, coef=None, noise=None, xout=None,
+                 net_out=None):
+    """One ``ou_conv_trunk`` launch for the three ConvOps of a TrunkOp (+ its fused tails)."""
+    prm = trunk_params(op, bufs, batch, film, film_bstride, max_ctas, coef, noise, xout, net_out)
     lib.check(lib.load().ou_conv_trunk(byref(prm), _stream()))
 
 
@@ -294,7 +303,7 @@ class Executor:
                 e0 = torch.cuda.Event(enable_timing=True)
                 e0.record()
             if isinstance(op, P.TrunkOp):
-                launch_trunk(op, bufs, B, film, film_bstride, self.max_ctas)
+                launch_trunk(op, bufs, B, film, film_bstride, self.max_ctas, coef, noise, xout, net_out)
             elif isinstance(op, P.ConvOp):
                 gamma = beta = None
                 if op.film_off is not None:

@@ -432,3 +432,74 @@ def test_conv_trunk_with_up_tail_vs_emulator(c):
         bad = (d > 0.05 * want.abs().max()).float()
         raise AssertionError(f"rel_rms={err:.4f} vs split {err_split:.4f} bad_fraction={bad.mean():.5f} "
                              f"bad rows (time) {bad.amax(dim=(0, 1)).nonzero().flatten()[:24].tolist()}")
+
+
+OUT_TAIL_CASES = [
+    dict(t=1000, B=2, sc=True, film=True, sde=True, noise=True),
+    dict(t=251, B=1, sc=False, film=False, sde=False, noise=False),      # raw network output only, partial item
+    dict(t=250 * 3, B=3, sc=True, film=False, sde=True, noise=False),    # exact multiple of the item
+    dict(t=250 * 2 + 1, B=2, sc=False, film=True, sde=True, noise=True),
+    dict(t=128160, B=2, sc=True, film=True, sde=True, noise=True),       # many items per CTA
+]
+
+
+@pytest.mark.parametrize("c", OUT_TAIL_CASES, ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items()))
+def test_conv_trunk_with_output_tail_vs_emulator(c):
+    """ou_conv_trunk with the network's output conv + EDM mix + SDE update fused behind conv3 (C = 32):
+    against the emulator and against the separate launches (trunk expansion + ou_output_sde)."""
+    g = torch.Generator().manual_seed(555)
+    B, C, t = c["B"], 32, c["t"]
+    prog = P.Program(B)
+    prog.buf("in", "blocked", C, t)
+    inputs = {"in": bf(torch.randn(B, C, t, generator=g))}
+    if c["sc"]:
+        prog.buf("sc", "blocked", C, t)
+        inputs["sc"] = bf(torch.randn(B, C, t, generator=g))
+    P.add_conv(prog, "conv1", "in", "c1", rand_fc(g, C, C, taps=5, tap_off=-2, prelu_in=0.2), t,
+               add1="sc" if c["sc"] else None, scale1=0.7071 if c["sc"] else 1.0,
+               film_off=0 if c["film"] else None, prelu_out=0.15)
+    P.add_conv(prog, "conv2", "c1", "c2", rand_fc(g, C, C, taps=3, tap_off=-1), t, prelu_out=0.3)
+    P.add_conv(prog, "conv3", "c2", "v", rand_fc(g, C, C, taps=3, tap_off=-1), t, add1="in", scale1=0.7071,
+               prelu_out=0.2)
+    assert P.fuse_trunk(prog, "trunk")
+    prog.ops.append(P.OutputOp("output_conv", "v", torch.randn(C, 3, generator=g) / 6, 0.3, t, t))
+    assert P.fuse_out_tail(prog) and len(prog.ops) == 1 and prog.ops[0].tail_out is not None
+    film = torch.randn(B, 2 * C, generator=g) if c["film"] else None
+    x = torch.randn(B, 1, t, generator=g)
+    coef = torch.randn(B, 3, generator=g) if c["sde"] else None
+    noise = torch.randn(B, 1, t, generator=g) if c["noise"] else None
+    _, want_net, want_x = E.run_program(prog, dict(inputs, x=x), film=film, coef=coef, noise=noise, quant=True)
+
+    exe = R.Executor(prog, DEV, external=list(inputs))
+    for k, v in inputs.items():
+        exe.bufs[k] = R.pack_blocked(v.to(DEV))
+    exe.bufs["x"] = x.to(DEV)
+    film_d = film.to(DEV).contiguous() if film is not None else None
+    d_coef = coef.to(DEV) if coef is not None else None
+    d_noise = noise.to(DEV) if noise is not None else None
+
+    def run():
+        xo = torch.full((B, 1, t), 7.0, device=DEV) if coef is not None else None
+        no = torch.full((B, 1, t), 7.0, device=DEV)
+        n0 = lib.launch_count()
+        exe.run(film=film_d, film_bstride=2 * C, coef=d_coef, noise=d_noise, xout=xo, net_out=no)
+        torch.cuda.synchronize()
+        return lib.launch_count() - n0, no.cpu(), (xo.cpu() if xo is not None else None)
+
+    n, net, xnew = run()
+    assert n == 1
+    R.USE_TRUNK = False
+    try:
+        n, net_split, xnew_split = run()
+        assert n == 4
+    finally:
+        R.USE_TRUNK = True
+    assert torch.isfinite(net).all()
+    err, err_split = rel_rms(net, want_net), rel_rms(net, net_split)
+    if err >= 3e-3 or err_split >= 3e-3:
+        bad = ((net - want_net).abs() > 0.05 * want_net.abs().max()).float()
+        raise AssertionError(f"net rel_rms={err:.4f} vs split {err_split:.4f} bad_fraction={bad.mean():.5f} "
+                             f"bad rows (time) {bad.amax(dim=(0, 1)).nonzero().flatten()[:24].tolist()}")
+    if coef is not None:
+        assert rel_rms(xnew, want_x) < 3e-3 and rel_rms(xnew, xnew_split) < 3e-3
+    # without the SDE arguments the raw output is still written and x_out is left alone
