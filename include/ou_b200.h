@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define OU_ABI_VERSION 3
+#define OU_ABI_VERSION 4
 
 enum {
   OU_OK = 0,
@@ -71,7 +71,7 @@ int64_t ou_conv_fallback_count(void);
  *   y = ((acc + bias[n] + add1[co][t]) * scale1 + add2[co][t]) * scale2
  *   y = gamma[b][co] * y + beta[b][co]                    (if gamma != NULL)
  *   y = PReLU(PReLU(y, prelu_out), prelu_out2)            (each if enabled)
- *   out (blocked act (B, cout, t_out))  or  out_f32_tm (fp32 [B][rows][n], no add/film/prelu)
+ *   out (blocked act (B, cout, t_out))  or  out_f32_blk (fp32 [B][n/16][rows][16], no add/film/prelu)
  * ------------------------------------------------------------------------------------------ */
 typedef struct ou_conv_params {
   const void* x;          /* blocked act (B, cin, t_in)                                  */
@@ -86,7 +86,7 @@ typedef struct ou_conv_params {
   const float* gamma;     /* fp32, element (b, co) at gamma[b*film_bstride + co], or NULL       */
   const float* beta;      /* fp32, same indexing                                                */
   void* out;              /* blocked act (B, cout, t_out) or NULL                         */
-  float* out_f32_tm;      /* fp32 [B][rows][n] or NULL (exactly one of out / out_f32_tm)        */
+  float* out_f32_blk;     /* fp32 [B][n/16][rows][16] or NULL (exactly one of out / out_f32_blk) */
   int32_t batch, cin, t_in;
   int32_t s, taps, tap_off;
   int32_t n, cout, up;
@@ -193,7 +193,8 @@ int ou_output_sde(const void* src, const float* w, float bias, const float* coef
 /* ------------------------------------------------------------------------------------------
  * Bidirectional GRU recurrence (one layer).  Replaces torch.nn.GRU at the score bottleneck
  * (score.py:82-89,116-117; every step) and in the conditioner (condition.py:173-179,213).
- *   gx    fp32 [B][T][6H]: x W_ih^T + b_ih, forward (r,z,n) then backward (r,z,n)
+ *   gx    fp32 blocked [B][6H/16][T][16] (what ou_conv1d writes through out_f32_blk): x W_ih^T + b_ih,
+ *         columns = forward (r,z,n) then backward (r,z,n)
  *   w_hh  fp32 [2][3H][H],  b_hh fp32 [2][3H]
  *   r = s(gx_r + W_hr h + b_hr); z = s(gx_z + W_hz h + b_hz); n = tanh(gx_n + r*(W_hn h + b_hn));
  *   h' = (1-z)*n + z*h; h0 = 0; backward direction runs t = T-1..0

@@ -83,6 +83,11 @@ __host__ __device__ inline size_t cl_off(int b, int c, int t, int channels, int 
   return (((size_t)b * (channels / cb) + c / cb) * t_len + t) * cb + (c % cb);
 }
 
+// fp32 blocked layout [B][N/16][rows][16] (GRU input pre-activations): element offset of column n, row j
+__host__ __device__ inline size_t f32blk_off(int b, int n, int j, int n_total, int rows) {
+  return (((size_t)b * (n_total >> 4) + (n >> 4)) * rows + j) * 16 + (n & 15);
+}
+
 __device__ __forceinline__ float prelu_f(float x, float a) { return x >= 0.f ? x : a * x; }
 
 // ---- storage / tensor-core operand type of every activation and conv weight ("act") ----

@@ -65,8 +65,8 @@ __device__ __forceinline__ void epilogue_pair(const ou_conv_params& p, int b, in
     v0 += p.bias[n];
     v1 += p.bias[n + 1];
   }
-  if (p.out_f32_tm) {
-    float2* dst = reinterpret_cast<float2*>(p.out_f32_tm + ((size_t)b * p.rows + j) * p.n + n);
+  if (p.out_f32_blk) {
+    float2* dst = reinterpret_cast<float2*>(p.out_f32_blk + f32blk_off(b, n, j, p.n, p.rows));
     *dst = make_float2(v0, v1);
     return;
   }
@@ -293,19 +293,19 @@ __global__ void conv1d_naive_kernel(const ConvArgs a) {
 static int validate(const ou_conv_params* p, ConvArgs* a) {
   OU_REQUIRE(p != nullptr, "ou_conv1d: null params");
   OU_REQUIRE(p->x && p->w, "ou_conv1d: null x / w");
-  OU_REQUIRE((p->out != nullptr) != (p->out_f32_tm != nullptr),
-             "ou_conv1d: exactly one of out / out_f32_tm must be set");
+  OU_REQUIRE((p->out != nullptr) != (p->out_f32_blk != nullptr),
+             "ou_conv1d: exactly one of out / out_f32_blk must be set");
   OU_REQUIRE(p->batch > 0 && p->cin > 0 && p->t_in > 0 && p->rows > 0, "ou_conv1d: empty problem");
   OU_REQUIRE(p->cin % 16 == 0 && p->cout % 16 == 0, "ou_conv1d: channels must be multiples of 16");
   OU_REQUIRE(p->s >= 1 && p->up >= 1 && p->taps >= 1 && p->taps <= 8, "ou_conv1d: bad s/up/taps");
   OU_REQUIRE(p->n == p->up * p->cout, "ou_conv1d: n != up*cout");
   OU_REQUIRE(p->kpad % 32 == 0 && p->kpad >= p->s * p->cin, "ou_conv1d: bad kpad");
   OU_REQUIRE(p->npad % 32 == 0 && p->npad >= p->n, "ou_conv1d: bad npad");
-  OU_REQUIRE(p->out_f32_tm == nullptr ||
+  OU_REQUIRE(p->out_f32_blk == nullptr ||
                  (!p->add1 && !p->add2 && !p->gamma && !p->has_prelu_out && !p->has_prelu_out2 &&
                   p->up == 1),
              "ou_conv1d: fp32 time-major output takes no epilogue");
-  OU_REQUIRE(p->out_f32_tm != nullptr || p->t_out > 0, "ou_conv1d: t_out");
+  OU_REQUIRE(p->out_f32_blk != nullptr || p->t_out > 0, "ou_conv1d: t_out");
   OU_REQUIRE((p->gamma == nullptr) == (p->beta == nullptr), "ou_conv1d: gamma/beta");
   a->p = *p;
   a->cin_chunks = p->cin / 8;

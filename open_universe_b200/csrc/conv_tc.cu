@@ -152,7 +152,10 @@ __device__ __forceinline__ void mma_role(const TcArgs& a, const Ctx& c, bool use
     tc_fence_after();
     if (issuer) trace_ev(a, 1, ti, 0);
     const uint32_t d_tmem = c.tmem_base + (uint32_t)(acc * a.bn * a.m_sub);
-    const int m_sub = a.m_sub;
+    // sub-tiles of the unit that hold rows of the clip at all (the last unit of a clip may be short: its empty
+    // sub-tiles are neither multiplied nor stored)
+    const int rows_left = a.p.rows - (mt % a.m_tiles) * BM * a.m_sub;
+    const int m_sub = rows_left >= BM * a.m_sub ? a.m_sub : (rows_left + BM - 1) / BM;
     const uint32_t sub_units = a.a_sub_bytes >> 4;
     for (int kb = 0; kb < n_kblocks; kb++) {
       mbar_wait(a_ready + 8u * ra.stage, ra.phase);
@@ -441,12 +444,21 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& a, const Ctx& c, int
         if (F32TM) {
           const int j = m0 + sub * BM + row;
           if (j < p.rows && n0 + col < n_total) {
-            float4* dst = reinterpret_cast<float4*>(p.out_f32_tm + ((size_t)b * p.rows + j) * n_total + n0 + col);
+            // blocked fp32 [B][N/16][rows][16]: the 16 columns of a row are one 64-byte line, consecutive rows
+            // (lanes) consecutive lines -- two full-sector 32-byte stores per lane
+            float* dst = p.out_f32_blk + f32blk_off(b, n0 + col, j, n_total, p.rows);
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-              const float4 x1 = lds_f4(coef + 4u * (bn + col + 4 * i));
-              dst[i] = make_float4(__uint_as_float(r[4 * i]) + x1.x, __uint_as_float(r[4 * i + 1]) + x1.y,
-                                   __uint_as_float(r[4 * i + 2]) + x1.z, __uint_as_float(r[4 * i + 3]) + x1.w);
+            for (int h = 0; h < 2; h++) {
+              U8 o;
+#pragma unroll
+              for (int i = 0; i < 2; i++) {
+                const float4 x1 = lds_f4(coef + 4u * (bn + col + 8 * h + 4 * i));
+                o.w[4 * i] = __float_as_uint(__uint_as_float(r[8 * h + 4 * i]) + x1.x);
+                o.w[4 * i + 1] = __float_as_uint(__uint_as_float(r[8 * h + 4 * i + 1]) + x1.y);
+                o.w[4 * i + 2] = __float_as_uint(__uint_as_float(r[8 * h + 4 * i + 2]) + x1.z);
+                o.w[4 * i + 3] = __float_as_uint(__uint_as_float(r[8 * h + 4 * i + 3]) + x1.w);
+              }
+              stg_v8(dst + 8 * h, o);
             }
           }
           continue;
@@ -609,7 +621,7 @@ conv1d_tc_kernel(const TcArgs a, const __grid_constant__ CUtensorMap tm_a,
     const int widx = warp >= EPI_WARP0 ? (warp - EPI_WARP0) >> 2 : N_EPI_WARPS / 4;
     const int nadd = p.add2 ? 2 : (p.add1 ? 1 : 0);
     const int nprelu = p.has_prelu_out2 ? 2 : (p.has_prelu_out ? 1 : 0);
-    if (p.out_f32_tm) {
+    if (p.out_f32_blk) {
       epilogue_role<0, 0, true, false>(a, c, warp, lane, widx, nw);
     } else if (p.gamma != nullptr) {
       switch (nadd * 3 + nprelu) {

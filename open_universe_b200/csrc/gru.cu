@@ -90,25 +90,26 @@ __global__ void __launch_bounds__(3 * (H / CS) * (H / KPT)) gru_cluster_kernel(c
   if (fvalid) {
     const float* bh = a.b_hh + (size_t)dir * 3 * H;
     bhr = bh[hu], bhz = bh[H + hu], bhn = bh[2 * H + hu];
-    gxp = a.gx + (size_t)(b0 + fb) * T * 6 * H + (size_t)dir * 3 * H + hu;
+    gxp = a.gx + f32blk_off(b0 + fb, dir * 3 * H + hu, 0, 6 * H, T);   // + 16 per time step, gates H columns apart
     const int ch = dir * H + hu;
     out_base = cl_off(b0 + fb, ch, 0, 2 * H, T, cl_cb(2 * H));
   }
   cluster.sync();
 
   // input pre-activations are prefetched one step ahead (they come from HBM / L2)
+  const size_t GSTRIDE = (size_t)(H / 16) * T * 16;   // H columns further in the blocked fp32 layout
   float gxr = 0.f, gxz = 0.f, gxn = 0.f;
   if (fvalid) {
-    const float* g = gxp + (size_t)(dir ? T - 1 : 0) * 6 * H;
-    gxr = __ldg(g), gxz = __ldg(g + H), gxn = __ldg(g + 2 * H);
+    const float* g = gxp + (size_t)(dir ? T - 1 : 0) * 16;
+    gxr = __ldg(g), gxz = __ldg(g + GSTRIDE), gxn = __ldg(g + 2 * GSTRIDE);
   }
   for (int step = 0; step < T; step++) {
     const int t = dir ? (T - 1 - step) : step;
     const int cur = step & 1;
     float nxr = 0.f, nxz = 0.f, nxn = 0.f;
     if (fvalid && step + 1 < T) {
-      const float* g = gxp + (size_t)(dir ? t - 1 : t + 1) * 6 * H;
-      nxr = __ldg(g), nxz = __ldg(g + H), nxn = __ldg(g + 2 * H);
+      const float* g = gxp + (size_t)(dir ? t - 1 : t + 1) * 16;
+      nxr = __ldg(g), nxz = __ldg(g + GSTRIDE), nxn = __ldg(g + 2 * GSTRIDE);
     }
     float acc[BG];
 #pragma unroll
@@ -305,9 +306,9 @@ __device__ __forceinline__ void gru_mbar_wait(uint32_t bar, uint32_t parity) {
 // columns of every 32) so that one 16-byte shared load feeds two k16 steps; W_hh fragments use the
 // same permutation.  h_buf holds 16-byte (octet, clip) cells at index octet * 10 + clip: the
 // B-fragment loads of a quarter warp then hit 32 distinct banks.
-template <int H>
+template <int H, int CS_ = 8>
 struct G16 {
-  static constexpr int CS = 8;
+  static constexpr int CS = CS_;         // CTAs per cluster: 8, or 12 (non-portable) so that H = 384 keeps one warp per scheduler
   static constexpr int HS = H / CS;      // hidden units per CTA
   static constexpr int NW = HS / 8;      // warps (8 units each)
   static constexpr int NT = NW * 32;
@@ -318,7 +319,7 @@ struct G16 {
   static constexpr int XD = 4;
   static constexpr int XCLIP = 28;
   static constexpr int XSTAGE = 8 * XCLIP * 4 + 8 * 16;   // bytes: 1 024
-  static_assert(H % 64 == 0 && HS % 8 == 0 && KS % 2 == 0, "bad GRU shape");
+  static_assert(H % 64 == 0 && H % CS == 0 && HS % 8 == 0 && KS % 2 == 0 && CS >= 8 && CS <= 16, "bad GRU shape");
 };
 
 // 1 / (1 + 2^x): ex2.approx.ftz + rcp.approx.ftz, ~2 ulp; the argument never leaves [-126, 126] in any
@@ -370,9 +371,9 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
 // BG: clip slots per cluster (4 or 8; the MMA n dimension is always 8); NCH: accumulator chains per
 // tile (measured: 4 chains are no faster than 2 -- the k loop is bound by HMMA issue, ~10 clk each);
 // LEAN: branch-free gate math on bare ex2 / rcp (halves the gate phase)
-template <int H, int BG, int NCH, bool LEAN>
-__global__ void __launch_bounds__(G16<H>::NT) gru_cluster_f16_kernel(const GruArgs a) {
-  using G = G16<H>;
+template <int H, int BG, int NCH, bool LEAN, int CSZ>
+__global__ void __launch_bounds__(G16<H, CSZ>::NT) gru_cluster_f16_kernel(const GruArgs a) {
+  using G = G16<H, CSZ>;
   constexpr int CS = G::CS, HS = G::HS, KS = G::KS;
   __shared__ __align__(16) uint4 h_buf[2][G::CELLS];
   __shared__ __align__(16) uint8_t x_ring[G::NW][G::XD][G::XSTAGE];
@@ -442,6 +443,11 @@ __global__ void __launch_bounds__(G16<H>::NT) gru_cluster_f16_kernel(const GruAr
   // push target of this lane: CTA g; cells (octet, clip 2*t4) and (octet, clip 2*t4 + 1) of its h_buf[0]
   const uint32_t dst_h = mapa_u32((uint32_t)__cvta_generic_to_shared(&h_buf[0][octet * 10 + 2 * t4]), (uint32_t)g);
   const uint32_t dst_bar = mapa_u32(bar0, (uint32_t)g);
+  // clusters of more than 8 CTAs: lanes g < CS - 8 also feed CTA g + 8
+  const bool push2 = CS > 8 && g + 8 < CS;
+  const uint32_t dst2 = push2 ? (uint32_t)(g + 8) : (uint32_t)g;
+  const uint32_t dst_h2 = mapa_u32((uint32_t)__cvta_generic_to_shared(&h_buf[0][octet * 10 + 2 * t4]), dst2);
+  const uint32_t dst_bar2 = mapa_u32(bar0, dst2);
 
   // Input pre-activations (and the residual) stream from HBM / L2 through a per-warp ring of XD stages in
   // shared memory, filled with 16-byte cp.async XD - 1 steps ahead: per step and warp 8 clips x 3 gates x 8
@@ -459,9 +465,9 @@ __global__ void __launch_bounds__(G16<H>::NT) gru_cluster_f16_kernel(const GruAr
     if (c < 48) {
       const int cs = c / 6, gate = (c % 6) >> 1, half = c & 1, clip = b0 + cs;
       if (cs < BG && clip < a.batch) {
-        src[j] = reinterpret_cast<const char*>(a.gx + ((size_t)clip * T + t_first) * 6 * H + (size_t)dir * 3 * H +
-                                               gate * H + rank * HS + 8 * warp + 4 * half);
-        src_step[j] = (dir ? -1 : 1) * (ptrdiff_t)(6 * H * sizeof(float));
+        src[j] = reinterpret_cast<const char*>(
+            a.gx + f32blk_off(clip, dir * 3 * H + gate * H + rank * HS + 8 * warp + 4 * half, t_first, 6 * H, T));
+        src_step[j] = (dir ? -1 : 1) * (ptrdiff_t)(16 * sizeof(float));
         dst_off[j] = (uint32_t)((cs * G::XCLIP + gate * 8 + half * 4) * 4);
       }
     } else if (c < 56 && has_add) {
@@ -585,6 +591,10 @@ __global__ void __launch_bounds__(G16<H>::NT) gru_cluster_f16_kernel(const GruAr
                                      prmt(w[4], w[5], 0x7632), prmt(w[6], w[7], 0x7632));
         st_async_u4(dst_h + boff, lo4, dst_bar + 8u * (cur ^ 1));
         st_async_u4(dst_h + boff + 16u, hi4, dst_bar + 8u * (cur ^ 1));
+        if (push2) {
+          st_async_u4(dst_h2 + boff, lo4, dst_bar2 + 8u * (cur ^ 1));
+          st_async_u4(dst_h2 + boff + 16u, hi4, dst_bar2 + 8u * (cur ^ 1));
+        }
       }
     }
     GRU_STAMP(4)
@@ -599,11 +609,24 @@ __global__ void __launch_bounds__(G16<H>::NT) gru_cluster_f16_kernel(const GruAr
   cluster.sync();
 }
 
-template <int H, int BG, int NCH = 2, bool LEAN = true>
+template <int H, int BG, int CSZ = 8, int NCH = 2, bool LEAN = true>
 static int launch_gru_f16_bg(const GruArgs& a, cudaStream_t st, int* max_clusters) {
-  using G = G16<H>;
-  auto kern = gru_cluster_f16_kernel<H, BG, NCH, LEAN>;
+  using G = G16<H, CSZ>;
+  auto kern = gru_cluster_f16_kernel<H, BG, NCH, LEAN, CSZ>;
   const int clusters = 2 * ceil_div(a.batch, BG);
+  if (CSZ > 8) {   // non-portable cluster size: opt in once per device
+    static bool allowed[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !allowed[dev]) {
+      if (cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+        cudaGetLastError();
+        if (max_clusters) *max_clusters = 0;
+        return OU_ERR_UNSUPPORTED;
+      }
+      allowed[dev] = true;
+    }
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(clusters * G::CS);
   cfg.blockDim = dim3(G::NT);
@@ -637,23 +660,37 @@ static int launch_gru_f16_bg(const GruArgs& a, cudaStream_t st, int* max_cluster
   }
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a);
   if (e != cudaSuccess) {
-    set_error("ou_gru_bidir(f16): launch H=%d BG=%d: %s", H, BG, cudaGetErrorString(e));
+    set_error("ou_gru_bidir(f16): launch H=%d BG=%d CS=%d: %s", H, BG, CSZ, cudaGetErrorString(e));
     return OU_ERR_CUDA;
   }
   return check_launch("ou_gru_bidir(f16)");
 }
 
-// 8 clip slots per cluster.  Measured on B200: 4 slots (half the exchange packets, twice the clusters)
-// is no faster while every cluster has its SMs to itself and slower once two CTAs share an SM;
-// OU_GRU_BG=4 keeps the variant reachable for A/B runs.
+// 8 clip slots per cluster, 4 when the whole batch fits (half the exchange packets for the same cluster count:
+// H = 384, 4 clips: 1 054 -> 945 us).  Measured on B200: 4 slots with twice the clusters is no faster while
+// every cluster has its SMs to itself and slower once two CTAs share an SM; OU_GRU_BG=4 / 8 forces either.
+// H = 384 splits into 48 units = 6 warps per CTA over a cluster of 8, so two of the four schedulers issue the
+// HMMAs of two warps.  A cluster of 12 (non-portable size; 4 warps per CTA) was measured: 932 us with 8 slots
+// but 1 055 us with 4 (longer exchange), and its 24 CTAs do not fit the SMs the pipelined sampler reserves
+// for the recurrence -- kept behind OU_GRU_CS=12 for A/B runs only.
 template <int H>
 static int launch_gru_f16(const GruArgs& a, cudaStream_t st) {
-  static int forced = -1;
-  if (forced < 0) {
-    const char* e = getenv("OU_GRU_BG");
-    forced = e ? atoi(e) : 0;
+  static const int forced = [] { const char* e = getenv("OU_GRU_BG"); return e ? atoi(e) : 0; }();
+  static const int forced_cs = [] { const char* e = getenv("OU_GRU_CS"); return e ? atoi(e) : 0; }();
+  const bool use4 = forced == 4 || (forced == 0 && a.batch <= 4);
+  if constexpr (H == 384) {
+    const int clusters = 2 * ceil_div(a.batch, use4 ? 4 : 8);
+    if (forced_cs == 12 && clusters <= 6) {
+      static int fit[2] = {-1, -1};   // clusters of 12 that can be co-resident (per BG variant; -1: not asked yet)
+      int& f = fit[use4 ? 0 : 1];
+      if (f < 0) {
+        int n = 0;
+        const int rc = use4 ? launch_gru_f16_bg<H, 4, 12>(a, st, &n) : launch_gru_f16_bg<H, 8, 12>(a, st, &n);
+        f = rc == OU_OK ? n : 0;
+      }
+      if (f >= clusters) return use4 ? launch_gru_f16_bg<H, 4, 12>(a, st, nullptr) : launch_gru_f16_bg<H, 8, 12>(a, st, nullptr);
+    }
   }
-  const bool use4 = forced == 4;
   return use4 ? launch_gru_f16_bg<H, 4>(a, st, nullptr) : launch_gru_f16_bg<H, 8>(a, st, nullptr);
 }
 

@@ -11,14 +11,14 @@ from ctypes import (POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int
 from pathlib import Path
 
 from ..build import LIB as LIB_PATH
-OU_ABI_VERSION = 3
+OU_ABI_VERSION = 4
 
 
 class ConvParams(Structure):
     _fields_ = [
         ("x", c_void_p), ("w", c_void_p), ("w_tc", c_void_p), ("bias", c_void_p), ("add1", c_void_p),
         ("add2", c_void_p), ("gamma", c_void_p), ("beta", c_void_p), ("out", c_void_p),
-        ("out_f32_tm", c_void_p),
+        ("out_f32_blk", c_void_p),
         ("batch", c_int32), ("cin", c_int32), ("t_in", c_int32),
         ("s", c_int32), ("taps", c_int32), ("tap_off", c_int32),
         ("n", c_int32), ("cout", c_int32), ("up", c_int32),

@@ -36,7 +36,7 @@ SQRT_HALF = 1.0 / math.sqrt(2.0)
 
 @dataclass
 class BufSpec:
-    kind: str        # 'blocked' (bf16 [B][C/8][T][8]) | 'f32_tm' (fp32 [B][T][C]) | 'f32_bt' (fp32 [B][T])
+    kind: str        # 'blocked' (bf16 [B][C/8][T][8]) | 'f32_blk' (fp32 [B][C/16][T][16]) | 'f32_bt' (fp32 [B][T])
     channels: int
     length: int
 
@@ -278,7 +278,7 @@ def add_conv(prog, name, src, dst, fc, t_in, t_out=None, **kw):
     if dst_kind == "blocked":
         prog.buf(dst, "blocked", fc.cout, t_out)
     else:
-        prog.buf(dst, "f32_tm", fc.n, rows)
+        prog.buf(dst, "f32_blk", fc.n, rows)
     op = ConvOp(name, src, dst, fc, t_in, t_out, rows, **kw)
     op.flops_exec = 2.0 * prog.batch * rows * fc.n * fc.taps * fc.s * fc.cin
     if fc.taps == 3 and (fc.s > 1 or fc.up > 1):
@@ -365,7 +365,7 @@ def lower_gru(prog, gru, pfx, src, t, *, add_last=None, scale_last=1.0):
     h = src
     for layer in range(gru.num_layers):
         fc, w_hh, b_hh = fold_gru_layer(gru, layer)
-        gx, _ = add_conv(prog, f"{pfx}.l{layer}.xproj", h, f"{pfx}.gx", fc, t, dst_kind="f32_tm")
+        gx, _ = add_conv(prog, f"{pfx}.l{layer}.xproj", h, f"{pfx}.gx", fc, t, dst_kind="f32_blk")
         last = layer == gru.num_layers - 1
         dst = prog.buf(f"{pfx}.l{layer}.out", "blocked", 2 * gru.hidden_size, t)
         prog.ops.append(GruOp(f"{pfx}.l{layer}", gx, dst, w_hh, b_hh, gru.hidden_size, t,

@@ -126,8 +126,8 @@ def alloc_buffers(prog, device, skip=()):
             continue
         if spec.kind == "blocked":
             bufs[name] = alloc_blocked(b, spec.channels, spec.length, device)
-        elif spec.kind == "f32_tm":
-            bufs[name] = torch.empty(b, spec.length, spec.channels, dtype=torch.float32,
+        elif spec.kind == "f32_blk":     # fp32 [B][C/16][T][16] (GRU input pre-activations)
+            bufs[name] = torch.empty(b, spec.channels // 16, spec.length, 16, dtype=torch.float32,
                                      device=device)
         elif spec.kind == "f32_bt":
             bufs[name] = None   # supplied by the caller
@@ -203,9 +203,9 @@ def conv_params(op, bufs, batch, gamma=None, beta=None, film_bstride=0, max_ctas
     prm.gamma = gamma
     prm.beta = beta
     if op.dst_kind == "blocked":
-        prm.out, prm.out_f32_tm = bufs[op.dst].data_ptr(), None
+        prm.out, prm.out_f32_blk = bufs[op.dst].data_ptr(), None
     else:
-        prm.out, prm.out_f32_tm = None, bufs[op.dst].data_ptr()
+        prm.out, prm.out_f32_blk = None, bufs[op.dst].data_ptr()
     prm.batch, prm.cin, prm.t_in = batch, fc.cin, op.t_in
     prm.s, prm.taps, prm.tap_off = fc.s, fc.taps, fc.tap_off
     prm.n, prm.cout, prm.up = fc.n, fc.cout, fc.up
@@ -363,6 +363,18 @@ def unpack_blocked(xb):
     out = torch.empty(b, nblk * cb, t, dtype=torch.float32, device=xb.device)
     lib.check(lib.load().ou_unpack_blocked(_ptr(xb), _ptr(out), b, nblk * cb, t, _stream()))
     return out
+
+
+def pack_f32_blocked(x):
+    """(B, T, N) fp32 -> the blocked fp32 layout [B][N/16][T][16] of the GRU input pre-activations."""
+    b, t, n = x.shape
+    return x.float().reshape(b, t, n // 16, 16).permute(0, 2, 1, 3).contiguous()
+
+
+def unpack_f32_blocked(xb):
+    """blocked fp32 [B][N/16][T][16] -> (B, T, N)."""
+    b, nblk, t, cb = xb.shape
+    return xb.permute(0, 2, 1, 3).reshape(b, t, nblk * cb)
 
 
 # ------------------------------------------------------------------------------------ caching

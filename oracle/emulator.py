@@ -54,7 +54,7 @@ def run_conv(op, bufs, film=None, quant=False):
     w = _q(fc.w, quant)                                          # (N, taps, s*Cin)
     acc = F.conv1d(seg, w.permute(0, 2, 1).contiguous())         # (B, N, rows)
     acc = acc + fc.bias[None, :, None]
-    if op.dst_kind == "f32_tm":
+    if op.dst_kind == "f32_blk":   # logical view (B, rows, N); the device layout is blocked
         bufs[op.dst] = acc.transpose(1, 2).contiguous()          # (B, rows, N)
         return
     # depth-to-space: n = p*Cout + co -> t = j*up + p

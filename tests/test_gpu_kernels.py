@@ -77,7 +77,7 @@ def test_conv1d_vs_emulator(c):
     kw = {}
     t_out = c.get("t_out")
     if c.get("f32_tm"):
-        kw["dst_kind"] = "f32_tm"
+        kw["dst_kind"] = "f32_blk"
     dst, t_out = P.add_conv(prog, "c", "in", "out", fc, t, t_out, **kw)
     op = prog.ops[0]
     x = bf(torch.randn(B, cin, t, generator=g))
@@ -105,7 +105,7 @@ def test_conv1d_vs_emulator(c):
         exe.naive = naive
         exe.run(film=film_d, film_bstride=2 * cout)
         got = exe.bufs["out"]
-        got = got.float().cpu() if c.get("f32_tm") else R.unpack_blocked(got).cpu()
+        got = R.unpack_f32_blocked(got).cpu() if c.get("f32_tm") else R.unpack_blocked(got).cpu()
         assert got.shape == want.shape
         err = rel_rms(got, want)
         if err >= 3e-3:   # locate the damage: which clip / channel / time the worst element sits at
@@ -182,7 +182,10 @@ def test_conv_trunk_vs_emulator(c):
 
 
 @pytest.mark.parametrize("hidden,B,T,add", [(256, 5, 37, True), (128, 2, 20, False),
-                                            (384, 3, 25, True), (256, 32, 801, True)])
+                                            (384, 3, 25, True), (256, 32, 801, True),
+                                            # batch <= 4: 4 clip slots per cluster; H = 384: cluster of 12
+                                            (384, 4, 61, True), (384, 9, 33, False), (256, 3, 40, False),
+                                            (128, 4, 9, True), (256, 1, 1, True), (384, 2, 3, False)])
 def test_gru_vs_explicit(hidden, B, T, add):
     g = torch.Generator().manual_seed(7)
     H = hidden
@@ -198,7 +201,7 @@ def test_gru_vs_explicit(hidden, B, T, add):
     want = bufs["out"]
     out = R.alloc_blocked(B, 2 * H, T, DEV)
     # keep every device tensor referenced until the kernel has run (raw pointers are passed)
-    d_gx, d_w, d_b = gx.to(DEV), w_hh.to(DEV), b_hh.to(DEV)
+    d_gx, d_w, d_b = R.pack_f32_blocked(gx.to(DEV)), w_hh.to(DEV), b_hh.to(DEV)
     d_add = R.pack_blocked(addt.to(DEV)) if add else None
     lib.check(lib.load().ou_gru_bidir(R._ptr(d_gx), R._ptr(d_w), R._ptr(d_b), R._ptr(d_add), 0.7071,
                                       R._ptr(out), B, T, H, R._stream()))
