@@ -499,6 +499,7 @@ __global__ void __launch_bounds__(G16<H, CSZ>::NT) gru_cluster_f16_kernel(const 
 
   for (int step = 0; step < T; step++) {
     const int cur = step & 1;
+    __syncwarp();   // every lane has read its values of step - 1 out of the stage that is refilled now
     prefetch((step + G::XD - 1) % G::XD, step + G::XD - 1 < T);
     // arm the barrier that collects h_t (H units x BG clips x 2 B), then wait for h_{t-1}
     if (tid == 0 && step + 1 < T)

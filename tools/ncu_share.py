@@ -1,8 +1,8 @@
 """Per-kernel share of ONE enhance() at the bench size from an ncu launch list taken at a reduced
 diffusion-step count: the list of `bench.py --diffusion-steps 4` is split, per enhance() call, into the
-once-per-call part and the score steps (the launches of the captured sampler loop, 34 per step, right
+once-per-call part and the score steps (the launches of the captured sampler loop, 32 per step, right
 before `unpad_limit_kernel`), and the score part is scaled to 64 steps.
-    python tools/ncu_share.py gpurun_out/launches.csv [steps_in_list=4] [steps_target=64]"""
+    python tools/ncu_share.py gpurun_out/launches.csv [steps_in_list=4] [steps_target=64] [launches_per_step=32]"""
 import csv
 import sys
 from collections import OrderedDict
@@ -10,7 +10,7 @@ from collections import OrderedDict
 path = sys.argv[1]
 n_list = int(sys.argv[2]) if len(sys.argv) > 2 else 4
 n_target = int(sys.argv[3]) if len(sys.argv) > 3 else 64
-PER_STEP = 34
+PER_STEP = int(sys.argv[4]) if len(sys.argv) > 4 else 32
 with open(path, newline="") as f:
     lines = [l for l in f if not l.startswith("==")]
 launches = OrderedDict()

@@ -12,7 +12,7 @@ TOOLS=${*:-memcheck racecheck synccheck}
 CS=${COMPUTE_SANITIZER:-/usr/local/cuda/bin/compute-sanitizer}
 # one conv per role mix (resident / streamed weights, input PReLU transform, FiLM, strided, up), both trunk
 # widths, the GRU cluster kernel, signal kernels
-SUBSET='(test_conv1d_vs_emulator and (t300 or t1001 or t403 or t500 or t601 or t777 or t1000 or t3200)) or (test_conv_trunk_vs_emulator and (t1000 or t123 or t251 or t868 or t757)) or (test_gru_vs_explicit and not 801) or test_input_and_output_kernels or test_conv_resident_weights or test_alias_free_snake or test_mel_vs_oracle or test_pad_normalize'
+SUBSET='(test_conv1d_vs_emulator and (t300 or t1001 or t403 or t500 or t601 or t777 or t1000 or t3200)) or (test_conv_trunk_vs_emulator and (t1000 or t123 or t251 or t868 or t757)) or (test_conv_trunk_with_up_tail_vs_emulator and (t1000 or t123 or t366)) or (test_conv_trunk_with_output_tail_vs_emulator and (t1000 or t251 or t750 or t501)) or (test_gru_vs_explicit and not 801) or test_input_and_output_kernels or test_conv_resident_weights or test_alias_free_snake or test_mel_vs_oracle or test_pad_normalize'
 : > gpurun_out/sanitize_summary.txt
 for tool in $TOOLS; do
   log=gpurun_out/sanitize_${tool}.log
