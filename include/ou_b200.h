@@ -158,6 +158,16 @@ typedef struct ou_trunk_params {
   const float* out_noise;   /* fp32 (B, t) or NULL                                                      */
   float* out_xout;          /* fp32 (B, t)                                                              */
   float* out_net;           /* fp32 (B, t) or NULL                                                      */
+  /* Optional down tail (ABI v4, channels = 32 only): the block's own anti-aliased stride-2 rate-change conv
+   * (blocks.py:205-227,400-404: PReLU -> binomial low-pass -> Conv1d(k = 2, stride 2), folded to 3 row taps of
+   * 2 samples = 6 sample taps) on the block output while it is still in shared memory:
+   *   dn_out[b][n][j] = dn_bias[n] + sum_{m<6} sum_c dn_w[m][n][c] * PReLU_dn(v)[c][2 j - 2 + m]
+   * `out` (the block output, the decoder's skip connection) is still written.                            */
+  const void* dn_w;         /* act [6][2C][C]: sample tap m, output channel n, input channel c, or NULL  */
+  const float* dn_bias;     /* fp32 [2C]                                                                 */
+  void* dn_out;             /* blocked act (B, 2C, dn_t_out)                                             */
+  int32_t dn_t_out;         /* ceil(t / 2)                                                               */
+  float dn_prelu_in;
 } ou_trunk_params;
 
 int ou_conv_trunk(const ou_trunk_params* p, void* stream);

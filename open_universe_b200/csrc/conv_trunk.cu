@@ -56,6 +56,7 @@ struct TrunkArgs {
   int items_per_clip, total_items;
   int x_box_rows, x_boxes;
   uint32_t idesc, desc_hi;
+  uint32_t idesc_dn;    // down tail: N = 2C
 };
 
 __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
@@ -72,10 +73,11 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
   return ok != 0;
 }
 
-// TAIL: 0 none; 1 the next block's x2 up conv (C = 64); 2 the network's output conv + EDM / SDE update (C = 32)
+// TAIL: 0 none; 1 the next block's x2 up conv (C = 64); 2 the network's output conv + EDM / SDE update (C = 32);
+// 3 the block's own stride-2 anti-aliased down conv (C = 32)
 template <int C, int S = 3, int TAIL = 0>
 struct Geo {
-  static constexpr bool UP = TAIL == 1, OUTC = TAIL == 2;
+  static constexpr bool UP = TAIL == 1, OUTC = TAIL == 2, DOWN = TAIL == 3;
   static constexpr int W = 64 / C;                     // 128-row sub-tiles per item
   static constexpr int ROWB = C * 2;                   // bytes per activation row
   static constexpr int CH = C / 8;                     // 16-byte chunks per row
@@ -86,9 +88,14 @@ struct Geo {
   static constexpr uint32_t W_TAP_BYTES = (uint32_t)(C * ROWB);
   static constexpr uint32_t SWZ_MASK = ROWB == 128 ? 7u : 3u;
   static constexpr int TAPS_UP = UP ? 3 : 0;                   // the fused up conv of the next block (tail)
-  static constexpr int ITEM_VALID = TAIL ? VALID - 2 : VALID;  // rows an item contributes to the final output
-  static constexpr uint32_t W_BYTES = (NTAPS + TAPS_UP) * W_TAP_BYTES;
-  static constexpr uint32_t TAIL_BYTES = 8u * (1 + 5 * S) + 32u + 4u * (S * 2 * C + (OUTC ? 5 : 3) * C);   // barriers, TMEM slot, coefficients
+  static constexpr int HALO = DOWN ? 2 : (TAIL ? 1 : 0);       // block-output rows an item recomputes on each side
+  static constexpr int ITEM_VALID = VALID - 2 * HALO;          // rows an item contributes to the final output
+  // down tail: 6 sample taps of [2C output channels][C] next to the block's own taps; the block output is kept
+  // de-interleaved in Cb: even time steps from row 0, odd ones from row DN_ODD (each 126 rows + 2 of tap reach)
+  static constexpr int DN_TAPS = 6, DN_ODD = 64 * W + 4;
+  static constexpr uint32_t DN_TAP_BYTES = 2u * W_TAP_BYTES;
+  static constexpr uint32_t W_BYTES = (NTAPS + TAPS_UP) * W_TAP_BYTES + (DOWN ? DN_TAPS * DN_TAP_BYTES : 0u);
+  static constexpr uint32_t TAIL_BYTES = 8u * (1 + 5 * S) + 32u + 4u * (S * 2 * C + (OUTC ? 5 : (DOWN ? 4 : 3)) * C);   // barriers, TMEM slot, coefficients
   // no alignment slack: the dynamic shared window of a kernel without static shared memory starts 1024-byte
   // aligned (checked at run time) -- with it, 4 slots do not fit next to the 90 KB of weights at C = 64
   static constexpr size_t SMEM = W_BYTES + (size_t)S * 2 * BUF_BYTES + TAIL_BYTES;
@@ -141,7 +148,7 @@ __device__ __forceinline__ void slot_role(const TrunkArgs& a, const Smem& sm, ui
                                           int n_items, const CUtensorMap* tm_x, const CUtensorMap* tm_sc,
                                           int warp, int lane) {
   using G = Geo<C, S, TAIL>;
-  constexpr bool UP = TAIL == 1, OUTC = TAIL == 2;
+  constexpr bool UP = TAIL == 1, OUTC = TAIL == 2, DOWN = TAIL == 3;
   const ou_trunk_params& p = a.p;
   const int quarter = warp & 3;                 // TMEM lane quarter this warp may read
   const int wis = warp % WPS;                   // warp index inside the slot's warpgroup
@@ -173,6 +180,8 @@ __device__ __forceinline__ void slot_role(const TrunkArgs& a, const Smem& sm, ui
   const float s3 = p.scale3;
   uint32_t a_in_hi, a_in_lo;
   split_slope(slope_in, a_in_hi, a_in_lo);
+  uint32_t a_dn_hi = 0, a_dn_lo = 0;
+  if (DOWN) split_slope(p.dn_prelu_in, a_dn_hi, a_dn_lo);
   const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(slot * SLOT_COLS);
   act_t* outp = (act_t*)p.out;
 
@@ -180,7 +189,7 @@ __device__ __forceinline__ void slot_role(const TrunkArgs& a, const Smem& sm, ui
     const int item = (int)blockIdx.x + (int)gridDim.x * n;
     b = item / a.items_per_clip;
     // with the up tail, output row r of an item is low-rate index t0 + 1 + r (one row of halo on each side)
-    t0 = (item - b * a.items_per_clip) * G::ITEM_VALID - (TAIL ? 1 : 0);
+    t0 = (item - b * a.items_per_clip) * G::ITEM_VALID - G::HALO;
   };
   auto load_x = [&](int n) {
     int b, t0;
@@ -444,7 +453,17 @@ __device__ __forceinline__ void slot_role(const TrunkArgs& a, const Smem& sm, ui
           o.w[h * 4 + 2 * k + 1] = f2_to_act2(v23.x, v23.y);
         }
       }
-      if (TAIL) {
+      if (DOWN) {
+        // the block output goes to HBM (the decoder's skip connection; each row by the one item that owns it) AND,
+        // through the down conv's input PReLU, into Cb as the tail's operand: even time steps from row 0, odd
+        // ones from row DN_ODD, zero outside the clip (the low-pass's "same" padding)
+        if (valid && i >= G::HALO && i < G::HALO + G::ITEM_VALID) stg_v8(dst + col0 + cc * 16, o);
+        const int drow = (i >> 1) + ((i & 1) ? G::DN_ODD : 0);
+        const uint32_t d0 = swz<C>(Cb, (uint32_t)(drow * G::ROWB + (ch0 + 2 * cc) * 16));
+        const uint32_t d1 = swz<C>(Cb, (uint32_t)(drow * G::ROWB + (ch0 + 2 * cc + 1) * 16));
+        sts_u4(d0, valid ? prelu_act8(make_uint4(o.w[0], o.w[1], o.w[2], o.w[3]), a_dn_hi, a_dn_lo) : zero4);
+        sts_u4(d1, valid ? prelu_act8(make_uint4(o.w[4], o.w[5], o.w[6], o.w[7]), a_dn_hi, a_dn_lo) : zero4);
+      } else if (TAIL) {
         // operand rows of the tail conv (zero outside the clip: its "same" padding)
         const uint32_t d0 = swz<C>(Cb, (uint32_t)(i * G::ROWB + (ch0 + 2 * cc) * 16));
         const uint32_t d1 = swz<C>(Cb, (uint32_t)(i * G::ROWB + (ch0 + 2 * cc + 1) * 16));
@@ -511,6 +530,59 @@ __device__ __forceinline__ void slot_role(const TrunkArgs& a, const Smem& sm, ui
       }
       TRUNK_STAMP(15)
     }
+    if (DOWN) {
+      // ---- stage 4 (tail): the block's stride-2 down conv on the de-interleaved tile: output row jj of the item
+      // is low-rate step (t0 + 2) / 2 + jj and reads block-output rows 2 jj .. 2 jj + 5 (sample taps m = 0..5):
+      // even m from the even tile at row jj + m / 2, odd m from the odd tile at row jj + (m - 1) / 2
+      static_assert(!DOWN || (C == 32 && WPS == 4 && SLOT_COLS >= 2 * C), "the down tail is built for C = 32");
+      wg_handover();
+      if (issuer_warp) {
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t wdn = sm.w + (uint32_t)NTAPS * G::W_TAP_BYTES;
+#pragma unroll
+          for (int m = 0; m < G::DN_TAPS; m++) {
+            const int arow = (m >> 1) + ((m & 1) ? G::DN_ODD : 0);
+            const uint32_t a_lo = (((Cb + (uint32_t)(arow * G::ROWB)) >> 4) & 0x3FFFu) | (1u << 16);
+            const uint32_t b_lo = (((wdn + (uint32_t)m * G::DN_TAP_BYTES) >> 4) & 0x3FFFu) | (1u << 16);
+#pragma unroll
+            for (int kk = 0; kk < G::K16; kk++)
+              umma_f16(d_tmem, hi64 | (a_lo + 2 * kk), hi64 | (b_lo + 2 * kk), a.idesc_dn, (m | kk) != 0 ? 1u : 0u);
+          }
+          umma_commit(bar_acc);
+        }
+        __syncwarp();
+      }
+      const int j = ((t0 + G::HALO) >> 1) + row;       // low-rate index of this thread's output row
+      const bool ok = row < G::ITEM_VALID / 2 && j < p.dn_t_out;
+      act_t* dn_out = (act_t*)p.dn_out + ((size_t)b * p.dn_t_out + j) * (2 * C);
+      mbar_wait(bar_acc, ph_acc);
+      ph_acc ^= 1;
+      tc_fence_after();
+      if (HAS_SC && leader && has_next) load_sc(n + S);   // the tail's MMAs are done with Cb
+      tmem_ld16(taddr, rbuf[0]);
+#pragma unroll
+      for (int q = 0; q < 2 * C / 16; q++) {
+        float4 kk[4];
+#pragma unroll
+        for (int jv = 0; jv < 4; jv++) kk[jv] = lds_f4(sm.coef_up + 4u * (q * 16 + jv * 4));
+        tmem_ld_wait();
+        if (q + 1 < 2 * C / 16) tmem_ld16(taddr + (uint32_t)((q + 1) * 16), rbuf[(q + 1) & 1]);
+        const uint32_t(&r)[16] = rbuf[q & 1];
+        if (ok) {
+          U8 o;
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const float2 a01 = fadd2(u2_as_f2(r[4 * k], r[4 * k + 1]), make_float2(kk[k].x, kk[k].y));
+            const float2 a23 = fadd2(u2_as_f2(r[4 * k + 2], r[4 * k + 3]), make_float2(kk[k].z, kk[k].w));
+            o.w[2 * k] = f2_to_act2(a01.x, a01.y);
+            o.w[2 * k + 1] = f2_to_act2(a23.x, a23.y);
+          }
+          stg_v8(dn_out + 16 * q, o);
+        }
+      }
+      TRUNK_STAMP(15)
+    }
     if (OUTC) {
       // ---- tail: the network's output conv (C -> 1, k = 3) on the block output just written to Cb, fused with
       // the EDM mix and the reverse-SDE update (ou_output_sde): thread = output time step t0 + 1 + r
@@ -572,7 +644,7 @@ trunk_kernel(const TrunkArgs a, const __grid_constant__ CUtensorMap tm_x,
              const __grid_constant__ CUtensorMap tm_w2, const __grid_constant__ CUtensorMap tm_w3,
              const __grid_constant__ CUtensorMap tm_wup) {
   using G = Geo<C, S, TAIL>;
-  constexpr bool UP = TAIL == 1, OUTC = TAIL == 2;
+  constexpr bool UP = TAIL == 1, OUTC = TAIL == 2, DOWN = TAIL == 3;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const ou_trunk_params& p = a.p;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -615,6 +687,7 @@ trunk_kernel(const TrunkArgs a, const __grid_constant__ CUtensorMap tm_x,
     sts_f1(sm.coef3 + 4u * threadIdx.x, p.scale3 * p.b3[threadIdx.x]);
     if (UP) sts_f1(sm.coef_up + 4u * threadIdx.x, p.up_scale * (p.up_bias ? p.up_bias[threadIdx.x] : 0.f));
   }
+  if (DOWN && threadIdx.x < 2 * C) sts_f1(sm.coef_up + 4u * threadIdx.x, p.dn_bias ? p.dn_bias[threadIdx.x] : 0.f);
   // output tail: the C x 3 fp32 weights of the output conv, tap-major [k][C]
   if (OUTC && threadIdx.x < 3 * C) sts_f1(sm.coef_up + 4u * threadIdx.x, p.out_w[threadIdx.x]);
   constexpr uint32_t TMEM_COLS = S * SLOT_COLS <= 256 ? 256u : 512u;
@@ -637,6 +710,9 @@ trunk_kernel(const TrunkArgs a, const __grid_constant__ CUtensorMap tm_x,
       tma_load_3d(sm.w + (TAPS1 + TAPS2 + q) * G::W_TAP_BYTES, &tm_w3, 0, 0, q, sm.w_full);
     for (int q = 0; q < G::TAPS_UP; q++)
       tma_load_3d(sm.w + (NTAPS + q) * G::W_TAP_BYTES, &tm_wup, 0, 0, q, sm.w_full);
+    if (DOWN)
+      for (int m = 0; m < G::DN_TAPS; m++)
+        tma_load_3d(sm.w + NTAPS * G::W_TAP_BYTES + m * G::DN_TAP_BYTES, &tm_wup, 0, 0, m, sm.w_full);
   }
   __syncwarp();
   {
@@ -697,7 +773,7 @@ static int encode3(CUtensorMap* tm, const void* base, int c, uint64_t d1, uint64
 template <int C, int S, int WPS, int TAIL = 0>
 static int launch_cfg(const ou_trunk_params* p, cudaStream_t st) {
   using G = Geo<C, S, TAIL>;
-  constexpr bool UP = TAIL == 1;
+  constexpr bool UP = TAIL == 1, DOWN = TAIL == 3;
   static_assert(G::SMEM <= 232448, "trunk_kernel: shared-memory budget exceeds the 227 KB a CTA may opt into");
   TrunkArgs a;
   a.trace = ou::tc::g_trace;
@@ -710,6 +786,7 @@ static int launch_cfg(const ou_trunk_params* p, cudaStream_t st) {
   while ((G::XPAD / a.x_boxes) > 256 || G::XPAD % a.x_boxes || (G::XPAD / a.x_boxes) % 8) a.x_boxes++;
   a.x_box_rows = G::XPAD / a.x_boxes;
   a.idesc = (1u << 4) | ((uint32_t)OU_ACT_IS_BF16 << 7) | ((uint32_t)OU_ACT_IS_BF16 << 10) | ((uint32_t)(C >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  a.idesc_dn = (1u << 4) | ((uint32_t)OU_ACT_IS_BF16 << 7) | ((uint32_t)OU_ACT_IS_BF16 << 10) | ((uint32_t)((2 * C) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   const uint32_t sbo = 8u * G::ROWB;
   const uint32_t layout = G::ROWB == 128 ? 2u : 4u;
   a.desc_hi = ((sbo >> 4) & 0x3FFFu) | (1u << (46 - 32)) | (layout << (61 - 32));
@@ -725,7 +802,10 @@ static int launch_cfg(const ou_trunk_params* p, cudaStream_t st) {
   if ((rc = encode3(&tm_w1, p->w1, C, (uint64_t)C, TAPS1, C, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, "w1"))) return rc;
   if ((rc = encode3(&tm_w2, p->w2, C, (uint64_t)C, TAPS2, C, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, "w2"))) return rc;
   if ((rc = encode3(&tm_w3, p->w3, C, (uint64_t)C, TAPS3, C, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, "w3"))) return rc;
-  if ((rc = encode3(&tm_wup, UP ? p->up_w : p->w3, C, (uint64_t)C, 3, C, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, "w_up")))
+  if (DOWN) {
+    if ((rc = encode3(&tm_wup, p->dn_w, C, (uint64_t)(2 * C), G::DN_TAPS, 2 * C, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, "w_dn")))
+      return rc;
+  } else if ((rc = encode3(&tm_wup, UP ? p->up_w : p->w3, C, (uint64_t)C, 3, C, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, "w_up")))
     return rc;
 
   // FASTP: every epilogue PReLU slope in [0, 1] -> PReLU(x) = max(x, a x)
@@ -757,6 +837,7 @@ static int launch_c(const ou_trunk_params* p, cudaStream_t st) {
   }
   if constexpr (C == 32) {
     if (p->out_w != nullptr) return launch_cfg<C, 4, 4, 2>(p, st);   // fused output conv + SDE update
+    if (p->dn_w != nullptr) return launch_cfg<C, 4, 4, 3>(p, st);    // fused stride-2 down conv
     // 4 slots fit next to the 22 KB of weights at C = 32 (16 warps -> 128 registers): measured 213 / 237 us
     // against 233 / 245 us with 3 slots (enc / dec, cfg-2 sizes); OU_TRUNK_S32=3 for A/B runs
     static const int s32 = [] { const char* e = getenv("OU_TRUNK_S32"); return e ? atoi(e) : 4; }();
@@ -779,6 +860,11 @@ extern "C" int ou_conv_trunk(const ou_trunk_params* p, void* stream) {
                                     p->up_t_out <= 2 * p->t && !p->has_prelu_out && !p->has_prelu_out2),
              "ou_conv_trunk: the fused up-conv tail needs C = 64, an output buffer of at most 2 t samples and no "
              "output PReLU on the block");
+  OU_REQUIRE(p->dn_w == nullptr || (p->channels == 32 && p->up_w == nullptr && p->out_w == nullptr && p->out != nullptr &&
+                                    p->dn_out != nullptr && p->dn_t_out == (p->t + 1) / 2 && !p->has_prelu_out &&
+                                    !p->has_prelu_out2),
+             "ou_conv_trunk: the fused down conv needs C = 32, no other tail, the block output buffer, an output of "
+             "ceil(t / 2) steps and no output PReLU on the block");
   OU_REQUIRE(p->batch > 0 && p->t > 0, "ou_conv_trunk: empty problem");
   OU_REQUIRE((p->gamma == nullptr) == (p->beta == nullptr), "ou_conv_trunk: gamma / beta must come together");
   if ((p->channels != 32 && p->channels != 64) || p->taps1 != ou::trunk::TAPS1 || p->taps2 != ou::trunk::TAPS2 ||

@@ -78,13 +78,16 @@ class TrunkOp:
     tail: Optional[ConvOp] = None
     # the network's output conv + EDM / SDE update fused behind conv3 (C = 32 only, ``OutputOp``)
     tail_out: Optional[object] = None
+    # the block's own anti-aliased stride-2 down conv fused behind conv3 (C = 32 only): the block output is still
+    # written (decoder skip connection) but not read back
+    tail_dn: Optional[ConvOp] = None
 
     def all_parts(self):
-        return (self.parts + ([self.tail] if self.tail is not None else [])
-                + ([self.tail_out] if self.tail_out is not None else []))
+        return (self.conv_parts() + ([self.tail_out] if self.tail_out is not None else []))
 
     def conv_parts(self):
-        return self.parts + ([self.tail] if self.tail is not None else [])
+        return (self.parts + ([self.tail] if self.tail is not None else [])
+                + ([self.tail_dn] if self.tail_dn is not None else []))
 
     @property
     def flops_exec(self):
@@ -150,6 +153,31 @@ def fuse_up_tail(prog):
     if not ok:
         return False
     tr.tail = up
+    del prog.ops[-1]
+    return True
+
+
+# OU_TRUNK_DOWN_TAIL=0 keeps enc.0.down as a separate ou_conv1d launch (A/B runs)
+TRUNK_DOWN_TAIL = _os.environ.get("OU_TRUNK_DOWN_TAIL", "1") != "0"
+
+
+def fuse_down_tail(prog):
+    """If the last op is the anti-aliased stride-2 down conv (32 -> 64 channels, 3 folded row taps) reading the
+    output of the 32-channel TrunkOp right before it (enc.0.trunk -> enc.0.down), fold it into that trunk launch."""
+    if not (TRUNK_TAIL and TRUNK_DOWN_TAIL) or len(prog.ops) < 2:
+        return False
+    dn, tr = prog.ops[-1], prog.ops[-2]
+    if not (isinstance(dn, ConvOp) and isinstance(tr, TrunkOp) and tr.tail is None and tr.tail_out is None
+            and tr.tail_dn is None):
+        return False
+    c3, fc = tr.parts[2], dn.fc
+    if not (fc.cin == 32 and fc.cout == 64 and fc.s == 2 and fc.up == 1 and fc.taps == 3 and fc.tap_off == -1
+            and dn.src == c3.dst and dn.add1 is None and dn.add2 is None and dn.film_off is None
+            and dn.prelu_out is None and dn.prelu_out2 is None and dn.dst_kind == "blocked"
+            and c3.prelu_out is None and c3.prelu_out2 is None and dn.t_in == c3.t_out
+            and dn.t_out == (dn.t_in + 1) // 2):
+        return False
+    tr.tail_dn = dn
     del prog.ops[-1]
     return True
 
@@ -345,6 +373,8 @@ def lower_conv_block(prog, blk, pfx, src, t_in, *, film_linear=None, input_cond=
     if is_down:
         fcr = fold.fold_prelu_conv(blk.rate_change_conv)
         out, t_out = add_conv(prog, pfx + ".down", v, pfx + ".out", fcr, t)
+        if not raw_cond_out:
+            fuse_down_tail(prog)
         return out, t_out, v, cond_out
     return v, t, v, cond_out
 
@@ -549,6 +579,9 @@ def op_bytes(op, batch, elem=2):
         w = sum(p.fc.w.numel() for p in op.conv_parts()) * elem
         if op.tail_out is not None:  # x (+ sc) in; signal x, noise in and x out (fp32); the block output stays on chip
             return elem * batch * c * t * (1 + (c1.add1 is not None)) + 3 * 4 * batch * t + w
+        if op.tail_dn is not None:   # x (+ sc) in; block output (skip connection) and the down conv's output out
+            dn = op.tail_dn
+            return (elem * batch * c * t * (2 + (c1.add1 is not None)) + elem * batch * dn.fc.cout * dn.t_out + w)
         if op.tail is not None:      # x (+ sc) in; the up conv's skip in and output out; the block output stays on chip
             up = op.tail
             return (elem * batch * c * t * (1 + (c1.add1 is not None))

@@ -263,6 +263,14 @@ def trunk_params(op, bufs, batch, film=None, film_bstride=0, max_ctas=0, coef=No
         prm.up_skip = bufs[up.add1].data_ptr() if up.add1 else None
         prm.up_out = bufs[up.dst].data_ptr()
         prm.up_t_out, prm.up_scale, prm.up_prelu_in = up.t_out, up.scale1, up.fc.prelu_in
+    if op.tail_dn is not None:
+        dn = op.tail_dn
+        if dn.packed["npad"] != dn.fc.cout:
+            raise ValueError("down tail: padded output width")
+        # w_tc of the 32 -> 64, s = 2, 3-tap conv is [3 taps][2 phases][64][32] = sample tap m = 2 q + r major
+        prm.dn_w, prm.dn_bias = dn.packed["w_tc"].data_ptr(), dn.packed["bias"].data_ptr()
+        prm.dn_out, prm.dn_t_out = bufs[dn.dst].data_ptr(), dn.t_out
+        prm.dn_prelu_in = 1.0 if dn.fc.prelu_in is None else dn.fc.prelu_in
     if op.tail_out is not None:
         oc = op.tail_out
         prm.out_w, prm.out_bias = oc.packed["w_kc"].data_ptr(), oc.bias

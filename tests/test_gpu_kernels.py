@@ -506,3 +506,61 @@ def test_conv_trunk_with_output_tail_vs_emulator(c):
     if coef is not None:
         assert rel_rms(xnew, want_x) < 3e-3 and rel_rms(xnew, xnew_split) < 3e-3
     # without the SDE arguments the raw output is still written and x_out is left alone
+
+
+DOWN_TAIL_CASES = [
+    dict(t=1000, B=2, film=True),
+    dict(t=123, B=1, film=False),             # one partial item
+    dict(t=248 * 3, B=2, film=False),         # exact multiple of the item
+    dict(t=248 * 2 + 2, B=1, film=True),      # one row pair into a third item
+    dict(t=128160, B=2, film=True),           # many items per CTA
+]
+
+
+@pytest.mark.parametrize("c", DOWN_TAIL_CASES, ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items()))
+def test_conv_trunk_with_down_tail_vs_emulator(c):
+    """ou_conv_trunk with the block's own anti-aliased stride-2 down conv (32 -> 64 channels) fused behind conv3:
+    block output (skip connection) AND down-conv output against the emulator and against the four separate
+    launches."""
+    g = torch.Generator().manual_seed(4242)
+    B, C, t = c["B"], 32, c["t"]
+    prog = P.Program(B)
+    prog.buf("in", "blocked", C, t)
+    inputs = {"in": bf(torch.randn(B, C, t, generator=g))}
+    P.add_conv(prog, "conv1", "in", "c1", rand_fc(g, C, C, taps=5, tap_off=-2, prelu_in=0.2), t,
+               film_off=0 if c["film"] else None, prelu_out=0.15)
+    P.add_conv(prog, "conv2", "c1", "c2", rand_fc(g, C, C, taps=3, tap_off=-1), t, prelu_out=0.3)
+    P.add_conv(prog, "conv3", "c2", "v", rand_fc(g, C, C, taps=3, tap_off=-1), t, add1="in", scale1=0.7071)
+    assert P.fuse_trunk(prog, "trunk")
+    P.add_conv(prog, "down", "v", "h", rand_fc(g, C, 2 * C, s=2, taps=3, tap_off=-1, prelu_in=0.25), t)
+    assert P.fuse_down_tail(prog) and len(prog.ops) == 1 and prog.ops[0].tail_dn is not None
+    film = torch.randn(B, 2 * C, generator=g) if c["film"] else None
+    bufs, _, _ = E.run_program(prog, inputs, film=film, quant=True)
+    want_v, want_h = bufs["v"], bufs["h"]
+
+    exe = R.Executor(prog, DEV, external=list(inputs))
+    for k, v in inputs.items():
+        exe.bufs[k] = R.pack_blocked(v.to(DEV))
+    film_d = film.to(DEV).contiguous() if film is not None else None
+    exe.bufs["h"].fill_(7.0)
+    exe.bufs["v"].fill_(7.0)
+    n0 = lib.launch_count()
+    exe.run(film=film_d, film_bstride=2 * C)
+    assert lib.launch_count() - n0 == 1
+    got_v, got_h = R.unpack_blocked(exe.bufs["v"]).cpu(), R.unpack_blocked(exe.bufs["h"]).cpu()
+    R.USE_TRUNK = False
+    try:
+        exe.bufs["h"].zero_()
+        n0 = lib.launch_count()
+        exe.run(film=film_d, film_bstride=2 * C)
+        assert lib.launch_count() - n0 == 4
+        split_h = R.unpack_blocked(exe.bufs["h"]).cpu()
+    finally:
+        R.USE_TRUNK = True
+    assert got_h.shape == want_h.shape and torch.isfinite(got_h).all() and torch.isfinite(got_v).all()
+    assert rel_rms(got_v, want_v) < 3e-3
+    err, err_split = rel_rms(got_h, want_h), rel_rms(got_h, split_h)
+    if err >= 3e-3 or err_split >= 3e-3:
+        bad = ((got_h - want_h).abs() > 0.05 * want_h.abs().max()).float()
+        raise AssertionError(f"rel_rms={err:.4f} vs split {err_split:.4f} bad_fraction={bad.mean():.5f} "
+                             f"bad rows (time) {bad.amax(dim=(0, 1)).nonzero().flatten()[:24].tolist()}")
