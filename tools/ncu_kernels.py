@@ -46,7 +46,9 @@ def conv(name, cin, cout, s, up, taps, t, prelu, add1):
     print(f"{name:34s} {us:8.1f} us  {op.flops_exec / us / 1e6:7.1f} TFLOP/s executed  {byts / us / 1e3:6.0f} GB/s algorithmic")
 
 
-def trunk(name, c, t, sc):
+def trunk(name, c, t, sc, tail=None):
+    """tail: None | 'up' (C = 64: next block's x2 up conv + skip) | 'down' (C = 32: own stride-2 down conv) |
+    'out' (C = 32: output conv + EDM / SDE update)."""
     def fc(taps, prelu):
         return FoldedConv(torch.randn(c, taps, c, generator=g) / math.sqrt(taps * c), torch.zeros(c), c, c, 1, 1,
                           taps, -(taps // 2), prelu)
@@ -59,13 +61,33 @@ def trunk(name, c, t, sc):
     P.add_conv(prog, "conv2", "c1", "c2", fc(3, None), t, prelu_out=0.25)
     P.add_conv(prog, "conv3", "c2", "v", fc(3, None), t, add1="in", scale1=0.7071)
     assert P.fuse_trunk(prog, "trunk")
+    kw = {}
+    if tail == "up":
+        prog.buf("skip", "blocked", c // 2, 2 * t)
+        fu = FoldedConv(torch.randn(2 * (c // 2), 3, c, generator=g) / math.sqrt(3 * c), torch.zeros(c), c, c // 2, 1, 2,
+                        3, -1, 0.25)
+        P.add_conv(prog, "up", "v", "h", fu, t, 2 * t, add1="skip", scale1=0.7071)
+        assert P.fuse_up_tail(prog)
+    elif tail == "down":
+        fd = FoldedConv(torch.randn(2 * c, 3, 2 * c, generator=g) / math.sqrt(6 * c), torch.zeros(2 * c), c, 2 * c, 2, 1,
+                        3, -1, 0.25)
+        P.add_conv(prog, "down", "v", "h", fd, t)
+        assert P.fuse_down_tail(prog)
+    elif tail == "out":
+        prog.ops.append(P.OutputOp("output_conv", "v", torch.randn(c, 3, generator=g) / 10, 0.0, t, t))
+        assert P.fuse_out_tail(prog)
+        kw = dict(coef=torch.randn(B, 3, device="cuda"), noise=torch.randn(B, 1, t, device="cuda"),
+                  xout=torch.empty(B, 1, t, device="cuda"))
     exe = R.Executor(prog, "cuda")
     exe.bufs["in"].normal_()
-    if sc:
-        exe.bufs["sc"].normal_()
+    for k in ("sc", "skip"):
+        if k in exe.bufs and exe.bufs[k] is not None:
+            exe.bufs[k].normal_()
+    if tail == "out":
+        exe.bufs["x"] = torch.randn(B, 1, t, device="cuda")
     film = torch.randn(1, 2 * c, device="cuda")
-    us = timed(lambda: exe.run(film=film, film_bstride=0))
-    byts = 2.0 * B * c * t * (3 if sc else 2)
+    us = timed(lambda: exe.run(film=film, film_bstride=0, **kw))
+    byts = P.op_bytes(prog.ops[0], B)
     print(f"{name:34s} {us:8.1f} us  {prog.ops[0].flops_exec / us / 1e6:7.1f} TFLOP/s executed  {byts / us / 1e3:6.0f} GB/s algorithmic")
 
 
@@ -82,7 +104,9 @@ def gru(H=256, T=801):
 
 conv("L2 conv1 C128 k5 prelu", 128, 128, 1, 1, 5, 16020, 0.25, False)
 conv("L3 conv1 C256 k5 prelu", 256, 256, 1, 1, 5, 4005, 0.25, False)
-conv("dec.4.up 64->32 x2 +skip", 64, 32, 1, 2, 3, 64080, 0.25, True)
+conv("dec.3.up 128->64 x4 +skip", 128, 64, 1, 4, 3, 16020, 0.25, True)
 trunk("enc.1 trunk C64", 64, 64080, False)
-trunk("dec.4 trunk C32 +sc", 32, 128160, True)
+trunk("dec.3 trunk C64 +sc +up tail", 64, 64080, True, "up")
+trunk("enc.0 trunk C32 +down tail", 32, 128160, False, "down")
+trunk("dec.4 trunk C32 +sc +out tail", 32, 128160, True, "out")
 gru()
