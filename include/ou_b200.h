@@ -168,6 +168,10 @@ typedef struct ou_trunk_params {
   void* dn_out;             /* blocked act (B, 2C, dn_t_out)                                             */
   int32_t dn_t_out;         /* ceil(t / 2)                                                               */
   float dn_prelu_in;
+  /* Row taps the up / down tail actually carries: 3 (anti-aliased, the low-pass folded in) or 1 (plain k = s
+   * conv of UNIVERSE (original): up_w / dn_w keep the 3-tap frame with the conv in the middle tap, the outer
+   * taps are neither read nor multiplied); 0 means 3.                                                     */
+  int32_t up_taps, dn_taps;
 } ou_trunk_params;
 
 int ou_conv_trunk(const ou_trunk_params* p, void* stream);

@@ -479,7 +479,19 @@ __device__ __forceinline__ void slot_role(const TrunkArgs& a, const Smem& sm, ui
       wg_handover();
       if (issuer_warp) {
         tc_fence_after();
-        issue_stage<C, 3>(Cb, sm.w + (TAPS1 + TAPS2 + TAPS3) * G::W_TAP_BYTES, d_tmem, bar_acc, idesc, hi64);
+        if (p.up_taps == 1) {   // plain k = s up conv: the middle tap of the 3-tap frame only
+          if (elect_one()) {
+            const uint32_t a_lo = (((Cb + (uint32_t)G::ROWB) >> 4) & 0x3FFFu) | (1u << 16);
+            const uint32_t b_lo = (((sm.w + (uint32_t)(NTAPS + 1) * G::W_TAP_BYTES) >> 4) & 0x3FFFu) | (1u << 16);
+#pragma unroll
+            for (int kk = 0; kk < G::K16; kk++)
+              umma_f16(d_tmem, hi64 | (a_lo + 2 * kk), hi64 | (b_lo + 2 * kk), idesc, kk != 0 ? 1u : 0u);
+            umma_commit(bar_acc);
+          }
+          __syncwarp();
+        } else {
+          issue_stage<C, 3>(Cb, sm.w + (TAPS1 + TAPS2 + TAPS3) * G::W_TAP_BYTES, d_tmem, bar_acc, idesc, hi64);
+        }
       }
       static_assert(!UP || (G::W == 1 && WPS == 4), "the up tail is built for C = 64 (one sub-tile, thread = row)");
       const int low = t0 + 1 + row;                    // low-rate index of this thread's output row
@@ -540,14 +552,16 @@ __device__ __forceinline__ void slot_role(const TrunkArgs& a, const Smem& sm, ui
         tc_fence_after();
         if (elect_one()) {
           const uint32_t wdn = sm.w + (uint32_t)NTAPS * G::W_TAP_BYTES;
+          const int m_lo = p.dn_taps == 1 ? 2 : 0, m_hi = p.dn_taps == 1 ? 4 : G::DN_TAPS;   // k = s conv: middle row tap
 #pragma unroll
           for (int m = 0; m < G::DN_TAPS; m++) {
+            if (m < m_lo || m >= m_hi) continue;
             const int arow = (m >> 1) + ((m & 1) ? G::DN_ODD : 0);
             const uint32_t a_lo = (((Cb + (uint32_t)(arow * G::ROWB)) >> 4) & 0x3FFFu) | (1u << 16);
             const uint32_t b_lo = (((wdn + (uint32_t)m * G::DN_TAP_BYTES) >> 4) & 0x3FFFu) | (1u << 16);
 #pragma unroll
             for (int kk = 0; kk < G::K16; kk++)
-              umma_f16(d_tmem, hi64 | (a_lo + 2 * kk), hi64 | (b_lo + 2 * kk), a.idesc_dn, (m | kk) != 0 ? 1u : 0u);
+              umma_f16(d_tmem, hi64 | (a_lo + 2 * kk), hi64 | (b_lo + 2 * kk), a.idesc_dn, (m != m_lo || kk != 0) ? 1u : 0u);
           }
           umma_commit(bar_acc);
         }
@@ -865,6 +879,8 @@ extern "C" int ou_conv_trunk(const ou_trunk_params* p, void* stream) {
                                     !p->has_prelu_out2),
              "ou_conv_trunk: the fused down conv needs C = 32, no other tail, the block output buffer, an output of "
              "ceil(t / 2) steps and no output PReLU on the block");
+  OU_REQUIRE((p->up_taps == 0 || p->up_taps == 1 || p->up_taps == 3) && (p->dn_taps == 0 || p->dn_taps == 1 || p->dn_taps == 3),
+             "ou_conv_trunk: up_taps / dn_taps must be 1 or 3 (0 = 3)");
   OU_REQUIRE(p->batch > 0 && p->t > 0, "ou_conv_trunk: empty problem");
   OU_REQUIRE((p->gamma == nullptr) == (p->beta == nullptr), "ou_conv_trunk: gamma / beta must come together");
   if ((p->channels != 32 && p->channels != 64) || p->taps1 != ou::trunk::TAPS1 || p->taps2 != ou::trunk::TAPS2 ||

@@ -50,7 +50,7 @@ class TrunkParams(Structure):
         ("out_w", c_void_p), ("out_bias", c_float), ("out_coef", c_void_p), ("out_x", c_void_p),
         ("out_noise", c_void_p), ("out_xout", c_void_p), ("out_net", c_void_p),
         ("dn_w", c_void_p), ("dn_bias", c_void_p), ("dn_out", c_void_p), ("dn_t_out", c_int32),
-        ("dn_prelu_in", c_float),
+        ("dn_prelu_in", c_float), ("up_taps", c_int32), ("dn_taps", c_int32),
     ]
 
 

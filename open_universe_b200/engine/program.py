@@ -142,7 +142,8 @@ def fuse_up_tail(prog):
     c3 = tr.parts[2]
     fc = up.fc
     ok = (c3.fc.cin == 64 and up.src == c3.dst and c3.prelu_out is None and c3.prelu_out2 is None
-          and fc.cin == 64 and fc.n == 64 and fc.up == 2 and fc.s == 1 and fc.taps == 3 and fc.tap_off == -1
+          and fc.cin == 64 and fc.n == 64 and fc.up == 2 and fc.s == 1
+          and (fc.taps, fc.tap_off) in ((3, -1), (1, 0))      # anti-aliased (low-pass folded in) or plain k = s
           and fc.prelu_in is not None and up.add2 is None and up.film_off is None and up.prelu_out is None
           and up.prelu_out2 is None and up.dst_kind == "blocked" and up.t_in == c3.t_out
           and up.t_out <= 2 * up.t_in and up.rows <= up.t_in
@@ -171,7 +172,7 @@ def fuse_down_tail(prog):
             and tr.tail_dn is None):
         return False
     c3, fc = tr.parts[2], dn.fc
-    if not (fc.cin == 32 and fc.cout == 64 and fc.s == 2 and fc.up == 1 and fc.taps == 3 and fc.tap_off == -1
+    if not (fc.cin == 32 and fc.cout == 64 and fc.s == 2 and fc.up == 1 and (fc.taps, fc.tap_off) in ((3, -1), (1, 0))
             and dn.src == c3.dst and dn.add1 is None and dn.add2 is None and dn.film_off is None
             and dn.prelu_out is None and dn.prelu_out2 is None and dn.dst_kind == "blocked"
             and c3.prelu_out is None and c3.prelu_out2 is None and dn.t_in == c3.t_out
@@ -404,6 +405,41 @@ def lower_gru(prog, gru, pfx, src, t, *, add_last=None, scale_last=1.0):
     return h
 
 
+# OU_HOIST_PRELU=0 leaves the input PReLU of the decoder's up convs to the conv kernel's transform warps (A/B runs)
+HOIST_PRELU = _os.environ.get("OU_HOIST_PRELU", "1") != "0"
+
+
+def hoist_up_prelus(prog):
+    """The input PReLU of a transposed up conv (blocks.py:205-227) whose input tensor has no other reader moves
+    into the epilogue of the conv that produces that tensor (``prelu_out`` / ``prelu_out2``): the up conv then
+    needs no transform pass over its landed tiles, and its four transform warps join the epilogue -- the stage
+    that bounds these layers.  Producers inside a fused trunk are left alone (their up conv is the trunk's tail)."""
+    if not HOIST_PRELU:
+        return 0
+    flat = flat_ops(prog.ops)
+    in_trunk = {id(c) for op in prog.ops if isinstance(op, TrunkOp) for c in op.all_parts()}
+    n = 0
+    for up in flat:
+        if not (isinstance(up, ConvOp) and up.fc.up > 1 and up.fc.prelu_in is not None and id(up) not in in_trunk):
+            continue
+        readers = [o for o in flat if up.src in (getattr(o, "src", None), getattr(o, "add1", None),
+                                                 getattr(o, "add2", None), getattr(o, "add", None))]
+        prod = [o for o in flat if getattr(o, "dst", None) == up.src]
+        if len(readers) != 1 or len(prod) != 1 or up.src in getattr(prog, "outputs", {}).values():
+            continue
+        p = prod[0]
+        if not (isinstance(p, ConvOp) and id(p) not in in_trunk and p.dst_kind == "blocked" and p.prelu_out2 is None):
+            continue
+        if p.prelu_out is None:
+            p.prelu_out = up.fc.prelu_in
+        else:
+            p.prelu_out2 = up.fc.prelu_in
+        fc = up.fc
+        up.fc = FoldedConv(fc.w, fc.bias, fc.cin, fc.cout, fc.s, fc.up, fc.taps, fc.tap_off, None)
+        n += 1
+    return n
+
+
 # --------------------------------------------------------------------------------- score network
 def lower_score_network(net, batch, t):
     """ScoreNetwork.forward (score.py:277-297) for a (batch, 1, t) input.
@@ -466,6 +502,7 @@ def lower_score_network(net, batch, t):
     b_out = float(b_out[0].item()) if b_out is not None else 0.0
     prog.ops.append(OutputOp("output_conv", h, w_out, b_out, tl, t))
     fuse_out_tail(prog)
+    hoist_up_prelus(prog)
     prog.meta["lengths"] = lengths
     prog.meta["cond_channels"] = [b.n_channels for b in dec.up_modules]
     return prog
@@ -533,10 +570,10 @@ def lower_conditioner(net, batch, t, need_signal_tail=True):
                 None)
     if last is None or last.add2 is not None:
         raise RuntimeError("unexpected producer of the encoder output")
-    if any(isinstance(op, TrunkOp) and last in op.parts for op in prog.ops):
-        # the fused trunk kernel has no second residual input: run this block conv by conv
-        idx = next(i for i, op in enumerate(prog.ops) if isinstance(op, TrunkOp) and last in op.parts)
-        prog.ops[idx:idx + 1] = prog.ops[idx].parts
+    if any(isinstance(op, TrunkOp) and last in op.all_parts() for op in prog.ops):
+        # the fused trunk kernel (and its tails) has no second residual input: run this block conv by conv
+        idx = next(i for i, op in enumerate(prog.ops) if isinstance(op, TrunkOp) and last in op.all_parts())
+        prog.ops[idx:idx + 1] = prog.ops[idx].all_parts()
     if tl != frames:
         raise ValueError("encoder output length does not match the mel frame count")
     last.add2, last.scale2 = acc, 1.0 / math.sqrt(n_sum)

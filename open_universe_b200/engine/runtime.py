@@ -259,7 +259,8 @@ def trunk_params(op, bufs, batch, film=None, film_bstride=0, max_ctas=0, coef=No
     prm.scale1, prm.scale3 = c1.scale1, c3.scale1
     if op.tail is not None:
         up = op.tail
-        prm.up_w, prm.up_bias = up.packed["w_tc"].data_ptr(), up.packed["bias"].data_ptr()
+        prm.up_w, prm.up_bias = _tail_frame(up).data_ptr(), up.packed["bias"].data_ptr()
+        prm.up_taps = up.fc.taps
         prm.up_skip = bufs[up.add1].data_ptr() if up.add1 else None
         prm.up_out = bufs[up.dst].data_ptr()
         prm.up_t_out, prm.up_scale, prm.up_prelu_in = up.t_out, up.scale1, up.fc.prelu_in
@@ -268,7 +269,8 @@ def trunk_params(op, bufs, batch, film=None, film_bstride=0, max_ctas=0, coef=No
         if dn.packed["npad"] != dn.fc.cout:
             raise ValueError("down tail: padded output width")
         # w_tc of the 32 -> 64, s = 2, 3-tap conv is [3 taps][2 phases][64][32] = sample tap m = 2 q + r major
-        prm.dn_w, prm.dn_bias = dn.packed["w_tc"].data_ptr(), dn.packed["bias"].data_ptr()
+        prm.dn_w, prm.dn_bias = _tail_frame(dn).data_ptr(), dn.packed["bias"].data_ptr()
+        prm.dn_taps = dn.fc.taps
         prm.dn_out, prm.dn_t_out = bufs[dn.dst].data_ptr(), dn.t_out
         prm.dn_prelu_in = 1.0 if dn.fc.prelu_in is None else dn.fc.prelu_in
     if op.tail_out is not None:
@@ -277,6 +279,19 @@ def trunk_params(op, bufs, batch, film=None, film_bstride=0, max_ctas=0, coef=No
         prm.out_coef, prm.out_x = _ptr(coef), _ptr(bufs.get("x"))
         prm.out_noise, prm.out_xout, prm.out_net = _ptr(noise), _ptr(xout), _ptr(net_out)
     return prm
+
+
+def _tail_frame(conv):
+    """Tensor-core weight tiles of a trunk tail in the kernel's 3-row-tap frame: a plain k = s conv (1 tap) sits
+    in the middle tap, the outer taps are zero (and skipped by the kernel)."""
+    pk = conv.packed
+    if conv.fc.taps == 3:
+        return pk["w_tc"]
+    if "w_tc3" not in pk:
+        w = pk["w_tc"]
+        z = torch.zeros_like(w)
+        pk["w_tc3"] = torch.cat([z, w, z], dim=0).contiguous()
+    return pk["w_tc3"]
 
 
 def launch_trunk(op, bufs, batch, film=None, film_bstride=0, max_ctas=0, coef=None, noise=None, xout=None,

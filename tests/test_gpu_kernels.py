@@ -379,6 +379,8 @@ TAIL_CASES = [
     dict(t=122 * 3, B=2, sc=True, film=False, skip=False, t_up=122 * 6),  # exact multiple of the item, no skip
     dict(t=122 * 2 + 1, B=1, sc=True, film=True, skip=True, t_up=2 * (122 * 2 + 1)),
     dict(t=64080, B=3, sc=True, film=True, skip=True, t_up=128160),     # many items per CTA
+    dict(t=1000, B=2, sc=True, film=True, skip=True, t_up=2000, taps=1),       # plain k = s up conv (UNIVERSE original)
+    dict(t=122 * 2 + 1, B=1, sc=False, film=False, skip=True, t_up=2 * (122 * 2 + 1) - 1, taps=1),
 ]
 
 
@@ -403,7 +405,8 @@ def test_conv_trunk_with_up_tail_vs_emulator(c):
     P.add_conv(prog, "conv2", "c1", "c2", rand_fc(g, C, C, taps=3, tap_off=-1), t, prelu_out=0.3)
     P.add_conv(prog, "conv3", "c2", "v", rand_fc(g, C, C, taps=3, tap_off=-1), t, add1="in", scale1=0.7071)
     assert P.fuse_trunk(prog, "trunk")
-    P.add_conv(prog, "up", "v", "h", rand_fc(g, C, C // 2, up=2, taps=3, tap_off=-1, prelu_in=0.25), t, t_up,
+    taps = c.get("taps", 3)
+    P.add_conv(prog, "up", "v", "h", rand_fc(g, C, C // 2, up=2, taps=taps, tap_off=-(taps // 2), prelu_in=0.25), t, t_up,
                add1="skip" if c["skip"] else None, scale1=0.7071 if c["skip"] else 1.0)
     assert P.fuse_up_tail(prog) and len(prog.ops) == 1 and prog.ops[0].tail is not None
     film = torch.randn(B, 2 * C, generator=g) if c["film"] else None
@@ -514,6 +517,8 @@ DOWN_TAIL_CASES = [
     dict(t=248 * 3, B=2, film=False),         # exact multiple of the item
     dict(t=248 * 2 + 2, B=1, film=True),      # one row pair into a third item
     dict(t=128160, B=2, film=True),           # many items per CTA
+    dict(t=1000, B=2, film=True, taps=1),     # plain k = s down conv (UNIVERSE original)
+    dict(t=248 * 2 + 3, B=1, film=False, taps=1),
 ]
 
 
@@ -532,7 +537,8 @@ def test_conv_trunk_with_down_tail_vs_emulator(c):
     P.add_conv(prog, "conv2", "c1", "c2", rand_fc(g, C, C, taps=3, tap_off=-1), t, prelu_out=0.3)
     P.add_conv(prog, "conv3", "c2", "v", rand_fc(g, C, C, taps=3, tap_off=-1), t, add1="in", scale1=0.7071)
     assert P.fuse_trunk(prog, "trunk")
-    P.add_conv(prog, "down", "v", "h", rand_fc(g, C, 2 * C, s=2, taps=3, tap_off=-1, prelu_in=0.25), t)
+    taps = c.get("taps", 3)
+    P.add_conv(prog, "down", "v", "h", rand_fc(g, C, 2 * C, s=2, taps=taps, tap_off=-(taps // 2), prelu_in=0.25), t)
     assert P.fuse_down_tail(prog) and len(prog.ops) == 1 and prog.ops[0].tail_dn is not None
     film = torch.randn(B, 2 * C, generator=g) if c["film"] else None
     bufs, _, _ = E.run_program(prog, inputs, film=film, quant=True)
