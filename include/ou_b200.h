@@ -326,7 +326,8 @@ int ou_lsd(const float* input, const float* target, const float* window, float* 
 /* ------------------------------------------------------------------------------------------
  * Plan level: ONE call per network evaluation.
  *
- * A plan is a recorded list of the launches of ScoreNetwork.forward (score.py:277-297) for a fixed
+ * A plan is a recorded list of the launches of ScoreNetwork.forward (score.py:277-297) -- or of
+ * ConditionerNetwork.forward (condition.py:346-377): SURVEY 8b's ou_condition_forward -- for a fixed
  * (batch, length) with every weight / activation pointer resolved; the host lowers the network once
  * (engine/program.py), records the ops in launch order with ou_plan_add_*, and replays them with
  * ou_plan_run.  What changes from one evaluation to the next comes in ou_step_args: the signal, the
@@ -347,6 +348,7 @@ typedef struct ou_step_args {
   const float* noise;     /* fp32 (B, 1, T), or NULL                                               */
   float* xout;            /* fp32 (B, 1, T) updated signal (may alias x), or NULL                  */
   float* net_out;         /* fp32 (B, 1, T) raw network output, or NULL                            */
+  const float* x_wav;     /* conditioner plans: fp32 (B, 1, T) waveform of the mel front-end, NULL = x */
 } ou_step_args;
 
 int ou_plan_create(ou_plan** plan);
@@ -360,6 +362,11 @@ int ou_plan_add_output_sde(ou_plan* plan, const void* src, const float* w, float
                            int k, int t_src, int t_sig);
 int ou_plan_add_gru(ou_plan* plan, const float* gx, const float* w_hh, const float* b_hh, const void* add,
                     float scale, void* out, int batch, int t, int hidden);
+/* ConditionerNetwork.forward (condition.py:346-377) is recorded the same way; its STFT-mel front-end
+ * (condition.py:92-108) is one op = ou_mel_power + ou_mel_finalize on args->x_wav (or args->x). */
+int ou_plan_add_mel(ou_plan* plan, const float* window, const float* fb, const float* dft, float* power, float* mel,
+                    float* energy, void* mel_blocked, int batch, int t, int n_fft, int hop, int n_mels, int pad_left,
+                    int frames);
 int ou_plan_run(const ou_plan* plan, const ou_step_args* args, int first, int count, void* stream);
 
 #ifdef __cplusplus

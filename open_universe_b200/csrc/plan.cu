@@ -1,5 +1,5 @@
-// Plan-level C ABI (ou_plan_create / ou_score_step): a recorded list of the
-// launches of one network evaluation with every device pointer resolved, replayed by ONE call per
+// Plan-level C ABI (ou_plan_create / ou_condition_forward / ou_score_step): a recorded list of
+// the launches of one network evaluation (ScoreNetwork.forward, or ConditionerNetwork.forward with its mel front-end) with every device pointer resolved, replayed by ONE call per
 // evaluation.  The per-evaluation inputs (signal, FiLM row, EDM input scale, update coefficients, noise,
 // outputs) arrive in ou_step_args.  The host lowers the network once (fold weights, pack, plan buffers:
 // open_universe_b200/engine/program.py), records the plan, and from then on a step costs one foreign call
@@ -11,7 +11,7 @@
 
 namespace ou {
 
-enum PlanOpKind { OP_CONV, OP_TRUNK, OP_INPUT, OP_OUTPUT, OP_GRU };
+enum PlanOpKind { OP_CONV, OP_TRUNK, OP_INPUT, OP_OUTPUT, OP_GRU, OP_MEL };
 
 struct PlanOp {
   PlanOpKind kind;
@@ -24,6 +24,10 @@ struct PlanOp {
   void* out;
   float bias_s, scale;
   int32_t batch, t, c, k, t_out, hidden, use_in_scale;
+  // mel front-end (ou_mel_power + ou_mel_finalize): tables and scratch
+  const float *window, *fb, *dft;
+  float *power, *mel, *energy;
+  int32_t n_fft, hop, n_mels, pad_left, frames;
 };
 
 }  // namespace ou
@@ -95,6 +99,19 @@ extern "C" int ou_plan_add_gru(ou_plan* plan, const float* gx, const float* w_hh
   return OU_OK;
 }
 
+extern "C" int ou_plan_add_mel(ou_plan* plan, const float* window, const float* fb, const float* dft, float* power,
+                               float* mel, float* energy, void* mel_blocked, int batch, int t, int n_fft, int hop,
+                               int n_mels, int pad_left, int frames) {
+  OU_REQUIRE(plan && window && fb && dft && power && mel && energy && mel_blocked, "ou_plan_add_mel: null argument");
+  ou::PlanOp op{};
+  op.kind = ou::OP_MEL, op.film_off = -1;
+  op.window = window, op.fb = fb, op.dft = dft, op.power = power, op.mel = mel, op.energy = energy, op.out = mel_blocked;
+  op.batch = batch, op.t = t, op.n_fft = n_fft, op.hop = hop, op.n_mels = n_mels, op.pad_left = pad_left;
+  op.frames = frames;
+  plan->ops.push_back(op);
+  return OU_OK;
+}
+
 extern "C" int ou_plan_run(const ou_plan* plan, const ou_step_args* args, int first, int count, void* stream) {
   OU_REQUIRE(plan && args, "ou_plan_run: null argument");
   const int n = (int)plan->ops.size();
@@ -139,6 +156,15 @@ extern "C" int ou_plan_run(const ou_plan* plan, const ou_step_args* args, int fi
         rc = ou_output_sde(op.src, op.w, op.bias_s, args->coef, args->x, args->noise, args->xout, args->net_out,
                            op.batch, op.c, op.k, op.t, op.t_out, stream);
         break;
+      case ou::OP_MEL: {
+        const float* wav = args->x_wav ? args->x_wav : args->x;
+        OU_REQUIRE(wav != nullptr, "ou_plan_run: op %d needs the waveform (x_wav or x)", i);
+        rc = ou_mel_power(wav, op.window, op.fb, op.dft, op.power, op.mel, op.energy, op.batch, op.t, op.n_fft,
+                          op.hop, op.n_mels, op.pad_left, op.frames, stream);
+        if (rc == OU_OK)
+          rc = ou_mel_finalize(op.mel, op.energy, op.mel, op.out, op.batch, op.n_mels, op.frames, stream);
+        break;
+      }
       case ou::OP_GRU:
         rc = ou_gru_bidir((const float*)op.src, op.w, op.b_hh, op.add, op.scale, op.out, op.batch, op.t, op.hidden,
                           stream);

@@ -56,7 +56,8 @@ class TrunkParams(Structure):
 
 class StepArgs(Structure):
     _fields_ = [("x", c_void_p), ("film", c_void_p), ("film_bstride", c_int32), ("in_scale", c_void_p),
-                ("coef", c_void_p), ("noise", c_void_p), ("xout", c_void_p), ("net_out", c_void_p)]
+                ("coef", c_void_p), ("noise", c_void_p), ("xout", c_void_p), ("net_out", c_void_p),
+                ("x_wav", c_void_p)]
 
 
 # name -> (restype, argtypes); every symbol of include/ou_b200.h
@@ -106,6 +107,8 @@ SIGNATURES = {
                                        c_int]),
     "ou_plan_add_output_sde": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_int, c_int,
                                        c_int]),
+    "ou_plan_add_mel": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                c_int, c_int, c_int, c_int, c_int, c_int]),
     "ou_plan_add_gru": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int,
                                 c_int, c_int]),
     "ou_plan_run": (c_int, [c_void_p, POINTER(StepArgs), c_int, c_int, c_void_p]),

@@ -301,6 +301,44 @@ def launch_trunk(op, bufs, batch, film=None, film_bstride=0, max_ctas=0, coef=No
     lib.check(lib.load().ou_conv_trunk(byref(prm), _stream()))
 
 
+def record_plan(exe):
+    """``ou_plan`` (include/ou_b200.h, plan level) of an Executor's program: every op with its device pointers
+    resolved, replayed by ``ou_plan_run``.  Returns the handle (caller destroys it with ``ou_plan_destroy``)."""
+    L = lib.load()
+    bufs, B = exe.bufs, exe.batch
+    handle = c_void_p()
+    lib.check(L.ou_plan_create(byref(handle)))
+    for op in exe.prog.ops:
+        if isinstance(op, P.TrunkOp):
+            off = op.parts[0].film_off
+            prm = trunk_params(op, bufs, B, max_ctas=exe.max_ctas)
+            lib.check(L.ou_plan_add_trunk(handle, byref(prm), -1 if off is None else off))
+        elif isinstance(op, P.ConvOp):
+            prm = conv_params(op, bufs, B, max_ctas=exe.max_ctas)
+            lib.check(L.ou_plan_add_conv(handle, byref(prm), -1 if op.film_off is None else op.film_off))
+        elif isinstance(op, P.InputConvOp):
+            c, k = op.packed["w"].shape
+            lib.check(L.ou_plan_add_input_conv(handle, _ptr(op.packed["w"]), _ptr(op.packed["bias"]),
+                                               _ptr(bufs[op.dst]), B, op.t, c, k, 1 if op.use_in_scale else 0))
+        elif isinstance(op, P.OutputOp):
+            c, k = op.packed["w"].shape
+            lib.check(L.ou_plan_add_output_sde(handle, _ptr(bufs[op.src]), _ptr(op.packed["w"]), op.bias, B,
+                                               c, k, op.t, op.t_out))
+        elif isinstance(op, P.GruOp):
+            lib.check(L.ou_plan_add_gru(handle, _ptr(bufs[op.src]), _ptr(op.packed["w_hh"]),
+                                        _ptr(op.packed["b_hh"]), _ptr(bufs[op.add] if op.add else None),
+                                        op.scale, _ptr(bufs[op.dst]), B, op.t, op.hidden))
+        elif isinstance(op, P.MelOp):
+            pk = op.packed
+            lib.check(L.ou_plan_add_mel(handle, _ptr(pk["window"]), _ptr(pk["fb"]), _ptr(pk["dft"]), _ptr(pk["power"]),
+                                        _ptr(pk["mel"]), _ptr(pk["energy"]), _ptr(bufs[op.dst]), B, op.t, op.n_fft,
+                                        op.hop, op.n_mels, op.pad_left, op.frames))
+        else:
+            raise TypeError(op)
+    assert L.ou_plan_size(handle) == len(exe.prog.ops)
+    return handle
+
+
 class Executor:
     """A lowered program bound to device buffers."""
 
@@ -552,35 +590,7 @@ class ScoreRunner:
     def _build_plan(self):
         """Record the evaluation as an ``ou_plan`` (include/ou_b200.h, plan level): every op with its device
         pointers resolved, so that ``step`` is ONE foreign call instead of one per launch."""
-        L = lib.load()
-        exe, bufs, B = self.exe, self.exe.bufs, self.batch
-        handle = c_void_p()
-        lib.check(L.ou_plan_create(byref(handle)))
-        self._plan, self._plan_ctas = handle, exe.max_ctas
-        for op in exe.prog.ops:
-            off = -1
-            if isinstance(op, P.TrunkOp):
-                off = op.parts[0].film_off
-                prm = trunk_params(op, bufs, B, max_ctas=exe.max_ctas)
-                lib.check(L.ou_plan_add_trunk(handle, byref(prm), -1 if off is None else off))
-            elif isinstance(op, P.ConvOp):
-                prm = conv_params(op, bufs, B, max_ctas=exe.max_ctas)
-                lib.check(L.ou_plan_add_conv(handle, byref(prm), -1 if op.film_off is None else op.film_off))
-            elif isinstance(op, P.InputConvOp):
-                c, k = op.packed["w"].shape
-                lib.check(L.ou_plan_add_input_conv(handle, _ptr(op.packed["w"]), _ptr(op.packed["bias"]),
-                                                   _ptr(bufs[op.dst]), B, op.t, c, k, 1 if op.use_in_scale else 0))
-            elif isinstance(op, P.OutputOp):
-                c, k = op.packed["w"].shape
-                lib.check(L.ou_plan_add_output_sde(handle, _ptr(bufs[op.src]), _ptr(op.packed["w"]), op.bias, B,
-                                                   c, k, op.t, op.t_out))
-            elif isinstance(op, P.GruOp):
-                lib.check(L.ou_plan_add_gru(handle, _ptr(bufs[op.src]), _ptr(op.packed["w_hh"]),
-                                            _ptr(op.packed["b_hh"]), _ptr(bufs[op.add] if op.add else None),
-                                            op.scale, _ptr(bufs[op.dst]), B, op.t, op.hidden))
-            else:
-                raise TypeError(op)
-        assert L.ou_plan_size(handle) == len(exe.prog.ops)
+        self._plan, self._plan_ctas = record_plan(self.exe), self.exe.max_ctas
 
     def __del__(self):
         plan = self.__dict__.get("_plan")
@@ -844,13 +854,32 @@ class ConditionerRunner:
         self.n_cond = len([k for k in self.prog.outputs if k.startswith("cond")])
 
     def run(self, x, x_wav=None):
-        self.exe.bufs["x"] = x
-        self.exe.bufs["x_wav"] = x if x_wav is None else x_wav
-        self.exe.run()
+        """ConditionerNetwork.forward as ONE foreign call (``ou_plan_run`` over the recorded plan: SURVEY 8b's
+        ``ou_condition_forward``); op by op through the Executor when profiling or with OU_PLAN=0."""
+        if USE_PLAN and PROFILE is None and USE_TRUNK and not self.exe.naive:
+            if self.__dict__.get("_plan") is None:
+                self._plan = record_plan(self.exe)
+            args = lib.StepArgs()
+            args.x = x.data_ptr()
+            args.x_wav = None if x_wav is None else x_wav.data_ptr()
+            lib.check(lib.load().ou_plan_run(self._plan, byref(args), 0, -1, _stream()))
+        else:
+            self.exe.bufs["x"] = x
+            self.exe.bufs["x_wav"] = x if x_wav is None else x_wav
+            self.exe.run()
         out = self.prog.outputs
         cond = [self.exe.bufs[out[f"cond{i}"]] for i in range(self.n_cond)]
         y_hat = self.exe.bufs[out["y_hat"]] if "y_hat" in out else None
         return cond, y_hat, self.exe.bufs[out["h"]]
+
+
+    def __del__(self):
+        plan = self.__dict__.get("_plan")
+        if plan is not None:
+            try:
+                lib.load().ou_plan_destroy(plan)
+            except Exception:
+                pass
 
 
 def get_conditioner_runner(net, batch, t, device, need_signal_tail=True):

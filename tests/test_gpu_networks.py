@@ -309,3 +309,24 @@ def test_plan_replay_equals_per_launch_execution():
     assert r.__dict__.get("_plan") is not None and n_plan >= len(r.exe.prog.ops)
     (e0, ne), (g0, ng), (d0, nd) = r.phase_ranges()
     assert e0 == 0 and g0 == ne and d0 == ne + 1 and ne + ng + nd == len(r.exe.prog.ops)
+
+
+def test_conditioner_plan_replay_equals_per_launch_execution():
+    """ConditionerNetwork.forward (mel front-end included) through ONE ou_plan_run call == the same ops launched
+    one by one from Python, bit for bit (ou_condition_forward)."""
+    from open_universe_b200.engine import runtime as R
+    m = our_model("upp16k")
+    net = m.condition_model
+    B, T = 2, 4800
+    x = det_noise(1, (B, 1, T), 5)[0].to(DEV) * 0.1
+    cond_p, y_p, h_p = net(x, x_wav=x, train=True)
+    r = R.get_conditioner_runner(net, B, T, x.device, True)
+    assert r.__dict__.get("_plan") is not None
+    old = R.USE_PLAN
+    R.USE_PLAN = False
+    try:
+        cond_o, y_o, h_o = net(x, x_wav=x, train=True)
+    finally:
+        R.USE_PLAN = old
+    assert torch.equal(h_p, h_o) and torch.equal(y_p, y_o)
+    assert all(torch.equal(a, b) for a, b in zip(cond_p, cond_o))
