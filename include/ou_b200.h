@@ -20,7 +20,7 @@
  *   The element type of activations and packed conv weights is a build-time policy reported by
  *   ou_act_dtype(): IEEE fp16 by default (11-bit significand = the TF32 the reference's cuDNN path
  *   uses), act when built with -DOU_ACT_BF16.  "act" below means that type.
- * Signals are fp32 [B][T]; GRU pre-activations fp32 time-major [B][T][N].
+ * Signals are fp32 [B][T]; GRU pre-activations fp32 blocked [B][N/16][T][16].
  */
 #ifndef OU_B200_H
 #define OU_B200_H

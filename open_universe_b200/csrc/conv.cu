@@ -304,7 +304,7 @@ static int validate(const ou_conv_params* p, ConvArgs* a) {
   OU_REQUIRE(p->out_f32_blk == nullptr ||
                  (!p->add1 && !p->add2 && !p->gamma && !p->has_prelu_out && !p->has_prelu_out2 &&
                   p->up == 1),
-             "ou_conv1d: fp32 time-major output takes no epilogue");
+             "ou_conv1d: the blocked fp32 output takes no epilogue");
   OU_REQUIRE(p->out_f32_blk != nullptr || p->t_out > 0, "ou_conv1d: t_out");
   OU_REQUIRE((p->gamma == nullptr) == (p->beta == nullptr), "ou_conv1d: gamma/beta");
   a->p = *p;

@@ -16,7 +16,7 @@
 //                             (bias, FiLM gamma/beta, residual scales) is folded into three smem
 //                             coefficient vectors so a column costs  y = c0*(acc+add1) + c2*add2 + c1;
 //                             residual vectors are prefetched before the accumulator is ready;
-//                             16-byte bf16 stores in the blocked layout (or fp32 time-major)
+//                             32-byte stores in the blocked layout (16-bit, or fp32 [B][N/16][rows][16])
 // TMEM holds two accumulator buffers (2 x BN columns): the epilogue of tile i overlaps the MMAs of
 // tile i+1.
 //

@@ -59,20 +59,6 @@ struct TrunkArgs {
   uint32_t idesc_dn;    // down tail: N = 2C
 };
 
-__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n"
-      ".reg .pred P;\n"
-      "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n"
-      "selp.u32 %0, 1, 0, P;\n"
-      "}\n"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-
 // TAIL: 0 none; 1 the next block's x2 up conv (C = 64); 2 the network's output conv + EDM / SDE update (C = 32);
 // 3 the block's own stride-2 anti-aliased down conv (C = 32)
 template <int C, int S = 3, int TAIL = 0>
