@@ -214,6 +214,13 @@ int ou_output_sde(const void* src, const float* w, float bias, const float* coef
  *   h' = (1-z)*n + z*h; h0 = 0; backward direction runs t = T-1..0
  *   out blocked act (B, 2H, T) = ((h_fwd | h_bwd) + add) * scale   (add blocked or NULL)
  * ------------------------------------------------------------------------------------------ */
+/* ou_gru_bidir_ex: cluster_ctas = 0 / 8: clusters of 8 CTAs per (direction, 8 clips) -- lowest latency;
+ * 4: clusters of 4 (hidden <= 256; otherwise as 0): a step takes ~30 % longer but the recurrence holds half
+ * the SMs -- for hosts that overlap it with other kernels (engine/runtime.py: PipelinedScoreRunner).
+ * ou_gru_ctas: CTAs such a launch occupies (what to leave free when capping other grids with max_ctas). */
+int ou_gru_bidir_ex(const float* gx, const float* w_hh, const float* b_hh, const void* add, float scale,
+                    void* out, int batch, int t, int hidden, int cluster_ctas, void* stream);
+int ou_gru_ctas(int hidden, int batch, int cluster_ctas);
 int ou_gru_bidir(const float* gx, const float* w_hh, const float* b_hh, const void* add, float scale,
                  void* out, int batch, int t, int hidden, void* stream);
 
@@ -361,7 +368,7 @@ int ou_plan_add_input_conv(ou_plan* plan, const float* w, const float* bias, voi
 int ou_plan_add_output_sde(ou_plan* plan, const void* src, const float* w, float bias, int batch, int cin,
                            int k, int t_src, int t_sig);
 int ou_plan_add_gru(ou_plan* plan, const float* gx, const float* w_hh, const float* b_hh, const void* add,
-                    float scale, void* out, int batch, int t, int hidden);
+                    float scale, void* out, int batch, int t, int hidden, int cluster_ctas /* see ou_gru_bidir_ex */);
 /* ConditionerNetwork.forward (condition.py:346-377) is recorded the same way; its STFT-mel front-end
  * (condition.py:92-108) is one op = ou_mel_power + ou_mel_finalize on args->x_wav (or args->x). */
 int ou_plan_add_mel(ou_plan* plan, const float* window, const float* fb, const float* dft, float* power, float* mel,

@@ -319,7 +319,7 @@ struct G16 {
   static constexpr int XD = 4;
   static constexpr int XCLIP = 28;
   static constexpr int XSTAGE = 8 * XCLIP * 4 + 8 * 16;   // bytes: 1 024
-  static_assert(H % 64 == 0 && H % CS == 0 && HS % 8 == 0 && KS % 2 == 0 && CS >= 8 && CS <= 16, "bad GRU shape");
+  static_assert(H % 64 == 0 && H % CS == 0 && HS % 8 == 0 && KS % 2 == 0 && CS >= 4 && CS <= 16, "bad GRU shape");
 };
 
 // 1 / (1 + 2^x): ex2.approx.ftz + rcp.approx.ftz, ~2 ulp; the argument never leaves [-126, 126] in any
@@ -441,8 +441,10 @@ __global__ void __launch_bounds__(G16<H, CSZ>::NT) gru_cluster_f16_kernel(const 
     if (valid[e]) outp[e] = a.out + cl_off(clip, dir * H + hu, t_first, 2 * H, T, ocb);
   }
   // push target of this lane: CTA g; cells (octet, clip 2*t4) and (octet, clip 2*t4 + 1) of its h_buf[0]
-  const uint32_t dst_h = mapa_u32((uint32_t)__cvta_generic_to_shared(&h_buf[0][octet * 10 + 2 * t4]), (uint32_t)g);
-  const uint32_t dst_bar = mapa_u32(bar0, (uint32_t)g);
+  const bool push1 = CS >= 8 || g < CS;            // clusters of fewer than 8 CTAs: lanes g >= CS have no target
+  const uint32_t dst1 = push1 ? (uint32_t)g : 0u;
+  const uint32_t dst_h = mapa_u32((uint32_t)__cvta_generic_to_shared(&h_buf[0][octet * 10 + 2 * t4]), dst1);
+  const uint32_t dst_bar = mapa_u32(bar0, dst1);
   // clusters of more than 8 CTAs: lanes g < CS - 8 also feed CTA g + 8
   const bool push2 = CS > 8 && g + 8 < CS;
   const uint32_t dst2 = push2 ? (uint32_t)(g + 8) : (uint32_t)g;
@@ -584,7 +586,7 @@ __global__ void __launch_bounds__(G16<H, CSZ>::NT) gru_cluster_f16_kernel(const 
       uint32_t w[8];
 #pragma unroll
       for (int j = 0; j < 8; j++) w[j] = __shfl_sync(0xffffffffu, hq, t4 + 4 * j);
-      if (slot_ok) {
+      if (slot_ok && push1) {
         const uint32_t boff = (uint32_t)((cur ^ 1) * G::CELLS * 16);
         const uint4 lo4 = make_uint4(prmt(w[0], w[1], 0x5410), prmt(w[2], w[3], 0x5410),
                                      prmt(w[4], w[5], 0x5410), prmt(w[6], w[7], 0x5410));
@@ -675,10 +677,16 @@ static int launch_gru_f16_bg(const GruArgs& a, cudaStream_t st, int* max_cluster
 // but 1 055 us with 4 (longer exchange), and its 24 CTAs do not fit the SMs the pipelined sampler reserves
 // for the recurrence -- kept behind OU_GRU_CS=12 for A/B runs only.
 template <int H>
-static int launch_gru_f16(const GruArgs& a, cudaStream_t st) {
+static int launch_gru_f16(const GruArgs& a, cudaStream_t st, int cs_req) {
   static const int forced = [] { const char* e = getenv("OU_GRU_BG"); return e ? atoi(e) : 0; }();
   static const int forced_cs = [] { const char* e = getenv("OU_GRU_CS"); return e ? atoi(e) : 0; }();
   const bool use4 = forced == 4 || (forced == 0 && a.batch <= 4);
+  if constexpr (H <= 256) {
+    // cluster of 4 (two warps per scheduler: a step takes 1 589 instead of 1 214 cycles, but the recurrence holds
+    // half the SMs: 16 x 0.71 ms instead of 32 x 0.53 ms for 16 clips): for hosts that overlap the recurrence with
+    // other work and care about SM time, not latency (ou_gru_bidir_ex cluster_ctas = 4; OU_GRU_CS=4 / 8 forces)
+    if (forced_cs == 4 || (forced_cs == 0 && cs_req == 4)) return use4 ? launch_gru_f16_bg<H, 4, 4>(a, st, nullptr) : launch_gru_f16_bg<H, 8, 4>(a, st, nullptr);
+  }
   if constexpr (H == 384) {
     const int clusters = 2 * ceil_div(a.batch, use4 ? 4 : 8);
     if (forced_cs == 12 && clusters <= 6) {
@@ -707,18 +715,31 @@ static int gru_impl() {
 
 }  // namespace ou
 
+extern "C" int ou_gru_ctas(int hidden, int batch, int cluster_ctas) {
+  const int cs = (cluster_ctas == 4 && hidden <= 256) ? 4 : 8;
+  const int bg = batch <= 4 ? 4 : 8;
+  return 2 * ((batch + bg - 1) / bg) * cs;
+}
+
 extern "C" int ou_gru_bidir(const float* gx, const float* w_hh, const float* b_hh, const void* add,
                             float scale, void* out, int batch, int t, int hidden, void* stream) {
+  return ou_gru_bidir_ex(gx, w_hh, b_hh, add, scale, out, batch, t, hidden, 0, stream);
+}
+
+extern "C" int ou_gru_bidir_ex(const float* gx, const float* w_hh, const float* b_hh, const void* add,
+                               float scale, void* out, int batch, int t, int hidden, int cluster_ctas,
+                               void* stream) {
   OU_REQUIRE(gx && w_hh && b_hh && out, "ou_gru_bidir: null pointer");
   OU_REQUIRE(batch > 0 && t > 0, "ou_gru_bidir: empty problem");
+  OU_REQUIRE(cluster_ctas == 0 || cluster_ctas == 4 || cluster_ctas == 8, "ou_gru_bidir_ex: cluster_ctas must be 0, 4 or 8");
   ou::GruArgs a{ou::tc::g_trace, gx, w_hh, b_hh, (const act_t*)add, (act_t*)out, scale, batch, t};
   cudaStream_t st = (cudaStream_t)stream;
   const int impl = ou::gru_impl();
   switch (hidden) {
-    case 128: return impl == 2 ? ou::launch_gru_f16<128>(a, st) : ou::launch_gru<128, 4>(a, st);
+    case 128: return impl == 2 ? ou::launch_gru_f16<128>(a, st, cluster_ctas) : ou::launch_gru<128, 4>(a, st);
     case 256:
-      return impl == 2 ? ou::launch_gru_f16<256>(a, st) : ou::launch_gru<256, 8>(a, st);
-    case 384: return impl == 2 ? ou::launch_gru_f16<384>(a, st) : ou::launch_gru<384, 16>(a, st);
+      return impl == 2 ? ou::launch_gru_f16<256>(a, st, cluster_ctas) : ou::launch_gru<256, 8>(a, st);
+    case 384: return impl == 2 ? ou::launch_gru_f16<384>(a, st, cluster_ctas) : ou::launch_gru<384, 16>(a, st);
     default:
       ou::set_error("ou_gru_bidir: hidden size %d has no kernel (128, 256, 384)", hidden);
       return OU_ERR_UNSUPPORTED;

@@ -90,11 +90,12 @@ extern "C" int ou_plan_add_output_sde(ou_plan* plan, const void* src, const floa
 }
 
 extern "C" int ou_plan_add_gru(ou_plan* plan, const float* gx, const float* w_hh, const float* b_hh,
-                               const void* add, float scale, void* out, int batch, int t, int hidden) {
+                               const void* add, float scale, void* out, int batch, int t, int hidden,
+                               int cluster_ctas) {
   OU_REQUIRE(plan && gx && w_hh && b_hh && out, "ou_plan_add_gru: null argument");
   ou::PlanOp op{};
   op.kind = ou::OP_GRU, op.film_off = -1, op.src = gx, op.w = w_hh, op.b_hh = b_hh, op.add = add;
-  op.scale = scale, op.out = out, op.batch = batch, op.t = t, op.hidden = hidden;
+  op.scale = scale, op.out = out, op.batch = batch, op.t = t, op.hidden = hidden, op.k = cluster_ctas;
   plan->ops.push_back(op);
   return OU_OK;
 }
@@ -166,8 +167,8 @@ extern "C" int ou_plan_run(const ou_plan* plan, const ou_step_args* args, int fi
         break;
       }
       case ou::OP_GRU:
-        rc = ou_gru_bidir((const float*)op.src, op.w, op.b_hh, op.add, op.scale, op.out, op.batch, op.t, op.hidden,
-                          stream);
+        rc = ou_gru_bidir_ex((const float*)op.src, op.w, op.b_hh, op.add, op.scale, op.out, op.batch, op.t,
+                             op.hidden, op.k, stream);
         break;
     }
     if (rc != OU_OK) return rc;

@@ -76,6 +76,9 @@ SIGNATURES = {
                               c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "ou_gru_bidir": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int,
                              c_int, c_int, c_void_p]),
+    "ou_gru_bidir_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int,
+                                c_int, c_int, c_int, c_void_p]),
+    "ou_gru_ctas": (c_int, [c_int, c_int, c_int]),
     "ou_mel_power": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                              c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "ou_mel_finalize": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
@@ -110,7 +113,7 @@ SIGNATURES = {
     "ou_plan_add_mel": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                 c_int, c_int, c_int, c_int, c_int, c_int]),
     "ou_plan_add_gru": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int,
-                                c_int, c_int]),
+                                c_int, c_int, c_int]),
     "ou_plan_run": (c_int, [c_void_p, POINTER(StepArgs), c_int, c_int, c_void_p]),
     "ou_debug_set_trace": (c_int, [c_void_p]),
 }

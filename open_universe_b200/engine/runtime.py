@@ -327,7 +327,7 @@ def record_plan(exe):
         elif isinstance(op, P.GruOp):
             lib.check(L.ou_plan_add_gru(handle, _ptr(bufs[op.src]), _ptr(op.packed["w_hh"]),
                                         _ptr(op.packed["b_hh"]), _ptr(bufs[op.add] if op.add else None),
-                                        op.scale, _ptr(bufs[op.dst]), B, op.t, op.hidden))
+                                        op.scale, _ptr(bufs[op.dst]), B, op.t, op.hidden, exe.gru_cluster))
         elif isinstance(op, P.MelOp):
             pk = op.packed
             lib.check(L.ou_plan_add_mel(handle, _ptr(pk["window"]), _ptr(pk["fb"]), _ptr(pk["dft"]), _ptr(pk["power"]),
@@ -350,6 +350,7 @@ class Executor:
         self.bufs = alloc_buffers(prog, device, skip=external)
         self.naive = False   # tests: route ConvOps through the fp32 CUDA-core reference kernel
         self.max_ctas = 0    # cap on the persistent conv grids (0 = all SMs), see PipelinedScoreRunner
+        self.gru_cluster = 0  # CTAs per GRU cluster (0 = lowest latency; 4 = half the SMs), see PipelinedScoreRunner
 
     def run(self, film=None, film_bstride=0, in_scale=None, coef=None, noise=None, xout=None,
             net_out=None, ops=None):
@@ -383,10 +384,10 @@ class Executor:
                                           _ptr(coef), _ptr(bufs["x"]), _ptr(noise), _ptr(xout),
                                           _ptr(net_out), B, c, k, op.t, op.t_out, _stream()))
             elif isinstance(op, P.GruOp):
-                lib.check(L.ou_gru_bidir(_ptr(bufs[op.src]), _ptr(op.packed["w_hh"]),
-                                         _ptr(op.packed["b_hh"]),
-                                         _ptr(bufs[op.add] if op.add else None), op.scale,
-                                         _ptr(bufs[op.dst]), B, op.t, op.hidden, _stream()))
+                lib.check(L.ou_gru_bidir_ex(_ptr(bufs[op.src]), _ptr(op.packed["w_hh"]),
+                                            _ptr(op.packed["b_hh"]),
+                                            _ptr(bufs[op.add] if op.add else None), op.scale,
+                                            _ptr(bufs[op.dst]), B, op.t, op.hidden, self.gru_cluster, _stream()))
             elif isinstance(op, P.MelOp):
                 pk = op.packed
                 lib.check(L.ou_mel_power(_ptr(bufs[op.src]), _ptr(pk["window"]), _ptr(pk["fb"]),
@@ -674,8 +675,13 @@ class PipelinedScoreRunner:
         self.film_cols = self.halves[0].film_cols
         self.film = None
         n_sms = torch.cuda.get_device_properties(device).multi_processor_count
+        # The overlapped recurrence is never on the critical path here: clusters of 4 CTAs (a step takes ~30 % longer,
+        # half the SMs: measured 1 000 -> 1 025 audio-s/s at cfg-2) leave more SMs to the other half's convolutions
+        hidden = [op.hidden for op in self.halves[0].prog.ops if isinstance(op, P.GruOp)]
+        cluster = int(os.environ.get("OU_PIPE_GRU_CLUSTER", "4"))
         for h, other in ((0, 1), (1, 0)):
-            gru_ctas = 2 * 8 * -(-self.halves[other].batch // 8)      # clusters of 8 CTAs per (direction, 8 clips)
+            self.halves[h].exe.gru_cluster = cluster
+            gru_ctas = lib.load().ou_gru_ctas(hidden[0] if hidden else 256, self.halves[other].batch, cluster)
             self.halves[h].exe.max_ctas = max(n_sms - gru_ctas, n_sms // 2)
             if os.environ.get("OU_PIPE_CAP"):        # A/B knob: explicit cap (0 = none)
                 self.halves[h].exe.max_ctas = int(os.environ["OU_PIPE_CAP"])

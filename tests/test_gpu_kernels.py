@@ -208,6 +208,13 @@ def test_gru_vs_explicit(hidden, B, T, add):
     torch.cuda.synchronize()
     got = R.unpack_blocked(out).cpu()
     assert rel_rms(got, want) < 3e-3   # bf16 output rounding only
+    # clusters of 4 CTAs (the SM-saving form the pipelined sampler asks for): same arithmetic, same bits
+    out4 = R.alloc_blocked(B, 2 * H, T, DEV)
+    assert lib.load().ou_gru_ctas(H, B, 4) == 2 * -(-B // (4 if B <= 4 else 8)) * (4 if H <= 256 else 8)
+    lib.check(lib.load().ou_gru_bidir_ex(R._ptr(d_gx), R._ptr(d_w), R._ptr(d_b), R._ptr(d_add), 0.7071,
+                                         R._ptr(out4), B, T, H, 4, R._stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(out4, out)
 
 
 @pytest.mark.parametrize("fs_cfg", [dict(n_fft=640, hop=160, n_mels=80), dict(n_fft=960, hop=240, n_mels=128)])
