@@ -270,3 +270,47 @@ def test_plan_abi_records_ops_without_a_gpu():
     assert "out of range" in lib.last_error()
     assert L.ou_plan_run(plan, byref(args), 2, -1, None) == 0           # empty range: nothing launched
     assert L.ou_plan_destroy(plan) == 0
+
+
+def test_gru_cta_count_and_plan_ops_for_the_conditioner():
+    """Host-only parts of the round-2 ABI additions: ou_gru_ctas (what a host leaves free next to the overlapped
+    recurrence) and the mel / GRU plan ops with their new arguments."""
+    from ctypes import byref, c_void_p
+    from open_universe_b200.engine import lib
+    L = lib.load()
+    # clusters of 8 CTAs per (direction, 8 clips); 4 clip slots when the batch fits; clusters of 4 only for H <= 256
+    assert L.ou_gru_ctas(256, 32, 0) == 2 * 4 * 8 and L.ou_gru_ctas(256, 16, 4) == 2 * 2 * 4
+    assert L.ou_gru_ctas(256, 3, 8) == 2 * 1 * 8 and L.ou_gru_ctas(384, 4, 4) == 2 * 1 * 8
+    assert L.ou_gru_bidir_ex(None, None, None, None, 1.0, None, 1, 1, 256, 4, None) < 0     # null pointers are refused
+    plan = c_void_p()
+    assert L.ou_plan_create(byref(plan)) == 0
+    one = c_void_p(16)      # any non-null pointer: recording does not dereference
+    assert L.ou_plan_add_mel(plan, one, one, one, one, one, one, one, 2, 4800, 640, 160, 80, 240, 31) == 0
+    assert L.ou_plan_add_gru(plan, one, one, one, None, 1.0, one, 2, 30, 256, 4) == 0
+    assert L.ou_plan_add_mel(plan, None, one, one, one, one, one, one, 2, 4800, 640, 160, 80, 240, 31) < 0
+    assert L.ou_plan_size(plan) == 2
+    assert L.ou_plan_destroy(plan) == 0
+
+
+def test_lowering_fuses_the_tails_and_hoists_the_up_prelus():
+    """UNIVERSE++ 16 kHz: one evaluation is 31 launches -- enc.0.down, dec.4.up and the output conv ride on trunk
+    launches, and the decoder's remaining up convs have no input PReLU of their own (engine/program.py)."""
+    import torch
+    from open_universe_b200.config import builtin_config, instantiate
+    from open_universe_b200.engine import program as P
+    torch.manual_seed(0)
+    m = instantiate(builtin_config("universepp_16k").model, _recursive_=False)
+    prog = P.lower_score_network(m.get_score_model(), 2, 16000)
+    trunks = {op.name: op for op in prog.ops if isinstance(op, P.TrunkOp)}
+    assert len(prog.ops) == 31 and set(trunks) == {"enc.0.trunk", "enc.1.trunk", "dec.3.trunk", "dec.4.trunk"}
+    assert trunks["enc.0.trunk"].tail_dn is not None and trunks["enc.0.trunk"].tail_dn.fc.taps == 3
+    assert trunks["dec.3.trunk"].tail is not None and trunks["dec.4.trunk"].tail_out is not None
+    ups = [op for op in prog.ops if isinstance(op, P.ConvOp) and op.fc.up > 1]
+    assert [u.name for u in ups] == ["dec.1.up", "dec.2.up", "dec.3.up"] and all(u.fc.prelu_in is None for u in ups)
+    by_name = {op.name: op for op in P.flat_ops(prog.ops)}
+    assert all(by_name[n].prelu_out is not None for n in ("dec.0.conv3", "dec.1.conv3", "dec.2.conv3"))
+    # UNIVERSE (original): plain k = s rate convs take the same tails through their 1-tap form
+    m = instantiate(builtin_config("universe_original_16k").model, _recursive_=False)
+    prog = P.lower_score_network(m.get_score_model(), 2, 16000)
+    trunks = {op.name: op for op in prog.ops if isinstance(op, P.TrunkOp)}
+    assert trunks["enc.0.trunk"].tail_dn.fc.taps == 1 and trunks["dec.3.trunk"].tail.fc.taps == 1
