@@ -20,7 +20,7 @@ __device__ __forceinline__ void commit(uint32_t bar) {
 }
 
 __global__ void __launch_bounds__(128, 1) bench(int n, int iters, int commit_every, int layout, int k_steps,
-                                                int n_acc, long long* out) {
+                                                int n_acc, long long* out, int m = 128) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t bar, bar_dummy;
@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(128, 1) bench(int n, int iters, int commit_eve
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = tslot;
   if (threadIdx.x == 0) {
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | (8u << 24);
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
     // layout 0: no-swizzle K-major (LBO = 2112 B like a 132-row tile, SBO = 128); 2: 128B swizzle (SBO = 1024)
     uint64_t hi;
     uint32_t lbo;
@@ -82,17 +82,20 @@ int main(int argc, char** argv) {
   cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   const int iters = 512;
   printf("grid=%d iters=%d  (cycles per MMA: issue-only / issue+complete)\n", grid, iters);
-  for (int layout : {0, 2}) {
-    for (int n : {32, 64, 128, 256}) {
-      for (int n_acc : {1, 2, 4}) {
-        if (n_acc * n > 512) continue;
-        for (int w = 0; w < 2; w++) {
-          bench<<<grid, 128, 100 * 1024>>>(n, iters, n_acc == 4 ? 512 : 4, layout, 4, n_acc, out);
-          cudaError_t e = cudaDeviceSynchronize();
-          if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
+  for (int m : {128, 64}) {
+    for (int layout : {0, 2}) {
+      if (m == 64 && layout == 0) continue;
+      for (int n : {32, 64, 128, 256}) {
+        for (int n_acc : {1, 2, 4}) {
+          if (n_acc * n > 512 || (m == 64 && n_acc != 2)) continue;
+          for (int w = 0; w < 2; w++) {
+            bench<<<grid, 128, 100 * 1024>>>(n, iters, n_acc == 4 ? 512 : 4, layout, 4, n_acc, out, m);
+            cudaError_t e = cudaDeviceSynchronize();
+            if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
+          }
+          printf("M=%3d layout=%d N=%3d accumulators=%d : issue %7.1f  complete %7.1f  (math floor %d)\n", m, layout, n, n_acc,
+                 (double)out[0] / iters, (double)out[1] / iters, m * n / 256);
         }
-        printf("layout=%d N=%3d accumulators=%d : issue %7.1f  complete %7.1f  (floor %d)\n", layout, n, n_acc,
-               (double)out[0] / iters, (double)out[1] / iters, 128 * n / 256);
       }
     }
   }
